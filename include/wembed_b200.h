@@ -1,0 +1,165 @@
+/*
+ * wembed_b200.h - C ABI of the B200-native WEmbed gradient-descent step.
+ *
+ * This is the drop-in boundary of the project: plain pointers and sizes, no C++ or
+ * torch types.  One handle owns one device-resident embedding problem (CSR graph,
+ * positions, weights, Adam moments, spatial index) on one GPU and is driven by one
+ * host thread.  The reference has no C ABI of its own for this path (its only FFI
+ * precedent is the four sprk_* functions bound in
+ * src/embeddingLib/src/spacialQuery/SprkQueries.cpp:22,27,59,64); each entry point
+ * below names the reference C++ interface it replaces.  Paths are relative to the
+ * reference checkout (Vraier/wembed).
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative wb_status on failure;
+ *     wb_last_error() returns a human readable message for the calling thread.
+ *   - all host buffers are caller owned and only read / written during the call.
+ *   - coordinates cross the boundary as row-major n x d doubles, exactly as
+ *     EmbedderInterface::copyCoordinatesTo does (EmbedderInterface.hpp:94-96).
+ *   - there is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef WEMBED_B200_H
+#define WEMBED_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WB_ABI_VERSION 1
+
+typedef struct wb_embedder wb_embedder; /* opaque */
+
+enum wb_status {
+    WB_OK = 0,
+    WB_ERR_INVALID = -1,  /* bad argument */
+    WB_ERR_CUDA = -2,     /* CUDA runtime error, see wb_last_error */
+    WB_ERR_NO_DEVICE = -3,
+    WB_ERR_UNSUPPORTED = -4
+};
+
+enum wb_optimizer { WB_OPT_SIMPLE = 0, WB_OPT_ADAM = 1 };    /* EmbedderOptions.hpp:6  */
+enum wb_precision { WB_PREC_F32 = 0, WB_PREC_F64 = 1 };      /* device state type      */
+
+/*
+ * The force / optimizer knobs of EmbedderOptions (EmbedderOptions.hpp:31-88) that the
+ * device step reads.  Scheduling and stopping knobs stay on the host (they are scalar
+ * logic layered over wb_step by the C++ facade, see wembed_b200/host).
+ */
+typedef struct wb_options {
+    int32_t embedding_dimension;   /* EmbedderOptions::embeddingDimension, 1..32            */
+    int32_t optimizer;             /* wb_optimizer; Adam: beta1=.9 beta2=.999 eps=1e-8      */
+                                   /*   (WembedEmbedder.hpp:46)                             */
+    int32_t precision;             /* wb_precision of device state; F32 is the product path */
+    int32_t device;                /* CUDA device ordinal                                   */
+    double attraction_scale;       /* EmbedderOptions::attractionScale                      */
+    double repulsion_scale;        /* EmbedderOptions::repulsionScale                       */
+    double centre_scale;           /* EmbedderOptions::centreScale (0 = off)                */
+    double edge_length;            /* EmbedderOptions::edgeLength                           */
+    double doubling_factor;        /* EmbedderOptions::doublingFactor (weight classes)      */
+    double simple_max_displacement;/* EmbedderOptions::simpleOptMaxDisplacement             */
+    uint32_t seed;                 /* base seed of the coincident-pair tie-break generator  */
+                                   /*   (Rand::localGenerator, Rand.cpp:29-35)              */
+    int32_t reserved[7];
+} wb_options;
+
+/*
+ * Per-step observables, the values WembedEmbedder::calculateStep leaves in
+ * EmbedderState (EmbedderState.hpp:30-35) plus the sums they are made of.
+ */
+typedef struct wb_step_stats {
+    double loss_attract;       /* state.lastAttractLoss (WembedEmbedder.cpp:270-271) */
+    double loss_repel;         /* state.lastRepelLoss   (WembedEmbedder.cpp:292-293) */
+    double sum_displacement;   /* sum_v ||x_v - xprev_v||   (WembedEmbedder.cpp:330-343) */
+    double sum_radius_sq;      /* sum_v ||x_v||^2, after recentring (:334-345)       */
+    double rel_displacement;   /* state.lastRelDisplacement (:347-350)               */
+    double num_repulsion_pairs;/* pairs that passed the neighbour filter and the     */
+                               /*   exact weighted-distance test                      */
+    double num_candidates;     /* distance evaluations done by the repulsion walk    */
+    double centroid[32];       /* per-dimension mean removed by applyGravityCentre   */
+    int64_t iteration;         /* state.currentIteration after the step              */
+} wb_step_stats;
+
+/* -- life cycle ----------------------------------------------------------------- */
+
+/* ABI / build information.  No device needed. */
+int wb_abi_version(void);
+const char* wb_build_info(void);
+const char* wb_last_error(void);
+/* Number of visible CUDA devices (0 when there is none).  No device needed. */
+int wb_device_count(void);
+
+/*
+ * Replaces the WembedEmbedder constructor (WembedEmbedder.hpp:90-125) minus the random
+ * initial layout: uploads the CSR (row_ptr[n+1], col[row_ptr[n]], neighbours sorted
+ * ascending, no self loops, symmetric - the invariants of Graph, Graph.cpp:87-150),
+ * allocates positions / weights / force / Adam moments.  Positions start at 0 and
+ * weights at 1 until wb_set_coordinates / wb_set_weights are called.
+ */
+int wb_create(wb_embedder** out, int32_t n, const int32_t* row_ptr, const int32_t* col, const wb_options* opts);
+int wb_destroy(wb_embedder* h);
+
+/* -- state ---------------------------------------------------------------------- */
+
+/* WembedEmbedder::setCoordinates (WembedEmbedder.cpp:104-119): n x d row-major doubles. */
+int wb_set_coordinates(wb_embedder* h, const double* coords);
+/* WembedEmbedder::setWeights (WembedEmbedder.cpp:121-131): n doubles, all > 0;
+ * recomputes invExpWeights[v] = 1 / w^(1/d) in double and the weight classes
+ * (WeightedIndex::getDoublingWeightBuckets, WeightedIndex.cpp:51-63). */
+int wb_set_weights(wb_embedder* h, const double* weights);
+/* EmbedderInterface::copyCoordinatesTo (EmbedderInterface.hpp:94-96). */
+int wb_get_coordinates(wb_embedder* h, double* coords);
+/* WembedEmbedder::getWeights (WembedEmbedder.cpp:96-98). */
+int wb_get_weights(wb_embedder* h, double* weights);
+/* state.force of the most recent step (EmbedderState.hpp:26), n x d doubles.  Test hook. */
+int wb_get_forces(wb_embedder* h, double* forces);
+/* AdamOptimizer::reset (AdamOptimizer.cpp:32-36) and state.currentIteration = 0. */
+int wb_reset_optimizer(wb_embedder* h);
+int wb_set_iteration(wb_embedder* h, int64_t iteration);
+
+/* -- the hot path ----------------------------------------------------------------- */
+
+/*
+ * One WembedEmbedder::calculateStep (WembedEmbedder.cpp:13-63) with the learning rate
+ * the host-side LRScheduler produced for this iteration: index rebuild, attractive and
+ * repulsive forces, optional centre force, optimizer update, recentring and the
+ * displacement / loss sums.  Blocks until `stats` is valid.
+ */
+int wb_step(wb_embedder* h, double learning_rate, wb_step_stats* stats);
+
+/*
+ * Asynchronous variant: enqueues the step on the handle's stream and returns.
+ * The k-th call's observables are fetched (in order) with wb_step_collect.
+ * At most WB_MAX_INFLIGHT steps may be outstanding.
+ */
+#define WB_MAX_INFLIGHT 64
+int wb_step_async(wb_embedder* h, double learning_rate);
+int wb_step_collect(wb_embedder* h, wb_step_stats* stats);
+int wb_synchronize(wb_embedder* h);
+
+/* -- test hooks for the spatial index ------------------------------------------------ */
+
+/*
+ * Rebuilds the device index from the current positions and evaluates, for each of the
+ * `nq` query vertices, the reference's candidate set
+ *   U_c { u in class c : ||x_u - x_v|| <= edgeLength * (w_v * maxW_c)^(1/d) }
+ * (WeightedIndex::getNodesWithinWeightedDistance, WeightedIndex.cpp:65-81; includes v
+ * itself and graph neighbours, as the reference's does).  Distances are evaluated in
+ * double.  Results are written as a CSR: out_offsets[nq+1], out_ids[cap] sorted
+ * ascending per query.  Returns WB_ERR_INVALID if cap is too small (out_offsets[nq]
+ * then holds the required size).
+ */
+int wb_query_candidates(wb_embedder* h, int32_t nq, const int32_t* queries, int64_t* out_offsets,
+                        int32_t* out_ids, int64_t cap);
+
+/* Device time (ms, CUDA events) of each phase of the most recent wb_step:
+ * [0] index  [1] attract  [2] repel  [3] optimizer  [4] recentre+observe  [5] total.
+ * Mirrors the util::Timer keys of WembedEmbedder.cpp:28-58. Requires wb_enable_timing(h,1). */
+int wb_enable_timing(wb_embedder* h, int enable);
+int wb_get_phase_times(wb_embedder* h, double* ms6);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WEMBED_B200_H */
