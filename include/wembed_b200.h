@@ -53,6 +53,8 @@ typedef struct wb_options {
                                    /*   (WembedEmbedder.hpp:46)                             */
     int32_t precision;             /* wb_precision of device state; F32 is the product path */
     int32_t device;                /* CUDA device ordinal                                   */
+    int32_t keep_forces;           /* 1: keep state.force of every step for wb_get_forces   */
+    int32_t reserved0;
     double attraction_scale;       /* EmbedderOptions::attractionScale                      */
     double repulsion_scale;        /* EmbedderOptions::repulsionScale                       */
     double centre_scale;           /* EmbedderOptions::centreScale (0 = off)                */
@@ -61,7 +63,7 @@ typedef struct wb_options {
     double simple_max_displacement;/* EmbedderOptions::simpleOptMaxDisplacement             */
     uint32_t seed;                 /* base seed of the coincident-pair tie-break generator  */
                                    /*   (Rand::localGenerator, Rand.cpp:29-35)              */
-    int32_t reserved[7];
+    uint32_t reserved1[7];
 } wb_options;
 
 /*
@@ -89,6 +91,8 @@ const char* wb_build_info(void);
 const char* wb_last_error(void);
 /* Number of visible CUDA devices (0 when there is none).  No device needed. */
 int wb_device_count(void);
+/* Fills `o` with the defaults of EmbedderOptions (EmbedderOptions.hpp:31-88).  No device needed. */
+void wb_options_default(wb_options* o);
 
 /*
  * Replaces the WembedEmbedder constructor (WembedEmbedder.hpp:90-125) minus the random

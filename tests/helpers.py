@@ -1,0 +1,61 @@
+"""Shared helpers of the parity tests."""
+from __future__ import annotations
+
+import numpy as np
+
+from wembed_b200.datasets import degree_weights, geometric_graph, initial_coordinates
+
+
+def ring_graph(n=64):
+    """The graph of the reference's tests/TestDeterminism.cpp:15-22: a ring with +1 and +7 chords."""
+    e = []
+    for v in range(n):
+        e.append((v, (v + 1) % n))
+        e.append((v, (v + 7) % n))
+    return np.asarray(e, np.int32)
+
+
+SMALL_GRAPH = np.asarray([(0, 1), (1, 2), (2, 3), (3, 4), (1, 3), (2, 4)], np.int32)  # assets/small_graph.edg
+
+
+def lr_exponential(iteration, lr0=10.0, cooling=0.995, warmup=20):
+    """LRScheduler::learningRate with ExponentialCoolingSchedule (LRScheduler.cpp:7-17)."""
+    lr = lr0 * cooling ** float(iteration)
+    return lr * iteration / warmup if iteration < warmup else lr
+
+
+def near_threshold_vertices(x, w, row_ptr, col, L=1.0, tau=1e-5, max_pairs=50_000_000):
+    """Vertices owning a pair whose weighted distance dist*ws lies within tau*L of the hinge at L.
+
+    fp32 and fp64 may legitimately disagree on which side of the discontinuity such a pair falls
+    ("hinge discontinuity"); parity tests mask these vertices and report their count.
+    """
+    from scipy.spatial import cKDTree
+    n, d = x.shape
+    iw = w ** (-1.0 / d)
+    src = np.repeat(np.arange(n), np.diff(row_ptr))
+    dist = np.sqrt(((x[src] - x[col]) ** 2).sum(1))
+    near = np.abs(dist * iw[src] * iw[col] - L) <= tau * L
+    flagged = np.zeros(n, bool)
+    flagged[src[near]] = True
+    rmax = L * (w.max() ** 2) ** (1.0 / d) * (1 + 2 * tau)
+    tree = cKDTree(x)
+    # only a thin shell can be near the threshold, but the shell radius depends on the pair: take all pairs
+    # within rmax (bounded) and test them exactly
+    pairs = tree.query_pairs(rmax, output_type="ndarray")
+    if len(pairs) > max_pairs:
+        raise RuntimeError("state too dense for the near-threshold scan")
+    if len(pairs):
+        a, b = pairs[:, 0], pairs[:, 1]
+        dist = np.sqrt(((x[a] - x[b]) ** 2).sum(1))
+        near = np.abs(dist * iw[a] * iw[b] - L) <= tau * L
+        flagged[a[near]] = True
+        flagged[b[near]] = True
+    return flagged
+
+
+def make_problem(n, d, avg_degree=10.0, seed=42):
+    edges, _ = geometric_graph(n, avg_degree, seed)
+    w = degree_weights(n, edges, d)
+    x0 = initial_coordinates(n, d, seed=1234)
+    return edges, w, x0

@@ -1,0 +1,608 @@
+// Device kernels of the WEmbed gradient-descent step for sm_100a.
+//
+// Reference semantics (paths relative to the Vraier/wembed checkout):
+//   index rebuild      WembedEmbedder::updateIndex            src/embeddingLib/src/embedder/WembedEmbedder.cpp:212-240
+//   repulsion          calculateAllRepellingForces/repellingForce                       :274-294, :174-210
+//   attraction         calculateAllAttractingForces/attractionForce                     :260-272, :140-172
+//   centre force       calculateAllCentreForces                                         :296-301
+//   optimizer          AdamOptimizer::update / SimpleOptimizer::update   src/embeddingLib/src/gradientOptimizer/*.cpp
+//   recentre+observe   applyGravityCentre / observeDisplacement                         :303-352
+//
+// All kernels are pull style: one owner computes force[v]; there are no floating-point atomics and
+// every reduction has a fixed shape, so a step is bit-reproducible from run to run
+// (tests/TestDeterminism.cpp protocol).  V = number of float4 chunks per position row.
+#pragma once
+#include "common.cuh"
+#include "mt19937.cuh"
+
+namespace wb {
+
+// ---------------------------------------------------------------------------------------------
+// Parameter blocks
+
+struct QuantParams {          // Morton quantisation frame, rebuilt every step on the device
+    float lo[kMaxDim];
+    float invCell[kMaxDim];
+};
+
+struct TreeView {             // implicit 8-ary box hierarchy, structure-of-planes (see common.cuh)
+    int numLevels;            // top level index; level 0 = points
+    int count[kMaxLevels];    // real nodes per level
+    int stride[kMaxLevels];   // plane stride (count rounded up to kFan)
+    const float4* lo[kMaxLevels];   // lo[l][c * stride[l] + node]
+    const float4* hi[kMaxLevels];   // hi[0] == lo[0] (points)
+    const float* bound[kMaxLevels]; // min over the subtree of the pruning weight factor (iw of points)
+    const int* ids;           // sorted position -> vertex id (-1 for padding)
+};
+
+struct ForceParams {
+    float edgeLength;         // L
+    float pruneL2;            // L^2 * (1 + slack): conservative bound for box pruning
+    float attractionScale, repulsionScale, centreScale;
+    // optimizer (AdamOptimizer.cpp:19-28 / SimpleOptimizer.cpp:13-30)
+    int optimizer;            // wb_optimizer
+    float lr, beta1, beta2, eps, invBias1, invBias2, maxDisplacement;
+    uint32_t seed, iteration; // tie-break generator key (Rand.cpp:29-35)
+    int dim;                  // real embedding dimension (<= 4V)
+    int keepForces;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Index, stage 1: per-dimension min / max / sum / sum of squares (fixed-order reduction).
+// partial layout: [block][4][kMaxDim] floats.
+template <int V>
+__global__ void __launch_bounds__(256) k_moments(const float4* __restrict__ x, int n, float* __restrict__ partial) {
+    float mn[4 * V], mx[4 * V], s1[4 * V], s2[4 * V];
+#pragma unroll
+    for (int k = 0; k < 4 * V; ++k) { mn[k] = 3.0e38f; mx[k] = -3.0e38f; s1[k] = 0.f; s2[k] = 0.f; }
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int c = 0; c < V; ++c) {
+            const float4 p = __ldg(x + (int64_t)v * V + c);
+            const float e[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int k = 4 * c + i;
+                mn[k] = fminf(mn[k], e[i]); mx[k] = fmaxf(mx[k], e[i]);
+                s1[k] += e[i]; s2[k] = fmaf(e[i], e[i], s2[k]);
+            }
+        }
+    }
+    __shared__ float sm[8][4][4 * V];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 4 * V; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+            mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+            s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], o);
+            s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], o);
+        }
+        if (lane == 0) { sm[warp][0][k] = mn[k]; sm[warp][1][k] = mx[k]; sm[warp][2][k] = s1[k]; sm[warp][3][k] = s2[k]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 4 * V) {
+        const int k = threadIdx.x;
+        float a = sm[0][0][k], b = sm[0][1][k], c = sm[0][2][k], d = sm[0][3][k];
+        for (int w = 1; w < 8; ++w) { a = fminf(a, sm[w][0][k]); b = fmaxf(b, sm[w][1][k]); c += sm[w][2][k]; d += sm[w][3][k]; }
+        float* out = partial + (int64_t)blockIdx.x * 4 * kMaxDim;
+        out[0 * kMaxDim + k] = a; out[1 * kMaxDim + k] = b; out[2 * kMaxDim + k] = c; out[3 * kMaxDim + k] = d;
+    }
+}
+
+// Index, stage 2: quantisation frame = [mean - 4 sd, mean + 4 sd] clipped to [min, max] per dimension, so a few
+// far outliers do not eat the key resolution of the bulk.  Only locality depends on this frame, never results.
+__global__ void k_quant_params(const float* __restrict__ partial, int numBlocks, int n, int dim, int bits, QuantParams* __restrict__ qp) {
+    const int k = threadIdx.x;
+    if (k >= dim) return;
+    float mn = 3.0e38f, mx = -3.0e38f; double s1 = 0.0, s2 = 0.0;
+    for (int b = 0; b < numBlocks; ++b) {
+        const float* p = partial + (int64_t)b * 4 * kMaxDim;
+        mn = fminf(mn, p[k]); mx = fmaxf(mx, p[kMaxDim + k]); s1 += p[2 * kMaxDim + k]; s2 += p[3 * kMaxDim + k];
+    }
+    const double mean = s1 / n;
+    const double var = fmax(0.0, s2 / n - mean * mean);
+    const float sd = (float)sqrt(var);
+    float lo = fmaxf(mn, (float)mean - 4.f * sd), hi = fminf(mx, (float)mean + 4.f * sd);
+    if (!(hi > lo)) hi = lo + 1.f;
+    qp->lo[k] = lo;
+    qp->invCell[k] = (float)(1u << bits) / (hi - lo);
+}
+
+// Index, stage 3: Morton key of every vertex (bit b of dimension k -> key bit b*dim + k).
+template <int V>
+__global__ void __launch_bounds__(256) k_morton_keys(const float4* __restrict__ x, int n, int dim, int bits,
+                                                     const QuantParams* __restrict__ qp, uint32_t* __restrict__ keys,
+                                                     int* __restrict__ vals) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const uint32_t qmax = (1u << bits) - 1u;
+    uint32_t key = 0;
+#pragma unroll
+    for (int c = 0; c < V; ++c) {
+        const float4 p = __ldg(x + (int64_t)v * V + c);
+        const float e[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int k = 4 * c + i;
+            if (k < dim) {
+                const float t = (e[i] - qp->lo[k]) * qp->invCell[k];
+                const uint32_t q = t <= 0.f ? 0u : (t >= (float)qmax ? qmax : (uint32_t)t);
+                for (int b = 0; b < bits; ++b) key |= ((q >> b) & 1u) << (b * dim + k);
+            }
+        }
+    }
+    keys[v] = key;
+    vals[v] = v;
+}
+
+// Index, stage 4: gather the positions into sorted order (plane layout) and build the level-1 boxes.
+// One 8-lane group per leaf; lane j owns sorted point leaf*8 + j.
+template <int V>
+__global__ void __launch_bounds__(256) k_build_leaves(const float4* __restrict__ x, const float* __restrict__ pointBound,
+                                                      const int* __restrict__ order, int n, float4* __restrict__ pts,
+                                                      int stride0, float* __restrict__ bound0, int* __restrict__ ids,
+                                                      float4* __restrict__ lo1, float4* __restrict__ hi1,
+                                                      float* __restrict__ bound1, int stride1) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // sorted position
+    const int leaf = i >> kFanLog2, j = i & (kFan - 1);
+    const bool real = i < n;
+    float4 lo[V], hi[V];
+    float b = 3.0e38f;
+    if (real) {
+        const int src = order[i];
+        b = __ldg(pointBound + src);
+#pragma unroll
+        for (int c = 0; c < V; ++c) {
+            const float4 p = __ldg(x + (int64_t)src * V + c);
+            pts[(int64_t)c * stride0 + i] = p;
+            lo[c] = p; hi[c] = p;
+        }
+        bound0[i] = b;
+        ids[i] = src;
+    } else {
+#pragma unroll
+        for (int c = 0; c < V; ++c) { lo[c] = make_float4(3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f); hi[c] = make_float4(-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f); }
+    }
+#pragma unroll
+    for (int o = kFan / 2; o > 0; o >>= 1) {
+#pragma unroll
+        for (int c = 0; c < V; ++c) { lo[c] = min4(lo[c], shfl_xor4(lo[c], o)); hi[c] = max4(hi[c], shfl_xor4(hi[c], o)); }
+        b = fminf(b, __shfl_xor_sync(0xffffffffu, b, o));
+    }
+    if (leaf * kFan < n) {
+#pragma unroll
+        for (int c = 0; c < V; ++c)
+            if (j == c) { lo1[(int64_t)c * stride1 + leaf] = lo[c]; hi1[(int64_t)c * stride1 + leaf] = hi[c]; }
+        if (j == kFan - 1) bound1[leaf] = b;
+    }
+}
+
+// Index, stage 5: one level of the hierarchy from the level below (8 lanes per parent).
+template <int V>
+__global__ void __launch_bounds__(256) k_build_level(const float4* __restrict__ cLo, const float4* __restrict__ cHi,
+                                                     const float* __restrict__ cBound, int cCount, int cStride,
+                                                     float4* __restrict__ pLo, float4* __restrict__ pHi,
+                                                     float* __restrict__ pBound, int pCount, int pStride) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // child index
+    const int parent = i >> kFanLog2, j = i & (kFan - 1);
+    float4 lo[V], hi[V];
+    float b = 3.0e38f;
+    if (i < cCount) {
+#pragma unroll
+        for (int c = 0; c < V; ++c) { lo[c] = cLo[(int64_t)c * cStride + i]; hi[c] = cHi[(int64_t)c * cStride + i]; }
+        b = cBound[i];
+    } else {
+#pragma unroll
+        for (int c = 0; c < V; ++c) { lo[c] = make_float4(3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f); hi[c] = make_float4(-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f); }
+    }
+#pragma unroll
+    for (int o = kFan / 2; o > 0; o >>= 1) {
+#pragma unroll
+        for (int c = 0; c < V; ++c) { lo[c] = min4(lo[c], shfl_xor4(lo[c], o)); hi[c] = max4(hi[c], shfl_xor4(hi[c], o)); }
+        b = fminf(b, __shfl_xor_sync(0xffffffffu, b, o));
+    }
+    if (parent < pCount) {
+#pragma unroll
+        for (int c = 0; c < V; ++c)
+            if (j == c) { pLo[(int64_t)c * pStride + parent] = lo[c]; pHi[(int64_t)c * pStride + parent] = hi[c]; }
+        if (j == kFan - 1) pBound[parent] = b;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Hierarchy walk shared by the repulsion kernel and the candidate-set test hook.
+//
+// One 8-lane group per query (4 queries per warp).  The group keeps a depth-first cursor in registers
+// (current level, index of the expanded parent, one 8-bit "pending children" mask per level) and in
+// every iteration expands one node: lane j tests child j.  Children that pass at level 0 are points
+// and are handed to `onPoint` by the lane that tested them; everything is visited in a fixed order.
+struct WalkMasks {
+    unsigned long long a = 0ull, b = 0ull;   // 8 bits per level, levels 0..7 in a, 8..15 in b
+    __device__ __forceinline__ uint32_t get(int l) const { return (uint32_t)(((l < 8) ? (a >> (8 * l)) : (b >> (8 * (l - 8)))) & 0xffull); }
+    __device__ __forceinline__ void set(int l, uint32_t m) {
+        if (l < 8) a = (a & ~(0xffull << (8 * l))) | ((unsigned long long)m << (8 * l));
+        else b = (b & ~(0xffull << (8 * (l - 8)))) | ((unsigned long long)m << (8 * (l - 8)));
+    }
+};
+
+// passes(level, idx, d2, bound, lo[]) decides whether a child survives; onPoint consumes level-0 survivors.
+template <int V, typename Pass, typename OnPoint>
+__device__ __forceinline__ void walk_tree(const TreeView& t, const float4 (&q)[V], bool valid, Pass&& passes, OnPoint&& onPoint,
+                                          int& pointTests) {
+    const int lane = threadIdx.x & 31, j = lane & (kFan - 1), g = lane >> kFanLog2;
+    const int top = t.numLevels;
+    int lvl = top + 1, cur = 0;
+    WalkMasks masks;
+    masks.set(top + 1, 1u);      // virtual root
+    bool done = !valid;
+    while (__any_sync(0xffffffffu, !done)) {
+        if (!done) {
+            while (lvl <= top + 1 && masks.get(lvl) == 0u) { ++lvl; cur >>= kFanLog2; }
+            if (lvl > top + 1) {
+                done = true;
+            } else {
+                const uint32_t m = masks.get(lvl);
+                const int bit = __ffs(m) - 1;
+                masks.set(lvl, m & (m - 1u));
+                cur = cur * kFan + bit;   // the node being expanded (index at level lvl)
+                --lvl;                    // its children live one level down
+            }
+        }
+        const int lv = done ? 0 : lvl;
+        const int idx = done ? 0 : cur * kFan + j;
+        float4 lo[V], hi[V];
+        const int64_t st = t.stride[lv];
+#pragma unroll
+        for (int c = 0; c < V; ++c) lo[c] = __ldg(t.lo[lv] + c * st + idx);
+        if (lv == 0) {
+#pragma unroll
+            for (int c = 0; c < V; ++c) hi[c] = lo[c];
+        } else {
+#pragma unroll
+            for (int c = 0; c < V; ++c) hi[c] = __ldg(t.hi[lv] + c * st + idx);
+        }
+        const float bnd = __ldg(t.bound[lv] + idx);
+        const float d2 = box_dist2<V>(q, lo, hi);
+        const bool pass = !done && passes(lv, idx, d2, bnd);
+        const uint32_t ball = __ballot_sync(0xffffffffu, pass);
+        if (!done) {
+            if (lvl == 0) {
+                ++pointTests;
+                if (pass) onPoint(idx, d2, bnd, lo);
+            } else {
+                masks.set(lvl, (ball >> (kFan * g)) & 0xffu);
+            }
+        }
+    }
+}
+
+// u in N(v)?  Rows are sorted ascending (Graph.cpp:87-150), so a binary search equals Graph::areNeighbors (:67-83).
+__device__ __forceinline__ bool is_neighbor(const int* __restrict__ col, int begin, int end, int u) {
+    while (begin < end) {
+        const int mid = (begin + end) >> 1;
+        const int w = __ldg(col + mid);
+        if (w == u) return true;
+        if (w < u) begin = mid + 1; else end = mid;
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Repulsion (WembedEmbedder.cpp:274-294 + 174-210).  Query order = sorted order, so neighbouring groups walk
+// similar paths.  Writes forceRep[v], lossRep[v], the number of coincident non-neighbours of v, and per-block
+// counters {pairs, point tests} for the statistics.
+template <int V>
+__global__ void __launch_bounds__(256) k_repulse(const TreeView t, const int* __restrict__ rowPtr, const int* __restrict__ col,
+                                                 int n, const ForceParams fp, float4* __restrict__ forceRep,
+                                                 float* __restrict__ lossRep, int* __restrict__ coincident,
+                                                 double* __restrict__ partials) {
+    __shared__ double smem[8 * 2];
+    const int lane = threadIdx.x & 31, j = lane & (kFan - 1);
+    const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> kFanLog2;
+    const bool valid = qi < n;
+    float4 q[V];
+    float iwq = 1.f;
+    int v = -1, rowBegin = 0, rowEnd = 0;
+    if (valid) {
+#pragma unroll
+        for (int c = 0; c < V; ++c) q[c] = __ldg(t.lo[0] + (int64_t)c * t.stride[0] + qi);
+        iwq = __ldg(t.bound[0] + qi);
+        v = __ldg(t.ids + qi);
+        rowBegin = __ldg(rowPtr + v);
+        rowEnd = __ldg(rowPtr + v + 1);
+    } else {
+#pragma unroll
+        for (int c = 0; c < V; ++c) q[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float4 acc[V];
+#pragma unroll
+    for (int c = 0; c < V; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float loss = 0.f;
+    int nCoincident = 0, nPairs = 0, nTests = 0;
+    const float L = fp.edgeLength;
+
+    walk_tree<V>(
+        t, q, valid,
+        [&](int, int, float d2, float bnd) {
+            const float s = iwq * bnd;
+            return d2 * s * s <= fp.pruneL2;       // superset of dist * ws <= L
+        },
+        [&](int idx, float d2, float iwu, const float4 (&pu)[V]) {
+            const int u = __ldg(t.ids + idx);
+            if (u == v) return;                      // areInSameColorClass (colours are unique ids, Graph.cpp:152-156)
+            const float dist = sqrtf(d2);
+            const float ws = iwq * iwu;
+            if (dist <= 0.f) {
+                if (!is_neighbor(col, rowBegin, rowEnd, u)) ++nCoincident;   // random direction added by k_attract
+            } else if (dist * ws <= L) {
+                if (!is_neighbor(col, rowBegin, rowEnd, u)) {
+                    axpy_diff<V>(acc, fp.repulsionScale * ws / dist, q, pu);
+                    loss += L / ws - dist;
+                    ++nPairs;
+                }
+            }
+        },
+        nTests);
+
+#pragma unroll
+    for (int c = 0; c < V; ++c) acc[c] = group_sum<kFan>(acc[c]);
+    loss = group_sum<kFan>(loss);
+    nCoincident = group_sum<kFan>(nCoincident);
+    nPairs = group_sum<kFan>(nPairs);
+    nTests = group_sum<kFan>(nTests);
+    if (valid) {
+#pragma unroll
+        for (int c = 0; c < V; ++c)
+            if (j == c) forceRep[(int64_t)v * V + c] = acc[c];
+        if (j == kFan - 1) { lossRep[v] = loss; coincident[v] = nCoincident; }
+    }
+    double sums[2] = {(valid && j == 0) ? (double)nPairs : 0.0, (valid && j == 0) ? (double)nTests : 0.0};
+    block_sum<2, 256>(sums, smem, partials + (int64_t)blockIdx.x * 2);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Attraction + centre force + optimizer, fused (WembedEmbedder.cpp:260-272, 140-172, 296-301; AdamOptimizer.cpp:15-30).
+// G lanes share one vertex: they stride over its CSR row, reduce with a fixed butterfly, add the repulsive force
+// computed by k_repulse, then lane c updates chunk c of x / m / v.  Each block owns a fixed contiguous vertex range
+// and emits the sums {lossA, lossR, sum_v xnew[v][k]} for the deterministic reducer.
+template <int V, int G>
+__global__ void __launch_bounds__(256) k_attract_update(const float4* __restrict__ x, const float* __restrict__ iw,
+                                                        const int* __restrict__ rowPtr, const int* __restrict__ col, int n,
+                                                        int vertsPerBlock, const ForceParams fp,
+                                                        const float4* __restrict__ forceRep, const float* __restrict__ lossRep,
+                                                        const int* __restrict__ coincidentRep, float4* __restrict__ xNew,
+                                                        float4* __restrict__ mom1, float4* __restrict__ mom2,
+                                                        float4* __restrict__ forceOut, double* __restrict__ partials) {
+    constexpr int GROUPS_PER_WARP = 32 / G, GROUPS_PER_BLOCK = 256 / G, K = 2 + 4 * V;
+    __shared__ uint32_t mtState[8][624];
+    __shared__ double unitBuf[8][GROUPS_PER_WARP][4 * V];
+    __shared__ double redBuf[8 * K];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, lig = lane % G, gInWarp = lane / G;
+    const int vBegin = blockIdx.x * vertsPerBlock;
+    const int vEnd = min(n, vBegin + vertsPerBlock);
+    double sums[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) sums[k] = 0.0;
+    const float L = fp.edgeLength;
+
+    for (int vBase = vBegin; vBase < vEnd; vBase += GROUPS_PER_BLOCK) {
+        const int v = vBase + threadIdx.x / G;
+        const bool valid = v < vEnd;
+        float4 xv[V], acc[V];
+#pragma unroll
+        for (int c = 0; c < V; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float loss = 0.f, iwv = 1.f;
+        int nCoincident = 0;
+        if (valid) {
+            load_row<V>(x, v, xv);
+            iwv = __ldg(iw + v);
+            const int end = __ldg(rowPtr + v + 1);
+            for (int e = __ldg(rowPtr + v) + lig; e < end; e += G) {
+                const int u = __ldg(col + e);
+                if (u == v) continue;                              // attractionForce: v == u -> 0 (:141)
+                float4 xu[V];
+                load_row<V>(x, u, xu);
+                const float d2 = point_dist2<V>(xu, xv);
+                const float dist = sqrtf(d2);
+                if (dist <= 0.f) { ++nCoincident; continue; }     // :150-155
+                const float ws = iwv * __ldg(iw + u);
+                if (dist * ws > L) {                               // :163-168
+                    axpy_diff<V>(acc, fp.attractionScale * ws / dist, xu, xv);
+                    loss += dist - L / ws;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < V; ++c) xv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int c = 0; c < V; ++c) acc[c] = group_sum<G>(acc[c]);
+        loss = group_sum<G>(loss);
+        nCoincident = group_sum<G>(nCoincident);
+        if (valid) nCoincident += __ldg(coincidentRep + v);
+
+        // coincident partners: every one of them adds the same unit vector (generator re-created per pair, :150-155, :183-188)
+        if (__any_sync(0xffffffffu, nCoincident > 0)) {
+            for (int gg = 0; gg < GROUPS_PER_WARP; ++gg) {
+                if (gInWarp == gg && lig == 0 && nCoincident > 0)
+                    random_unit_vector(mtState[warp], fp.seed, (uint32_t)v, fp.iteration, fp.dim, unitBuf[warp][gg]);
+                __syncwarp();
+            }
+            if (nCoincident > 0) {
+                const double* uvec = unitBuf[warp][gInWarp];
+#pragma unroll
+                for (int c = 0; c < V; ++c) {
+                    acc[c].x += (4 * c + 0 < fp.dim) ? (float)(nCoincident * uvec[4 * c + 0]) : 0.f;
+                    acc[c].y += (4 * c + 1 < fp.dim) ? (float)(nCoincident * uvec[4 * c + 1]) : 0.f;
+                    acc[c].z += (4 * c + 2 < fp.dim) ? (float)(nCoincident * uvec[4 * c + 2]) : 0.f;
+                    acc[c].w += (4 * c + 3 < fp.dim) ? (float)(nCoincident * uvec[4 * c + 3]) : 0.f;
+                }
+            }
+            __syncwarp();
+        }
+
+        if (valid) {
+            if (lig == 0) { sums[0] += (double)loss; sums[1] += (double)__ldg(lossRep + v); }
+#pragma unroll
+            for (int c = 0; c < V; ++c) {
+                if ((c % G) == lig) {
+                    const int64_t at = (int64_t)v * V + c;
+                    float4 f = add4(acc[c], __ldg(forceRep + at));
+                    if (fp.centreScale != 0.f) {                   // :296-301
+                        f.x = fmaf(-fp.centreScale, xv[c].x, f.x); f.y = fmaf(-fp.centreScale, xv[c].y, f.y);
+                        f.z = fmaf(-fp.centreScale, xv[c].z, f.z); f.w = fmaf(-fp.centreScale, xv[c].w, f.w);
+                    }
+                    if (fp.keepForces) forceOut[at] = f;
+                    float4 xn;
+                    if (fp.optimizer == 1) {
+                        float4 m = mom1[at], s = mom2[at];
+                        const float fe[4] = {f.x, f.y, f.z, f.w};
+                        float me[4] = {m.x, m.y, m.z, m.w}, se[4] = {s.x, s.y, s.z, s.w};
+                        float xe[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            me[i] = fp.beta1 * me[i] + (1.f - fp.beta1) * fe[i];
+                            se[i] = fp.beta2 * se[i] + (1.f - fp.beta2) * fe[i] * fe[i];
+                            const float mHat = me[i] * fp.invBias1, vHat = se[i] * fp.invBias2;
+                            xe[i] += fp.lr * mHat / (sqrtf(vHat) + fp.eps);
+                        }
+                        mom1[at] = make_float4(me[0], me[1], me[2], me[3]);
+                        mom2[at] = make_float4(se[0], se[1], se[2], se[3]);
+                        xn = make_float4(xe[0], xe[1], xe[2], xe[3]);
+                    } else {
+                        const float cap = fp.maxDisplacement;
+                        xn.x = xv[c].x + fminf(fmaxf(f.x, -cap), cap) * fp.lr;
+                        xn.y = xv[c].y + fminf(fmaxf(f.y, -cap), cap) * fp.lr;
+                        xn.z = xv[c].z + fminf(fmaxf(f.z, -cap), cap) * fp.lr;
+                        xn.w = xv[c].w + fminf(fmaxf(f.w, -cap), cap) * fp.lr;
+                    }
+                    xNew[at] = xn;
+                    sums[2 + 4 * c + 0] += (double)xn.x; sums[2 + 4 * c + 1] += (double)xn.y;
+                    sums[2 + 4 * c + 2] += (double)xn.z; sums[2 + 4 * c + 3] += (double)xn.w;
+                }
+            }
+        }
+    }
+    block_sum<K, 256>(sums, redBuf, partials + (int64_t)blockIdx.x * K);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Deterministic reduction of per-block partial sums: block k reduces column k.
+// Thread t adds rows t, t+256, ... in order, then the 256 thread sums are combined by a fixed tree.
+__global__ void __launch_bounds__(256) k_reduce_partials(const double* __restrict__ partials, int rows, int cols,
+                                                         double* __restrict__ out) {
+    __shared__ double sm[256];
+    const int k = blockIdx.x;
+    double s = 0.0;
+    for (int r = threadIdx.x; r < rows; r += 256) s += partials[(int64_t)r * cols + k];
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[k] = sm[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// applyGravityCentre + observeDisplacement (WembedEmbedder.cpp:303-352): x = xnew - centroid, and the sums of
+// ||x - xprev|| and ||x||^2.  forceSums = output of the reducer for k_attract_update ({lossA, lossR, sum xnew[k]}).
+template <int V>
+__global__ void __launch_bounds__(256) k_recentre_observe(float4* __restrict__ x, const float4* __restrict__ xNew, int n,
+                                                          int vertsPerBlock, int dim, const double* __restrict__ forceSums,
+                                                          double* __restrict__ partials) {
+    __shared__ double redBuf[8 * 2];
+    float cen[4 * V];
+#pragma unroll
+    for (int k = 0; k < 4 * V; ++k) cen[k] = (k < dim) ? (float)(forceSums[2 + k] / (double)n) : 0.f;
+    const int vBegin = blockIdx.x * vertsPerBlock, vEnd = min(n, vBegin + vertsPerBlock);
+    double sums[2] = {0.0, 0.0};
+    for (int v = vBegin + threadIdx.x; v < vEnd; v += 256) {
+        float disp2 = 0.f, rad2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < V; ++c) {
+            const int64_t at = (int64_t)v * V + c;
+            const float4 a = xNew[at], o = x[at];
+            const float4 r = make_float4(a.x - cen[4 * c], a.y - cen[4 * c + 1], a.z - cen[4 * c + 2], a.w - cen[4 * c + 3]);
+            x[at] = r;
+            disp2 = fmaf(r.x - o.x, r.x - o.x, disp2); disp2 = fmaf(r.y - o.y, r.y - o.y, disp2);
+            disp2 = fmaf(r.z - o.z, r.z - o.z, disp2); disp2 = fmaf(r.w - o.w, r.w - o.w, disp2);
+            rad2 = fmaf(r.x, r.x, rad2); rad2 = fmaf(r.y, r.y, rad2); rad2 = fmaf(r.z, r.z, rad2); rad2 = fmaf(r.w, r.w, rad2);
+        }
+        sums[0] += (double)sqrtf(disp2);
+        sums[1] += (double)rad2;
+    }
+    block_sum<2, 256>(sums, redBuf, partials + (int64_t)blockIdx.x * 2);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Boundary conversions (coordinates cross the C ABI as row-major n x d doubles).
+__global__ void k_rows_from_double(const double* __restrict__ in, int n, int dim, int rowFloats, float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n * rowFloats) return;
+    const int v = (int)(i / rowFloats), k = (int)(i % rowFloats);
+    out[i] = k < dim ? (float)in[(int64_t)v * dim + k] : 0.f;
+}
+__global__ void k_rows_to_double(const float* __restrict__ in, int n, int dim, int rowFloats, double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n * dim) return;
+    const int v = (int)(i / dim), k = (int)(i % dim);
+    out[i] = (double)in[(int64_t)v * rowFloats + k];
+}
+template <typename T>
+__global__ void k_fill(T* p, int64_t count, T value) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) p[i] = value;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Test hook: the reference's candidate set (WeightedIndex.cpp:65-81), evaluated in double on the same walk.
+// writePass 0 counts per query; writePass 1 writes the ids behind offsets[q] (slot order is arbitrary - an
+// integer cursor - because the host sorts every query's ids before returning them).
+template <int V>
+__global__ void __launch_bounds__(256) k_candidates(const TreeView t, const float4* __restrict__ x, const double* __restrict__ w,
+                                                    const double* __restrict__ classMax, int dim, double edgeLength,
+                                                    float pruneL2, const float* __restrict__ iw, const int* __restrict__ queries,
+                                                    int nq, int64_t* __restrict__ counts, const int64_t* __restrict__ offsets,
+                                                    int* __restrict__ cursor, int* __restrict__ outIds, int writePass) {
+    const int lane = threadIdx.x & 31, j = lane & (kFan - 1);
+    const int qn = (blockIdx.x * blockDim.x + threadIdx.x) >> kFanLog2;
+    const bool valid = qn < nq;
+    const int v = valid ? queries[qn] : 0;
+    float4 q[V];
+    load_row<V>(x, v, q);
+    const float iwq = __ldg(iw + v);
+    const double wq = w[v];
+    int found = 0, nTests = 0;
+    const int64_t base = (valid && writePass) ? offsets[qn] : 0;
+    walk_tree<V>(
+        t, q, valid,
+        [&](int, int, float d2, float bnd) {
+            const float s = iwq * bnd;
+            return d2 * s * s <= pruneL2;
+        },
+        [&](int idx, float, float, const float4 (&pu)[V]) {
+            const int u = __ldg(t.ids + idx);
+            double d2 = 0.0;
+#pragma unroll
+            for (int c = 0; c < V; ++c) {
+                double e;
+                e = (double)pu[c].x - (double)q[c].x; d2 += e * e;
+                e = (double)pu[c].y - (double)q[c].y; d2 += e * e;
+                e = (double)pu[c].z - (double)q[c].z; d2 += e * e;
+                e = (double)pu[c].w - (double)q[c].w; d2 += e * e;
+            }
+            const double r = edgeLength * pow(wq * classMax[u], 1.0 / (double)dim);
+            if (d2 <= r * r) {
+                if (writePass) outIds[base + atomicAdd(cursor + qn, 1)] = u;
+                ++found;
+            }
+        },
+        nTests);
+    found = group_sum<kFan>(found);
+    if (valid && !writePass && j == 0) counts[qn] = found;
+}
+
+}  // namespace wb

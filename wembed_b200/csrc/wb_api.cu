@@ -1,0 +1,600 @@
+// C ABI (include/wembed_b200.h) and host orchestration of the device step.
+//
+// One wb_embedder owns one device-resident problem and one CUDA stream.  A step is a fixed sequence of
+// kernel launches on that stream (see enqueue_step); the only host<->device traffic per step is one
+// small D2H copy of the reduced sums.  There is no CPU fallback anywhere in this file.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <deque>
+#include <limits>
+#include <stdexcept>
+#include <vector>
+
+#include "../../include/wembed_b200.h"
+#include "kernels.cuh"
+
+#define WB_STRINGIFY_(x) #x
+#define WB_STRINGIFY(x) WB_STRINGIFY_(x)
+
+namespace {
+
+thread_local std::string g_lastError;
+
+int fail(int code, const std::string& msg) {
+    g_lastError = msg;
+    return code;
+}
+
+template <typename T>
+T* dalloc(size_t count) {
+    T* p = nullptr;
+    WB_CUDA(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    return p;
+}
+
+struct PendingStep {
+    cudaEvent_t done;
+    double* hostSums;     // pinned, kSumsTotal doubles
+    int64_t iteration;
+    bool trivial;         // n <= 1: nothing was launched
+};
+
+}  // namespace
+
+struct wb_embedder {
+    int n = 0, dim = 0, V = 0, rowFloats = 0;
+    int64_t numDirected = 0;
+    wb_options opt{};
+    cudaStream_t stream = nullptr;
+
+    // graph (Graph.hpp:24-85): CSR, rows sorted ascending
+    int *rowPtr = nullptr, *col = nullptr;
+
+    // layout state
+    float4 *x = nullptr, *xNew = nullptr, *mom1 = nullptr, *mom2 = nullptr, *forceRep = nullptr, *force = nullptr;
+    float *iw = nullptr, *lossRep = nullptr;
+    int* coincident = nullptr;
+    std::vector<double> weights;          // state.currentWeights
+    std::vector<double> classMax;         // maxWeightOfClass[class(v)] (WeightedIndex.cpp:25-32), for the test hook
+    int64_t iteration = 0;                // state.currentIteration
+    int adamT = 0;                        // AdamOptimizer::t
+
+    // spatial index
+    int mortonBits = 0;
+    uint32_t *keysIn = nullptr, *keysOut = nullptr;
+    int *valsIn = nullptr, *valsOut = nullptr;
+    void* cubTemp = nullptr;
+    size_t cubBytes = 0;
+    int momentBlocks = 0;
+    float* momentPartials = nullptr;
+    wb::QuantParams* quant = nullptr;
+    float4* lvlLo[wb::kMaxLevels] = {};
+    float4* lvlHi[wb::kMaxLevels] = {};
+    float* lvlBound[wb::kMaxLevels] = {};
+    int* ids = nullptr;
+    wb::TreeView tree{};
+
+    // reductions: sumsAll = [ force sums (2 + 4V) | repulsion counters (2) | observe sums (2) ]
+    int forceBlocks = 0, forceVertsPerBlock = 0, repBlocks = 0, obsBlocks = 0, obsVertsPerBlock = 0;
+    double *partialsForce = nullptr, *partialsRep = nullptr, *partialsObs = nullptr, *sumsAll = nullptr;
+    int sumsTotal = 0;
+
+    std::deque<PendingStep> pending;
+    std::vector<PendingStep> freeSlots;
+
+    bool timing = false;
+    cudaEvent_t ev[7] = {};
+    double phaseMs[6] = {0, 0, 0, 0, 0, 0};
+    bool havePhase = false;
+};
+
+namespace {
+
+using wb::kFan;
+
+#define WB_DISPATCH_V(V_, ...)                                   \
+    switch (V_) {                                                \
+        case 1: { constexpr int V = 1; __VA_ARGS__; } break;     \
+        case 2: { constexpr int V = 2; __VA_ARGS__; } break;     \
+        case 3: { constexpr int V = 3; __VA_ARGS__; } break;     \
+        case 4: { constexpr int V = 4; __VA_ARGS__; } break;     \
+        case 5: { constexpr int V = 5; __VA_ARGS__; } break;     \
+        case 6: { constexpr int V = 6; __VA_ARGS__; } break;     \
+        case 7: { constexpr int V = 7; __VA_ARGS__; } break;     \
+        case 8: { constexpr int V = 8; __VA_ARGS__; } break;     \
+        default: throw wb::CudaError{cudaErrorInvalidValue, "unsupported dimension", __FILE__, __LINE__}; \
+    }
+
+inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+void free_all(wb_embedder* h) {
+    auto F = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
+    F(h->rowPtr); F(h->col); F(h->x); F(h->xNew); F(h->mom1); F(h->mom2); F(h->forceRep); F(h->force);
+    F(h->iw); F(h->lossRep); F(h->coincident); F(h->keysIn); F(h->keysOut); F(h->valsIn); F(h->valsOut);
+    F(h->cubTemp); F(h->momentPartials); F(h->quant); F(h->ids);
+    for (int l = 0; l < wb::kMaxLevels; ++l) { F(h->lvlLo[l]); if (l > 0) F(h->lvlHi[l]); F(h->lvlBound[l]); }
+    F(h->partialsForce); F(h->partialsRep); F(h->partialsObs); F(h->sumsAll);
+    for (auto& p : h->pending) { cudaEventDestroy(p.done); cudaFreeHost(p.hostSums); }
+    for (auto& p : h->freeSlots) { cudaEventDestroy(p.done); cudaFreeHost(p.hostSums); }
+    h->pending.clear(); h->freeSlots.clear();
+    for (auto& e : h->ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+    if (h->stream) cudaStreamDestroy(h->stream);
+    h->stream = nullptr;
+}
+
+void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
+    const int n = h->n, V = h->V;
+    WB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->rowPtr = dalloc<int>(n + 1);
+    h->col = dalloc<int>(h->numDirected);
+    WB_CUDA(cudaMemcpyAsync(h->rowPtr, rowPtr, sizeof(int) * (n + 1), cudaMemcpyHostToDevice, h->stream));
+    if (h->numDirected) WB_CUDA(cudaMemcpyAsync(h->col, col, sizeof(int) * h->numDirected, cudaMemcpyHostToDevice, h->stream));
+
+    const size_t rows = (size_t)n * V;
+    for (float4** p : {&h->x, &h->xNew, &h->mom1, &h->mom2, &h->forceRep, &h->force}) {
+        *p = dalloc<float4>(rows);
+        WB_CUDA(cudaMemsetAsync(*p, 0, std::max<size_t>(rows, 1) * sizeof(float4), h->stream));
+    }
+    h->iw = dalloc<float>(n);
+    h->lossRep = dalloc<float>(n);
+    h->coincident = dalloc<int>(n);
+    WB_CUDA(cudaMemsetAsync(h->lossRep, 0, std::max(n, 1) * sizeof(float), h->stream));
+    WB_CUDA(cudaMemsetAsync(h->coincident, 0, std::max(n, 1) * sizeof(int), h->stream));
+    if (n) wb::k_fill<float><<<div_up(n, 256), 256, 0, h->stream>>>(h->iw, n, 1.0f);
+    h->weights.assign(n, 1.0);
+    h->classMax.assign(n, 1.0);
+
+    // Morton keys: as many bits per dimension as fit a 32-bit key
+    h->mortonBits = std::max(1, std::min(16, 32 / h->dim));
+    h->keysIn = dalloc<uint32_t>(n); h->keysOut = dalloc<uint32_t>(n);
+    h->valsIn = dalloc<int>(n); h->valsOut = dalloc<int>(n);
+    h->cubBytes = 0;
+    WB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, h->cubBytes, h->keysIn, h->keysOut, h->valsIn, h->valsOut, std::max(n, 1), 0,
+                                            h->mortonBits * h->dim, h->stream));
+    h->cubTemp = dalloc<char>(h->cubBytes);
+    h->momentBlocks = std::max(1, std::min(div_up(n, 256), 592));
+    h->momentPartials = dalloc<float>((size_t)h->momentBlocks * 4 * wb::kMaxDim);
+    h->quant = dalloc<wb::QuantParams>(1);
+
+    // hierarchy: level 0 = points (stride = n rounded up to kFan); level l >= 1 = ceil(count[l-1] / kFan) boxes
+    wb::TreeView& t = h->tree;
+    std::memset(&t, 0, sizeof(t));
+    int count = n, level = 0;
+    while (true) {
+        t.count[level] = count;
+        t.stride[level] = std::max(kFan, div_up(count, kFan) * kFan);
+        const size_t planes = (size_t)t.stride[level] * V;
+        h->lvlLo[level] = dalloc<float4>(planes);
+        wb::k_fill<float4><<<div_up(planes, 256), 256, 0, h->stream>>>(h->lvlLo[level], (int64_t)planes,
+                                                                          make_float4(wb::kPadCoord, wb::kPadCoord, wb::kPadCoord, wb::kPadCoord));
+        if (level > 0) {
+            h->lvlHi[level] = dalloc<float4>(planes);
+            wb::k_fill<float4><<<div_up(planes, 256), 256, 0, h->stream>>>(h->lvlHi[level], (int64_t)planes,
+                                                                              make_float4(wb::kPadCoord, wb::kPadCoord, wb::kPadCoord, wb::kPadCoord));
+        } else {
+            h->lvlHi[level] = h->lvlLo[level];
+        }
+        h->lvlBound[level] = dalloc<float>(t.stride[level]);
+        wb::k_fill<float><<<div_up(t.stride[level], 256), 256, 0, h->stream>>>(h->lvlBound[level], t.stride[level], 1.0f);
+        t.lo[level] = h->lvlLo[level]; t.hi[level] = h->lvlHi[level]; t.bound[level] = h->lvlBound[level];
+        if (level >= 1 && count <= kFan) break;
+        count = std::max(1, div_up(count, kFan));
+        ++level;
+        if (level >= wb::kMaxLevels - 1) throw wb::CudaError{cudaErrorInvalidValue, "graph too large for the index", __FILE__, __LINE__};
+    }
+    t.numLevels = level;
+    h->ids = dalloc<int>(t.stride[0]);
+    WB_CUDA(cudaMemsetAsync(h->ids, 0xff, sizeof(int) * t.stride[0], h->stream));
+    t.ids = h->ids;
+
+    // reductions: fixed block -> vertex-range assignment so the sums do not depend on scheduling
+    const int groupsPerBlock = 256 / 8;
+    h->forceBlocks = std::max(1, std::min(div_up(n, groupsPerBlock), 148 * 16));
+    h->forceVertsPerBlock = std::max(groupsPerBlock, div_up(div_up(n, h->forceBlocks), groupsPerBlock) * groupsPerBlock);
+    h->forceBlocks = std::max(1, div_up(n, h->forceVertsPerBlock));
+    h->repBlocks = std::max(1, div_up((int64_t)n * kFan, 256));
+    h->obsBlocks = std::max(1, std::min(div_up(n, 256), 148 * 8));
+    h->obsVertsPerBlock = std::max(256, div_up(div_up(n, h->obsBlocks), 256) * 256);
+    h->obsBlocks = std::max(1, div_up(n, h->obsVertsPerBlock));
+    const int K = 2 + 4 * V;
+    h->sumsTotal = K + 4;
+    h->partialsForce = dalloc<double>((size_t)h->forceBlocks * K);
+    h->partialsRep = dalloc<double>((size_t)h->repBlocks * 2);
+    h->partialsObs = dalloc<double>((size_t)h->obsBlocks * 2);
+    h->sumsAll = dalloc<double>(h->sumsTotal);
+    WB_CUDA(cudaMemsetAsync(h->sumsAll, 0, sizeof(double) * h->sumsTotal, h->stream));
+    for (auto& e : h->ev) WB_CUDA(cudaEventCreate(&e));
+    WB_CUDA(cudaStreamSynchronize(h->stream));
+}
+
+// Rebuild the index from the current positions (WembedEmbedder::updateIndex, every step from scratch).
+// pointBound[v] = the pruning weight factor of v: iw[v] for forces, iw of v's class maximum for the test hook.
+void enqueue_index(wb_embedder* h, const float* pointBound) {
+    const int n = h->n, V = h->V;
+    cudaStream_t s = h->stream;
+    WB_DISPATCH_V(V, wb::k_moments<V><<<h->momentBlocks, 256, 0, s>>>(h->x, n, h->momentPartials));
+    wb::k_quant_params<<<1, 32, 0, s>>>(h->momentPartials, h->momentBlocks, n, h->dim, h->mortonBits, h->quant);
+    WB_DISPATCH_V(V, wb::k_morton_keys<V><<<div_up(n, 256), 256, 0, s>>>(h->x, n, h->dim, h->mortonBits, h->quant, h->keysIn, h->valsIn));
+    WB_CUDA(cub::DeviceRadixSort::SortPairs(h->cubTemp, h->cubBytes, h->keysIn, h->keysOut, h->valsIn, h->valsOut, n, 0,
+                                            h->mortonBits * h->dim, s));
+    const wb::TreeView& t = h->tree;
+    WB_DISPATCH_V(V, wb::k_build_leaves<V><<<div_up(t.stride[0], 256), 256, 0, s>>>(
+                         h->x, pointBound, h->valsOut, n, h->lvlLo[0], t.stride[0], h->lvlBound[0], h->ids, h->lvlLo[1], h->lvlHi[1],
+                         h->lvlBound[1], t.stride[1]));
+    for (int l = 2; l <= t.numLevels; ++l) {
+        WB_DISPATCH_V(V, wb::k_build_level<V><<<div_up((int64_t)t.count[l] * kFan, 256), 256, 0, s>>>(
+                             h->lvlLo[l - 1], h->lvlHi[l - 1], h->lvlBound[l - 1], t.count[l - 1], t.stride[l - 1], h->lvlLo[l], h->lvlHi[l],
+                             h->lvlBound[l], t.count[l], t.stride[l]));
+    }
+    WB_CUDA(cudaGetLastError());
+}
+
+PendingStep take_slot(wb_embedder* h) {
+    if (!h->freeSlots.empty()) {
+        PendingStep p = h->freeSlots.back();
+        h->freeSlots.pop_back();
+        return p;
+    }
+    PendingStep p{};
+    WB_CUDA(cudaEventCreateWithFlags(&p.done, cudaEventDisableTiming));
+    WB_CUDA(cudaMallocHost(&p.hostSums, sizeof(double) * (wb::kMaxSums + 8)));
+    return p;
+}
+
+// WembedEmbedder::calculateStep (WembedEmbedder.cpp:13-63) as a stream of launches.
+void enqueue_step(wb_embedder* h, double learningRate) {
+    const int n = h->n, V = h->V;
+    cudaStream_t s = h->stream;
+    h->iteration++;                                           // EmbedderState::nextStep
+    PendingStep slot = take_slot(h);
+    slot.iteration = h->iteration;
+    slot.trivial = n <= 1;
+    if (slot.trivial) {                                       // "Abort in the case of the first hierarchy layer" (:19-21)
+        WB_CUDA(cudaEventRecord(slot.done, s));
+        h->pending.push_back(slot);
+        return;
+    }
+    wb::ForceParams fp{};
+    fp.edgeLength = (float)h->opt.edge_length;
+    fp.pruneL2 = (float)(h->opt.edge_length * h->opt.edge_length) * (1.0f + wb::kPruneSlack);
+    fp.attractionScale = (float)h->opt.attraction_scale;
+    fp.repulsionScale = (float)h->opt.repulsion_scale;
+    fp.centreScale = (float)h->opt.centre_scale;
+    fp.optimizer = h->opt.optimizer;
+    fp.lr = (float)learningRate;
+    fp.beta1 = 0.9f; fp.beta2 = 0.999f; fp.eps = 1e-8f;      // WembedEmbedder.hpp:46
+    if (h->opt.optimizer == WB_OPT_ADAM) h->adamT++;          // AdamOptimizer.cpp:19
+    fp.invBias1 = (float)(1.0 / (1.0 - std::pow(0.9, h->adamT)));
+    fp.invBias2 = (float)(1.0 / (1.0 - std::pow(0.999, h->adamT)));
+    fp.maxDisplacement = (float)h->opt.simple_max_displacement;
+    fp.seed = h->opt.seed;
+    fp.iteration = (uint32_t)h->iteration;
+    fp.dim = h->dim;
+    fp.keepForces = h->opt.keep_forces;
+    const int K = 2 + 4 * V;
+
+    if (h->timing) WB_CUDA(cudaEventRecord(h->ev[0], s));
+    enqueue_index(h, h->iw);
+    if (h->timing) WB_CUDA(cudaEventRecord(h->ev[1], s));
+    WB_DISPATCH_V(V, wb::k_repulse<V><<<h->repBlocks, 256, 0, s>>>(h->tree, h->rowPtr, h->col, n, fp, h->forceRep, h->lossRep,
+                                                                    h->coincident, h->partialsRep));
+    wb::k_reduce_partials<<<2, 256, 0, s>>>(h->partialsRep, h->repBlocks, 2, h->sumsAll + K);
+    if (h->timing) WB_CUDA(cudaEventRecord(h->ev[2], s));
+    WB_DISPATCH_V(V, wb::k_attract_update<V, 8><<<h->forceBlocks, 256, 0, s>>>(
+                         h->x, h->iw, h->rowPtr, h->col, n, h->forceVertsPerBlock, fp, h->forceRep, h->lossRep, h->coincident, h->xNew,
+                         h->mom1, h->mom2, h->force, h->partialsForce));
+    wb::k_reduce_partials<<<K, 256, 0, s>>>(h->partialsForce, h->forceBlocks, K, h->sumsAll);
+    if (h->timing) WB_CUDA(cudaEventRecord(h->ev[3], s));
+    WB_DISPATCH_V(V, wb::k_recentre_observe<V><<<h->obsBlocks, 256, 0, s>>>(h->x, h->xNew, n, h->obsVertsPerBlock, h->dim, h->sumsAll,
+                                                                              h->partialsObs));
+    wb::k_reduce_partials<<<2, 256, 0, s>>>(h->partialsObs, h->obsBlocks, 2, h->sumsAll + K + 2);
+    if (h->timing) WB_CUDA(cudaEventRecord(h->ev[4], s));
+    WB_CUDA(cudaGetLastError());
+    WB_CUDA(cudaMemcpyAsync(slot.hostSums, h->sumsAll, sizeof(double) * h->sumsTotal, cudaMemcpyDeviceToHost, s));
+    WB_CUDA(cudaEventRecord(slot.done, s));
+    h->pending.push_back(slot);
+}
+
+void collect_step(wb_embedder* h, wb_step_stats* out) {
+    PendingStep slot = h->pending.front();
+    h->pending.pop_front();
+    WB_CUDA(cudaEventSynchronize(slot.done));
+    wb_step_stats st;
+    std::memset(&st, 0, sizeof(st));
+    st.iteration = slot.iteration;
+    if (!slot.trivial) {
+        const int K = 2 + 4 * h->V;
+        const double* s = slot.hostSums;
+        st.loss_attract = s[0];
+        st.loss_repel = s[1];
+        for (int k = 0; k < h->dim; ++k) st.centroid[k] = s[2 + k] / (double)h->n;
+        st.num_repulsion_pairs = s[K];
+        st.num_candidates = s[K + 1];
+        st.sum_displacement = s[K + 2];
+        st.sum_radius_sq = s[K + 3];
+        const double invN = 1.0 / (double)h->n;                              // observeDisplacement (:341-350)
+        const double radius = std::sqrt(st.sum_radius_sq * invN);
+        st.rel_displacement = radius > 0.0 ? (st.sum_displacement * invN) / radius : 0.0;
+        if (h->timing && h->pending.empty()) {
+            // events: 0 start | 1 index built | 2 repulsion done | 3 attraction+optimizer done | 4 recentred
+            float ms;
+            WB_CUDA(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1])); h->phaseMs[0] = ms;
+            WB_CUDA(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3])); h->phaseMs[1] = ms;
+            WB_CUDA(cudaEventElapsedTime(&ms, h->ev[1], h->ev[2])); h->phaseMs[2] = ms;
+            h->phaseMs[3] = 0.0;  // the optimizer is fused into the attraction kernel
+            WB_CUDA(cudaEventElapsedTime(&ms, h->ev[3], h->ev[4])); h->phaseMs[4] = ms;
+            WB_CUDA(cudaEventElapsedTime(&ms, h->ev[0], h->ev[4])); h->phaseMs[5] = ms;
+            h->havePhase = true;
+        }
+    }
+    h->freeSlots.push_back(slot);
+    if (out) *out = st;
+}
+
+void upload_rows(wb_embedder* h, const double* src, float4* dst) {
+    const int64_t count = (int64_t)h->n * h->dim;
+    if (count == 0) return;
+    double* tmp = dalloc<double>(count);
+    cudaError_t e = cudaMemcpyAsync(tmp, src, sizeof(double) * count, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        const int64_t total = (int64_t)h->n * h->rowFloats;
+        wb::k_rows_from_double<<<div_up(total, 256), 256, 0, h->stream>>>(tmp, h->n, h->dim, h->rowFloats, reinterpret_cast<float*>(dst));
+        e = cudaStreamSynchronize(h->stream);
+    }
+    cudaFree(tmp);
+    WB_CUDA(e);
+}
+
+void download_rows(wb_embedder* h, const float4* src, double* dst) {
+    const int64_t count = (int64_t)h->n * h->dim;
+    if (count == 0) return;
+    double* tmp = dalloc<double>(count);
+    wb::k_rows_to_double<<<div_up(count, 256), 256, 0, h->stream>>>(reinterpret_cast<const float*>(src), h->n, h->dim, h->rowFloats, tmp);
+    cudaError_t e = cudaMemcpyAsync(dst, tmp, sizeof(double) * count, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(tmp);
+    WB_CUDA(e);
+}
+
+template <typename F>
+int guarded(wb_embedder* h, F&& body) {
+    if (!h) return fail(WB_ERR_INVALID, "null handle");
+    try {
+        WB_CUDA(cudaSetDevice(h->opt.device));
+        body();
+        return WB_OK;
+    } catch (const wb::CudaError& e) {
+        return fail(e.code == cudaErrorInvalidValue ? WB_ERR_INVALID : WB_ERR_CUDA,
+                    std::string(e.what) + ": " + cudaGetErrorString(e.code) + " (" + e.file + ":" + std::to_string(e.line) + ")");
+    } catch (const std::exception& e) {
+        return fail(WB_ERR_INVALID, e.what());
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int wb_abi_version(void) { return WB_ABI_VERSION; }
+
+const char* wb_build_info(void) {
+    return "wembed_b200 sm_100a fp32 | index: morton-sorted 8-ary box hierarchy | cuda " WB_STRINGIFY(CUDART_VERSION);
+}
+
+const char* wb_last_error(void) { return g_lastError.c_str(); }
+
+int wb_device_count(void) {
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return c;
+}
+
+void wb_options_default(wb_options* o) {
+    std::memset(o, 0, sizeof(*o));
+    o->embedding_dimension = 4;          // EmbedderOptions.hpp:32
+    o->optimizer = WB_OPT_ADAM;          // :49
+    o->precision = WB_PREC_F32;
+    o->device = 0;
+    o->keep_forces = 0;
+    o->attraction_scale = 1.0;           // :40
+    o->repulsion_scale = 1.0;            // :41
+    o->centre_scale = 0.0;               // :43
+    o->edge_length = 1.0;                // :44
+    o->doubling_factor = 2.0;            // :39
+    o->simple_max_displacement = 1.0;    // :51
+    o->seed = 0;
+}
+
+int wb_create(wb_embedder** out, int32_t n, const int32_t* row_ptr, const int32_t* col, const wb_options* opts) {
+    if (!out || !opts || n < 0 || (n > 0 && !row_ptr)) return fail(WB_ERR_INVALID, "wb_create: bad arguments");
+    if (opts->embedding_dimension < 1 || opts->embedding_dimension > wb::kMaxDim)
+        return fail(WB_ERR_UNSUPPORTED, "wb_create: embedding_dimension must be in 1..32");
+    if (opts->precision != WB_PREC_F32) return fail(WB_ERR_UNSUPPORTED, "wb_create: only WB_PREC_F32 device state is implemented");
+    if (wb_device_count() <= opts->device) return fail(WB_ERR_NO_DEVICE, "wb_create: no CUDA device (there is no CPU fallback)");
+    static const int32_t zeroRow[1] = {0};
+    if (n == 0) row_ptr = zeroRow;
+    // the invariants of Graph (Graph.cpp:87-150): monotone offsets, rows strictly ascending, ids in range, no self loops
+    if (row_ptr[0] != 0) return fail(WB_ERR_INVALID, "wb_create: row_ptr[0] != 0");
+    for (int v = 0; v < n; ++v) {
+        if (row_ptr[v + 1] < row_ptr[v]) return fail(WB_ERR_INVALID, "wb_create: row_ptr not monotone");
+        for (int e = row_ptr[v]; e < row_ptr[v + 1]; ++e) {
+            if (col[e] < 0 || col[e] >= n || col[e] == v) return fail(WB_ERR_INVALID, "wb_create: neighbour id out of range or self loop");
+            if (e > row_ptr[v] && col[e] <= col[e - 1]) return fail(WB_ERR_INVALID, "wb_create: rows must be strictly ascending");
+        }
+    }
+    auto* h = new wb_embedder();
+    h->n = n;
+    h->dim = opts->embedding_dimension;
+    h->V = (h->dim + 3) / 4;
+    h->rowFloats = 4 * h->V;
+    h->numDirected = row_ptr[n];
+    h->opt = *opts;
+    const int rc = guarded(h, [&] { allocate(h, row_ptr, col); });
+    if (rc != WB_OK) { free_all(h); delete h; return rc; }
+    *out = h;
+    return WB_OK;
+}
+
+int wb_destroy(wb_embedder* h) {
+    if (!h) return WB_OK;
+    cudaSetDevice(h->opt.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    free_all(h);
+    delete h;
+    return WB_OK;
+}
+
+int wb_set_coordinates(wb_embedder* h, const double* coords) {
+    if (h && h->n > 0 && !coords) return fail(WB_ERR_INVALID, "wb_set_coordinates: null buffer");
+    return guarded(h, [&] { upload_rows(h, coords, h->x); });
+}
+
+int wb_set_weights(wb_embedder* h, const double* weights) {
+    if (h && h->n > 0 && !weights) return fail(WB_ERR_INVALID, "wb_set_weights: null buffer");
+    return guarded(h, [&] {
+        const int n = h->n;
+        for (int v = 0; v < n; ++v)
+            if (!(weights[v] > 0.0) || !std::isfinite(weights[v])) throw std::runtime_error("wb_set_weights: weights must be finite and > 0");
+        h->weights.assign(weights, weights + n);
+        if (n == 0) return;
+        // invExpWeights[v] = 1 / pow(w, 1/d), computed in double like the reference (WembedEmbedder.cpp:127-130)
+        std::vector<float> iw(n);
+        for (int v = 0; v < n; ++v) iw[v] = (float)(1.0 / std::pow(weights[v], 1.0 / (double)h->dim));
+        WB_CUDA(cudaMemcpyAsync(h->iw, iw.data(), sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+        WB_CUDA(cudaStreamSynchronize(h->stream));
+        // weight classes (WeightedIndex::getDoublingWeightBuckets + updateIndices, WeightedIndex.cpp:51-63, 18-32)
+        const double minW = *std::min_element(h->weights.begin(), h->weights.end());
+        const double maxW = *std::max_element(h->weights.begin(), h->weights.end());
+        std::vector<double> buckets;
+        if (h->opt.doubling_factor > 1.0)
+            for (double c = minW * h->opt.doubling_factor; c < maxW; c *= h->opt.doubling_factor) buckets.push_back(c);
+        std::vector<double> classMaxOf = buckets;
+        classMaxOf.push_back(maxW);
+        for (int v = 0; v < n; ++v)
+            h->classMax[v] = classMaxOf[std::upper_bound(buckets.begin(), buckets.end(), h->weights[v]) - buckets.begin()];
+    });
+}
+
+int wb_get_coordinates(wb_embedder* h, double* coords) {
+    if (h && h->n > 0 && !coords) return fail(WB_ERR_INVALID, "wb_get_coordinates: null buffer");
+    return guarded(h, [&] { download_rows(h, h->x, coords); });
+}
+
+int wb_get_weights(wb_embedder* h, double* weights) {
+    if (!h) return fail(WB_ERR_INVALID, "null handle");
+    std::copy(h->weights.begin(), h->weights.end(), weights);
+    return WB_OK;
+}
+
+int wb_get_forces(wb_embedder* h, double* forces) {
+    if (h && !h->opt.keep_forces) return fail(WB_ERR_INVALID, "wb_get_forces: create the handle with keep_forces = 1");
+    return guarded(h, [&] { download_rows(h, h->force, forces); });
+}
+
+int wb_reset_optimizer(wb_embedder* h) {
+    return guarded(h, [&] {
+        const size_t bytes = (size_t)h->n * h->V * sizeof(float4);
+        if (bytes) { WB_CUDA(cudaMemsetAsync(h->mom1, 0, bytes, h->stream)); WB_CUDA(cudaMemsetAsync(h->mom2, 0, bytes, h->stream)); }
+        WB_CUDA(cudaStreamSynchronize(h->stream));
+        h->adamT = 0;
+        h->iteration = 0;
+    });
+}
+
+int wb_set_iteration(wb_embedder* h, int64_t iteration) {
+    if (!h) return fail(WB_ERR_INVALID, "null handle");
+    h->iteration = iteration;
+    return WB_OK;
+}
+
+int wb_step_async(wb_embedder* h, double learning_rate) {
+    if (h && (int)h->pending.size() >= WB_MAX_INFLIGHT) return fail(WB_ERR_INVALID, "wb_step_async: too many steps in flight");
+    return guarded(h, [&] { enqueue_step(h, learning_rate); });
+}
+
+int wb_step_collect(wb_embedder* h, wb_step_stats* stats) {
+    if (h && h->pending.empty()) return fail(WB_ERR_INVALID, "wb_step_collect: no step in flight");
+    return guarded(h, [&] { collect_step(h, stats); });
+}
+
+int wb_step(wb_embedder* h, double learning_rate, wb_step_stats* stats) {
+    if (h && !h->pending.empty()) return fail(WB_ERR_INVALID, "wb_step: collect the asynchronous steps first");
+    return guarded(h, [&] { enqueue_step(h, learning_rate); collect_step(h, stats); });
+}
+
+int wb_synchronize(wb_embedder* h) {
+    return guarded(h, [&] { WB_CUDA(cudaStreamSynchronize(h->stream)); });
+}
+
+int wb_enable_timing(wb_embedder* h, int enable) {
+    if (!h) return fail(WB_ERR_INVALID, "null handle");
+    h->timing = enable != 0;
+    return WB_OK;
+}
+
+int wb_get_phase_times(wb_embedder* h, double* ms6) {
+    if (!h || !ms6) return fail(WB_ERR_INVALID, "null argument");
+    if (!h->havePhase) return fail(WB_ERR_INVALID, "wb_get_phase_times: enable timing and run a synchronous step first");
+    std::copy(h->phaseMs, h->phaseMs + 6, ms6);
+    return WB_OK;
+}
+
+int wb_query_candidates(wb_embedder* h, int32_t nq, const int32_t* queries, int64_t* out_offsets, int32_t* out_ids, int64_t cap) {
+    if (h && (nq < 0 || (nq > 0 && (!queries || !out_offsets)))) return fail(WB_ERR_INVALID, "wb_query_candidates: bad arguments");
+    if (h && !h->pending.empty()) return fail(WB_ERR_INVALID, "wb_query_candidates: steps in flight");
+    int rc = WB_OK;
+    const int g = guarded(h, [&] {
+        const int n = h->n;
+        for (int i = 0; i < nq; ++i)
+            if (queries[i] < 0 || queries[i] >= n) throw std::runtime_error("wb_query_candidates: query id out of range");
+        out_offsets[0] = 0;
+        if (nq == 0 || n == 0) { for (int i = 0; i < nq; ++i) out_offsets[i + 1] = 0; return; }
+        cudaStream_t s = h->stream;
+        // index over class-maximum weights: the radius of class c is L * (w_v * maxW_c)^(1/d) (WeightedIndex.cpp:78-80)
+        std::vector<float> iwClass(n);
+        for (int v = 0; v < n; ++v) iwClass[v] = (float)(1.0 / std::pow(h->classMax[v], 1.0 / (double)h->dim)) * (1.0f - 1e-6f);
+        float* dIwClass = dalloc<float>(n);
+        double* dW = dalloc<double>(n);
+        double* dClassMax = dalloc<double>(n);
+        int* dQueries = dalloc<int>(nq);
+        int64_t* dCounts = dalloc<int64_t>(nq);
+        int64_t* dOffsets = dalloc<int64_t>(nq + 1);
+        int* dCursor = dalloc<int>(nq);
+        int* dOut = nullptr;
+        auto cleanup = [&] { cudaFree(dIwClass); cudaFree(dW); cudaFree(dClassMax); cudaFree(dQueries); cudaFree(dCounts); cudaFree(dOffsets); cudaFree(dCursor); if (dOut) cudaFree(dOut); };
+        try {
+            WB_CUDA(cudaMemcpyAsync(dIwClass, iwClass.data(), sizeof(float) * n, cudaMemcpyHostToDevice, s));
+            WB_CUDA(cudaMemcpyAsync(dW, h->weights.data(), sizeof(double) * n, cudaMemcpyHostToDevice, s));
+            WB_CUDA(cudaMemcpyAsync(dClassMax, h->classMax.data(), sizeof(double) * n, cudaMemcpyHostToDevice, s));
+            WB_CUDA(cudaMemcpyAsync(dQueries, queries, sizeof(int) * nq, cudaMemcpyHostToDevice, s));
+            WB_CUDA(cudaMemsetAsync(dCursor, 0, sizeof(int) * nq, s));
+            enqueue_index(h, dIwClass);
+            const float pruneL2 = (float)(h->opt.edge_length * h->opt.edge_length) * (1.0f + wb::kPruneSlack);
+            const int blocks = div_up((int64_t)nq * kFan, 256);
+            WB_DISPATCH_V(h->V, wb::k_candidates<V><<<blocks, 256, 0, s>>>(h->tree, h->x, dW, dClassMax, h->dim, h->opt.edge_length, pruneL2, h->iw,
+                                                                            dQueries, nq, dCounts, nullptr, dCursor, nullptr, 0));
+            std::vector<int64_t> counts(nq);
+            WB_CUDA(cudaMemcpyAsync(counts.data(), dCounts, sizeof(int64_t) * nq, cudaMemcpyDeviceToHost, s));
+            WB_CUDA(cudaStreamSynchronize(s));
+            for (int i = 0; i < nq; ++i) out_offsets[i + 1] = out_offsets[i] + counts[i];
+            const int64_t total = out_offsets[nq];
+            if (total > cap || (total > 0 && !out_ids)) { rc = WB_ERR_INVALID; g_lastError = "wb_query_candidates: output capacity too small"; cleanup(); return; }
+            if (total > 0) {
+                dOut = dalloc<int>(total);
+                WB_CUDA(cudaMemcpyAsync(dOffsets, out_offsets, sizeof(int64_t) * (nq + 1), cudaMemcpyHostToDevice, s));
+                WB_DISPATCH_V(h->V, wb::k_candidates<V><<<blocks, 256, 0, s>>>(h->tree, h->x, dW, dClassMax, h->dim, h->opt.edge_length, pruneL2, h->iw,
+                                                                                dQueries, nq, dCounts, dOffsets, dCursor, dOut, 1));
+                WB_CUDA(cudaMemcpyAsync(out_ids, dOut, sizeof(int) * total, cudaMemcpyDeviceToHost, s));
+                WB_CUDA(cudaStreamSynchronize(s));
+                for (int i = 0; i < nq; ++i) std::sort(out_ids + out_offsets[i], out_ids + out_offsets[i + 1]);
+            }
+        } catch (...) { cleanup(); throw; }
+        cleanup();
+    });
+    return g != WB_OK ? g : rc;
+}
+
+}  // extern "C"
