@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py - WEmbed gradient-descent step throughput on B200 (see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4|small]
+
+One "step" = one WembedEmbedder::calculateStep over the whole graph (index rebuild, attractive and
+repulsive forces, Adam, recentring, observables).  Metric = directed edge-force updates per second =
+2m * steps / seconds (BASELINE.json "edge-force updates/sec"); steps/s is reported beside it.
+
+Workload (N = 1): BASELINE.json configs[2] - synthetic 2-D geometric random graph, n = 1M, average degree 10,
+embedded in d = 8 with default options (Adam, ExponentialCooling lr 10, L = 1), trajectory started from the
+reference's initial layout (uniform cube) with W warm-up steps then K timed steps.
+
+Lines printed (one JSON object on stdout, rank 0):
+  value     device-resident throughput: K asynchronous steps, CUDA events on the handle's stream
+  e2e       through the blocking C ABI with host buffers: wb_set_coordinates(host) + K x wb_step (per-step
+            D2H of the observables) + wb_get_coordinates(host), all inside the timed region
+  roofline  dominant kernel (repulsion walk) - algorithmic bytes / measured time vs measured HBM peak
+  cpu_baseline  oracle port (oracle/wembed_port.cpp, OpenMP) timed for one step of the same state
+--impl reference times the reference's own C++ (oracle/_ref, SNN index) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n, avg_degree, d, family)
+    "small": (20_000, 10, 8, "geometric"),
+    "c2": (100_000, 10, 4, "geometric"),
+    "c3": (1_000_000, 10, 8, "geometric"),
+    "c4": (1_000_000, 20, 8, "heavy_tailed"),
+}
+
+
+def lr_schedule(it, lr0=10.0, cooling=0.995, warmup=20):
+    """ExponentialCoolingSchedule + warm-up (LRScheduler.cpp:7-17), iterations are 1-based."""
+    lr = lr0 * cooling ** float(it)
+    return lr * it / warmup if it < warmup else lr
+
+
+def make_workload(name, rank=0, world=1):
+    from wembed_b200 import cabi
+    from wembed_b200.datasets import degree_weights, geometric_graph, heavy_tailed_graph, initial_coordinates
+    n, deg, d, family = WORKLOADS[name]
+    seed = 42 + rank  # weak scaling: every rank embeds its own graph of the named shape
+    cache = os.path.join(ROOT, "gpurun_out", f"_wl_{name}_{seed}.npz")
+    if os.path.exists(cache):
+        z = np.load(cache)
+        edges = z["edges"]
+    else:
+        edges = geometric_graph(n, deg, seed)[0] if family == "geometric" else heavy_tailed_graph(n, deg, seed=seed)[0]
+        try:
+            os.makedirs(os.path.dirname(cache), exist_ok=True)
+            np.savez(cache, edges=edges)
+        except OSError:
+            pass
+    rp, col = cabi.csr_from_edges(n, edges)
+    w = degree_weights(n, edges, d)
+    x0 = initial_coordinates(n, d, seed=1234)
+    return dict(name=name, n=n, d=d, m=len(edges), edges=edges, row_ptr=rp, col=col, weights=w, x0=x0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes_per_step(n, m, d):
+    """B_alg = 8m + 24n + 36nd (fp32 state, int32 ids, every array moved once)."""
+    return 8 * m + 24 * n + 36 * n * d
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    from wembed_b200 import build, cabi
+    build.build()
+    wl = make_workload(args.workload, rank, world)
+    n, d, m = wl["n"], wl["d"], wl["m"]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    dev = cabi.DeviceEmbedder(wl["row_ptr"], wl["col"], embedding_dimension=d, device=local, seed=1234)
+    dev.set_weights(wl["weights"])
+    dev.set_coordinates(wl["x0"])
+    it = 0
+    for _ in range(args.warmup):
+        it += 1
+        dev.step(lr_schedule(it))
+    x_start = dev.coordinates()          # state at the start of the timed window (also the CPU baseline's input)
+    launches_per_step = None
+
+    # ---- value: device-resident, K async steps, one collect at the end --------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    launches0 = dev.launch_count()
+    dev.mark(0)
+    stats = []
+    inflight = 0
+    for _ in range(args.steps):
+        it += 1
+        dev.step_async(lr_schedule(it))
+        inflight += 1
+        if inflight >= 32:
+            stats.append(dev.step_collect())
+            inflight -= 1
+    dev.mark(1)
+    while inflight:
+        stats.append(dev.step_collect())
+        inflight -= 1
+    dt = dev.elapsed_ms(0, 1) * 1e-3     # CUDA events on the stream the kernels are launched on
+    launches = dev.launch_count() - launches0
+    barrier()
+    clocks = sampler.stop()
+    t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+
+    # ---- per-phase device times (CUDA events on the handle's stream) over the same trajectory window -------
+    dev.set_coordinates(x_start)
+    dev.enable_timing(True)
+    it_p = args.warmup
+    phases = []
+    for _ in range(min(args.steps, 20)):
+        it_p += 1
+        dev.step(lr_schedule(it_p))
+        phases.append(dev.phase_times())
+    dev.enable_timing(False)
+    ph = {k: float(np.mean([p[k] for p in phases])) for k in phases[0]}
+
+    # ---- e2e: blocking C ABI, host buffers in and out ---------------------------------------------------------
+    it_e = args.warmup
+    barrier()
+    t0 = time.perf_counter()
+    dev.mark(2)
+    dev.set_coordinates(x_start)
+    for _ in range(args.steps):
+        it_e += 1
+        dev.step(lr_schedule(it_e))
+    x_end = dev.coordinates()
+    dev.mark(3)
+    de_events = dev.elapsed_ms(2, 3) * 1e-3
+    barrier()
+    de = max(time.perf_counter() - t0, de_events)   # host-visible time of the blocking calls (>= the device time)
+    t = torch.tensor([de], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    de = float(t.item())
+    assert np.isfinite(x_end).all()
+
+    if rank != 0:
+        return
+    units = 2.0 * m * args.steps * world
+    peak, peak_src = measured_peak_gbs()
+    dom = max(("index", "attract_update", "repel", "recentre_observe"), key=lambda k: ph[k])
+    bytes_step = algorithmic_bytes_per_step(n, m, d)
+    dom_bytes = {  # algorithmic bytes of each kernel group (DESIGN.md "Kernels")
+        "repel": (4 * d + 8) * n * 2 + 4 * d * n + 8 * n,        # sorted points + ids/iw read once, force + loss written, CSR row ends
+        "attract_update": 8 * m + 4 * (n + 1) + 4 * n + 4 * d * n * 7 + 8 * n,  # CSR, iw, x, forceRep, m, v read; m, v, xnew written
+        "index": 4 * d * n * 2 + 16 * n * 2,
+        "recentre_observe": 4 * d * n * 3,
+    }[dom]
+    achieved = dom_bytes / (ph[dom] * 1e-3) / 1e9
+    out = {
+        "metric": "edge_force_updates_per_s", "value": units / dt, "unit": "directed-edge force updates/s",
+        "steps_per_s": args.steps / dt, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {WORKLOADS[args.workload][3]} graph n={n} m={m} d={d}, default options, "
+                               f"trajectory steps {args.warmup + 1}..{args.warmup + args.steps} from the uniform-cube layout",
+                   "per_gpu": "one independent graph of this shape per GPU (replicas, weak scaling)",
+                   "l2": "working set (x, m, v, CSR, index: ~260 MB at c3) exceeds the 126 MB L2; no flush needed"},
+        "e2e": {"value": units / de, "unit": "directed-edge force updates/s", "steps_per_s": args.steps / de,
+                "h2d_bytes_per_step": n * d * 8 / args.steps + 8, "d2h_bytes_per_step": n * d * 8 / args.steps + 8 * (8 + 4 * ((d + 3) // 4)),
+                "what": "wb_set_coordinates(host doubles) + K blocking wb_step (observables copied to the host every step) + wb_get_coordinates(host doubles)"},
+        "gpu_launches": None,
+        "phases_ms": ph,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes": dom_bytes,
+                     "whole_step": {"algorithmic_bytes": bytes_step, "achieved": bytes_step / (ph["total"] * 1e-3) / 1e9,
+                                    "frac": bytes_step / (ph["total"] * 1e-3) / 1e9 / peak}},
+        "clocks": clocks,
+        "last_step": {k: stats[-1][k] for k in ("loss_attract", "loss_repel", "rel_displacement", "num_repulsion_pairs", "num_candidates")},
+    }
+    out["gpu_launches"] = int(launches)   # kernels of libwembed_b200.so inside the timed `value` region (wb_launch_count)
+    if not args.no_cpu:
+        out["cpu_baseline"] = cpu_baseline(wl, x_start, args.warmup)
+    print(json.dumps(out), flush=True)
+
+
+def cpu_baseline(wl, x_start, iteration):
+    """One step of the oracle port from the GPU's state at the start of the timed window (bounded sample)."""
+    import oracle
+    oracle.build("port")
+    n, d, m = wl["n"], wl["d"], wl["m"]
+    cores = os.cpu_count() or 1
+    cpu = oracle.CpuEmbedder("port", wl["edges"], n=n, embeddingDimension=d, init_state=False, numThreads=cores)
+    cpu.set_weights(wl["weights"])
+    cpu.set_coordinates(x_start)
+    t0 = time.perf_counter()
+    cpu.step()
+    dt = time.perf_counter() - t0
+    cpu.close()
+    return {"value": 2.0 * m / dt, "unit": "directed-edge force updates/s", "steps_per_s": 1.0 / dt, "cores": cores, "kind": "port",
+            "sample": f"1 step of the same workload from the device state after {iteration} steps (oracle/wembed_port.cpp, OpenMP, fp64)"}
+
+
+def run_reference(args):
+    """The reference's own C++ (oracle/_ref, its SNN index) on a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import oracle
+    from wembed_b200.datasets import degree_weights, geometric_graph, heavy_tailed_graph, initial_coordinates
+    n_full, deg, d, family = WORKLOADS[args.workload]
+    kind = "reference" if oracle.have("ref") or oracle.build("ref") else "port"
+    if kind == "port":
+        oracle.build("port")
+    n = min(n_full, 20_000 if kind == "reference" else 100_000)
+    edges = geometric_graph(n, deg, 42)[0] if family == "geometric" else heavy_tailed_graph(n, deg, seed=42)[0]
+    cores = os.cpu_count() or 1
+    cpu = oracle.CpuEmbedder("ref" if kind == "reference" else "port", edges, n=n, embeddingDimension=d, init_state=False, numThreads=cores)
+    cpu.set_weights(degree_weights(n, edges, d))
+    cpu.set_coordinates(initial_coordinates(n, d, seed=1234))
+    for _ in range(args.warmup):
+        cpu.step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu.step()
+    dt = time.perf_counter() - t0
+    m = len(edges)
+    value = 2.0 * m * args.steps / dt
+    sample = (f"{family} graph n={n} m={m} d={d} (same generator and options as the workload, smaller n: the reference's SNN index "
+              f"scans O(n^(1-1/d)) points per query and cannot finish a step at n={n_full}); throughput is per directed edge")
+    print(json.dumps({
+        "impl": "reference", "metric": "edge_force_updates_per_s", "value": value, "unit": "directed-edge force updates/s",
+        "steps_per_s_on_sample": args.steps / dt, "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload} (bounded sample)"},
+        "cpu_baseline": {"value": value, "unit": "directed-edge force updates/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "directed-edge force updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 10:
+            args.steps = 10      # bounded: the whole reference run must end within minutes
+        if args.warmup > 5:
+            args.warmup = 5
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

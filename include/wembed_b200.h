@@ -163,6 +163,16 @@ int wb_query_candidates(wb_embedder* h, int32_t nq, const int32_t* queries, int6
 int wb_enable_timing(wb_embedder* h, int enable);
 int wb_get_phase_times(wb_embedder* h, double* ms6);
 
+/* -- measurement ------------------------------------------------------------------------- */
+
+/* Records CUDA event `slot` (0..7) on the handle's stream; wb_elapsed_ms waits for event `to` and returns the
+ * device time between two recorded events.  This is how bench.py times steps on the launching stream. */
+int wb_mark(wb_embedder* h, int slot);
+int wb_elapsed_ms(wb_embedder* h, int from, int to, double* ms);
+/* Number of kernels of this library launched through the handle since wb_create
+ * (the CUB radix-sort call of the index rebuild is counted as one). */
+int64_t wb_launch_count(wb_embedder* h);
+
 #ifdef __cplusplus
 }
 #endif

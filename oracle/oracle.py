@@ -157,6 +157,15 @@ class CpuEmbedder:
         s = self._get("get_stats", (8,))
         return dict(zip(self.STATS, s.tolist()))
 
+    def near_threshold(self, tau=1e-5):
+        """Port only: vertices owning a pair within tau*L of the hinge threshold at the current coordinates."""
+        assert self.kind == "port"
+        f = self._l.port_flag_near_threshold
+        f.restype, f.argtypes = None, [C.c_void_p, C.c_double, C.POINTER(C.c_uint8)]
+        out = np.zeros(self.n, np.uint8)
+        f(self._h, float(tau), out.ctypes.data_as(C.POINTER(C.c_uint8)))
+        return out.astype(bool)
+
     def candidates(self, v):
         cap = 1024
         while True:

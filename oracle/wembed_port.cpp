@@ -581,6 +581,34 @@ void port_get_stats(void* h, double* s) {
     s[ORC_NUM_REP_PAIRS] = static_cast<double>(p->numRepPairs);
     s[ORC_RESERVED] = static_cast<double>(p->numNodeVisits);
 }
+// Test helper (port only): flags[v] = 1 if v owns a pair - neighbour or not - whose weighted distance dist*ws lies
+// within tau*L of the hinge threshold L, i.e. a pair on which fp32 and fp64 may legitimately disagree.
+void port_flag_near_threshold(void* h, double tau, uint8_t* flags) {
+    auto* p = static_cast<Port*>(h);
+    const int n = p->n, d = p->d;
+    const double L = p->o.edgeLength;
+    p->rebuildIndex(false);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int v = 0; v < n; v++) {
+        bool near = false;
+        const double* q = &p->x[(size_t)v * d];
+        for (int e = p->rowPtr[v]; e < p->rowPtr[v + 1] && !near; e++) {
+            const int u = p->col[e];
+            near = std::abs(p->distance(q, &p->x[(size_t)u * d]) * p->iw[v] * p->iw[u] - L) <= tau * L;
+        }
+        if (!near) {
+            const double rq = L * (1.0 + 2.0 * tau) * std::pow(p->w[v], 1.0 / d);
+            p->tree.query(q, rq * rq, 2.0 / d, [&](int pos) {
+                const int u = p->tree.order[pos];
+                if (u == v || near) return;
+                const double dist = p->distance(q, &p->tree.pts[(size_t)pos * d]);
+                if (std::abs(dist * p->iw[v] * p->iw[u] - L) <= tau * L) near = true;
+            });
+        }
+        flags[v] = near ? 1 : 0;
+    }
+}
+
 int64_t port_candidates(void* h, int32_t v, int32_t* out, int64_t cap) {
     auto* p = static_cast<Port*>(h);
     p->rebuildIndex(true);

@@ -1,0 +1,98 @@
+"""Generates tests/golden/*.npz from the reference's own sources (oracle/_ref, built in place from /root/reference
+by oracle/Makefile).  Run here, where the reference checkout exists:  python tests/golden/make_golden.py
+
+The fixtures pin the CPU port (tests -m "not gpu") and, on the GPU box where /root/reference does not exist, the
+device path (tests -m gpu).  Index = SNN (the only index whose source is in the reference tree).
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import oracle  # noqa: E402
+from helpers import SMALL_GRAPH, ring_graph  # noqa: E402
+from wembed_b200.datasets import geometric_graph  # noqa: E402
+
+
+def trace(cpu, steps, forces=True):
+    out = {"x0": cpu.coordinates(), "w": cpu.weights()}
+    xs, fs, st = [], [], []
+    for _ in range(steps):
+        cpu.step()
+        s = cpu.stats()
+        xs.append(cpu.coordinates())
+        if forces:
+            fs.append(cpu.forces())
+        st.append([s["loss_attract"], s["loss_repel"], s["lr"], s["rel_displacement"], s["rel_loss_improvement"], s["iteration"]])
+    out["x"] = np.stack(xs)
+    if forces:
+        out["f"] = np.stack(fs)
+    out["stats"] = np.asarray(st)
+    return out
+
+
+def main():
+    assert oracle.build("ref"), "reference checkout not available"
+    # (a) tests/TestDeterminism.cpp protocol: ring-64 (+1, +7 chords), d = 2, seed 1234, all-coincident start, 25 steps
+    ring = ring_graph(64)
+    cpu = oracle.CpuEmbedder("ref", ring, seed=1234, embeddingDimension=2, maxIterations=1000)
+    cpu.set_coordinates(np.zeros((64, 2)))
+    g = trace(cpu, 25)
+    np.savez_compressed(os.path.join(HERE, "ring64_d2_coincident.npz"), edges=ring, **g)
+    # (a') same graph, the constructor's random layout (Rand::setSeed(1234)), 10 steps
+    cpu = oracle.CpuEmbedder("ref", ring, seed=1234, embeddingDimension=2, maxIterations=1000)
+    g = trace(cpu, 10)
+    np.savez_compressed(os.path.join(HERE, "ring64_d2_random.npz"), edges=ring, **g)
+    # (b) assets/small_graph.edg, defaults (d = 4), to convergence
+    for seed in (1, 2):
+        cpu = oracle.CpuEmbedder("ref", SMALL_GRAPH, seed=seed)
+        x0, w = cpu.coordinates(), cpu.weights()
+        iters = cpu.run()
+        s = cpu.stats()
+        np.savez_compressed(os.path.join(HERE, f"small_graph_seed{seed}.npz"), edges=SMALL_GRAPH, x0=x0, w=w, iterations=iters,
+                            x_final=cpu.coordinates(), loss_final=s["loss_attract"] + s["loss_repel"], csr_row=cpu.csr()[0], csr_col=cpu.csr()[1])
+    # (c) geometric graph n = 600, d = 4 and d = 8: 6 steps with forces; candidate sets at the state after step 3
+    for d in (4, 8):
+        n = 600
+        edges, _ = geometric_graph(n, 10, seed=5)
+        cpu = oracle.CpuEmbedder("ref", edges, n=n, seed=99, embeddingDimension=d)
+        x0 = cpu.coordinates().astype(np.float32).astype(np.float64)   # fp32-exact start
+        cpu.set_coordinates(x0)
+        g = trace(cpu, 3)
+        queries = np.arange(0, n, 30, dtype=np.int32)
+        cands = [np.sort(cpu.candidates(int(q))) for q in queries]
+        g2 = trace(cpu, 3)
+        rp, col = cpu.csr()
+        np.savez_compressed(os.path.join(HERE, f"geo600_d{d}.npz"), edges=edges, x0=x0, w=g["w"], x=np.concatenate([g["x"], g2["x"]]),
+                            f=np.concatenate([g["f"], g2["f"]]), stats=np.concatenate([g["stats"], g2["stats"]]), queries=queries,
+                            cand_offsets=np.cumsum([0] + [len(c) for c in cands]), cand_ids=np.concatenate(cands), csr_row=rp, csr_col=col)
+    # (d) option coverage on a small geometric graph: Simple optimizer, centre force, unit weights, dimension hint, scales
+    n = 300
+    edges, _ = geometric_graph(n, 8, seed=11)
+    variants = {
+        "simple": dict(optimizerType=0, simpleOptMaxDisplacement=0.5),
+        "centre": dict(centreScale=0.05),
+        "unit": dict(weightType=0),
+        "hint": dict(dimensionHint=2.0, embeddingDimension=3),
+        "scales": dict(attractionScale=2.0, repulsionScale=0.5, edgeLength=1.5),
+        "adaptive": dict(lrScheduleType=1, lossRateWindow=3, lrAdaptPatience=2),
+    }
+    out = {}
+    for name, o in variants.items():
+        cpu = oracle.CpuEmbedder("ref", edges, n=n, seed=7, **o)
+        x0 = cpu.coordinates().astype(np.float32).astype(np.float64)
+        cpu.set_coordinates(x0)
+        g = trace(cpu, 4)
+        for k, v in g.items():
+            out[f"{name}_{k}"] = v
+    np.savez_compressed(os.path.join(HERE, "geo300_options.npz"), edges=edges, **out)
+    print("golden fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()

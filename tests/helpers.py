@@ -59,3 +59,46 @@ def make_problem(n, d, avg_degree=10.0, seed=42):
     w = degree_weights(n, edges, d)
     x0 = initial_coordinates(n, d, seed=1234)
     return edges, w, x0
+
+
+# ---- test-side restatement of the host scalar logic (used until a test drives the C++ facade instead) ----------
+class LossMonitor:
+    """ConvergenceMonitor (src/embeddingLib/src/embedder/ConvergenceMonitor.cpp:6-42)."""
+
+    def __init__(self, tol=1e-3, patience=50, alpha=0.3, window=30):
+        self.tol, self.patience, self.alpha = tol, patience, alpha
+        self.ring = [0.0] * (max(1, window) + 1)
+        self.head = self.count = self.observed = self.stagnant = 0
+        self.smoothed, self.rate = 0.0, float("inf")
+
+    def observe(self, loss):
+        self.smoothed = loss if self.observed == 0 else self.alpha * loss + (1 - self.alpha) * self.smoothed
+        self.observed += 1
+        self.ring[self.head] = self.smoothed
+        self.head = (self.head + 1) % len(self.ring)
+        self.count = min(self.count + 1, len(self.ring))
+        if self.count >= len(self.ring):
+            start = self.ring[self.head]
+            self.rate = (start - self.smoothed) / max(abs(start), 1e-12)
+        else:
+            self.rate = float("inf")
+        self.stagnant = self.stagnant + 1 if self.rate < self.tol else 0
+
+    def converged(self):
+        return self.stagnant >= self.patience
+
+
+def run_to_convergence(dev, o):
+    """WembedEmbedder::calculateEmbedding loop (WembedEmbedder.cpp:65-86) over a DeviceEmbedder; ExponentialCooling only."""
+    mon = LossMonitor(o.get("stopLossTol", 1e-3), o.get("stopLossPatience", 50), o.get("lossSmoothingFactor", 0.3), o.get("lossRateWindow", 30))
+    settled, it, st = 0, 0, None
+    while it < o.get("maxIterations", 10000):
+        if o.get("stopCriterion", 1) == 0 and settled >= o.get("stopDisplacementPatience", 5):
+            break
+        if o.get("stopCriterion", 1) == 1 and mon.converged():
+            break
+        it += 1
+        st = dev.step(lr_exponential(it, o.get("learningRate", 10.0), o.get("lrCoolingFactor", 0.995), o.get("warmupSteps", 20)))
+        settled = settled + 1 if st["rel_displacement"] < o.get("stopDisplacementTol", 3e-4) else 0
+        mon.observe(st["loss_attract"] + st["loss_repel"])
+    return it, st

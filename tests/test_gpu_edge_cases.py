@@ -1,0 +1,121 @@
+"""Edge cases of the device path: empty / tiny graphs, isolated vertices, hubs, duplicate points, round trips."""
+import numpy as np
+import pytest
+
+import oracle
+from helpers import SMALL_GRAPH, lr_exponential, run_to_convergence
+
+pytestmark = pytest.mark.gpu
+
+
+def test_empty_and_single_vertex(device_lib):
+    dev = device_lib.DeviceEmbedder(np.zeros(1, np.int32), np.zeros(0, np.int32))
+    st = dev.step(1.0)
+    assert st["iteration"] == 1 and st["loss_attract"] == 0.0
+    assert dev.coordinates().shape == (0, 4)
+    one = device_lib.DeviceEmbedder(np.array([0, 0], np.int32), np.zeros(0, np.int32), embedding_dimension=3)
+    one.set_coordinates(np.array([[1.0, 2.0, 3.0]]))
+    one.set_weights(np.array([1.0]))
+    st = one.step(1.0)                                # WembedEmbedder.cpp:19-21: graphSize() <= 1 -> only the counter moves
+    assert st["iteration"] == 1
+    np.testing.assert_array_equal(one.coordinates(), [[1.0, 2.0, 3.0]])
+
+
+def test_two_vertices_against_oracle(device_lib, port_lib):
+    for edges, n in (([(0, 1)], 2), ([(0, 1)], 3)):      # n = 3: vertex 2 is isolated
+        rp, col = device_lib.csr_from_edges(n, edges)
+        x0 = np.array([[0.0, 0.0], [3.0, 4.0], [0.5, 0.1]])[:n]
+        w = np.ones(n)
+        cpu = oracle.CpuEmbedder("port", edges, n=n, embeddingDimension=2, init_state=False)
+        dev = device_lib.DeviceEmbedder(rp, col, embedding_dimension=2, keep_forces=1)
+        for e in (cpu, dev):
+            e.set_weights(w)
+            e.set_coordinates(x0)
+        for it in range(1, 6):
+            cpu.step()
+            st = dev.step(lr_exponential(it))
+            assert np.abs(cpu.forces() - dev.forces()).max() <= 1e-5 * max(1e-30, np.abs(cpu.forces()).max())
+            assert np.abs(cpu.coordinates() - dev.coordinates()).max() <= 1e-5 * max(1.0, np.abs(cpu.coordinates()).max())
+            np.testing.assert_allclose(st["loss_attract"], cpu.stats()["loss_attract"], rtol=1e-5, atol=1e-7)
+            cpu.set_coordinates(dev.coordinates())     # one trajectory: fp32 rounding must not feed back through the dynamics
+
+
+def test_star_hub_and_isolated(device_lib, port_lib):
+    """One hub adjacent to everything (row length n-1), the rest leaves, plus isolated vertices."""
+    n, d = 5000, 4
+    edges = [(0, v) for v in range(1, n - 50)]
+    rng = np.random.default_rng(0)
+    x0 = (rng.random((n, d)) * 4).astype(np.float32).astype(np.float64)
+    from wembed_b200.datasets import degree_weights
+    w = degree_weights(n, np.asarray(edges), d)
+    rp, col = device_lib.csr_from_edges(n, edges)
+    cpu = oracle.CpuEmbedder("port", edges, n=n, embeddingDimension=d, init_state=False)
+    dev = device_lib.DeviceEmbedder(rp, col, embedding_dimension=d, keep_forces=1)
+    for e in (cpu, dev):
+        e.set_weights(w)
+        e.set_coordinates(x0)
+    for it in range(1, 4):
+        cpu.step()
+        st = dev.step(lr_exponential(it))
+        fr, fd = cpu.forces(), dev.forces()
+        # the hub sums 4949 terms in fp32: tolerance relative to the sum of magnitudes, 1e-5 elsewhere
+        assert np.abs(fr[1:] - fd[1:]).max() <= 1e-5 * np.abs(fr).max()
+        assert np.abs(fr[0] - fd[0]).max() <= 1e-5 * np.abs(fr).max()
+        assert abs(st["num_repulsion_pairs"] - cpu.stats()["num_rep_pairs"]) <= 8
+        cpu.set_coordinates(dev.coordinates())
+
+
+def test_duplicate_points_use_tie_break(device_lib, port_lib):
+    """Pairs of exactly coincident vertices (neighbours and non-neighbours) inside an otherwise generic layout."""
+    n, d = 400, 3
+    rng = np.random.default_rng(2)
+    edges = [(i, i + 1) for i in range(n - 1)] + [(i, i + 5) for i in range(n - 5)]
+    x0 = (rng.random((n, d)) * 5).astype(np.float32).astype(np.float64)
+    x0[10] = x0[11]          # coincident neighbours  -> attraction tie-break
+    x0[100] = x0[300]        # coincident non-neighbours -> repulsion tie-break
+    x0[200] = x0[201] = x0[350]
+    w = np.ones(n)
+    rp, col = device_lib.csr_from_edges(n, edges)
+    cpu = oracle.CpuEmbedder("port", edges, n=n, seed=1234, embeddingDimension=d, init_state=False)
+    dev = device_lib.DeviceEmbedder(rp, col, embedding_dimension=d, keep_forces=1, seed=1234)
+    for e in (cpu, dev):
+        e.set_weights(w)
+        e.set_coordinates(x0)
+    cpu.step()
+    dev.step(lr_exponential(1))
+    fr, fd = cpu.forces(), dev.forces()
+    assert np.abs(fr - fd).max() <= 1e-5 * np.abs(fr).max()
+    assert np.abs(fr[[10, 11, 100, 300, 200, 201, 350]]).max() > 0
+
+
+def test_coordinate_and_weight_round_trip(device_lib):
+    n, d = 1000, 5
+    rng = np.random.default_rng(4)
+    edges = [(i, (i + 1) % n) for i in range(n)]
+    rp, col = device_lib.csr_from_edges(n, edges)
+    dev = device_lib.DeviceEmbedder(rp, col, embedding_dimension=d)
+    x = rng.normal(size=(n, d)) * 100
+    w = rng.random(n) + 0.1
+    dev.set_coordinates(x)
+    dev.set_weights(w)
+    np.testing.assert_array_equal(dev.coordinates(), x.astype(np.float32).astype(np.float64))
+    np.testing.assert_array_equal(dev.weights(), w)
+    with pytest.raises(device_lib.WbError):
+        dev.set_weights(np.zeros(n))
+    with pytest.raises(device_lib.WbError):
+        dev.forces()           # keep_forces was not requested
+
+
+def test_small_graph_reaches_zero_loss(device_lib):
+    """BASELINE.json configs[0]: assets/small_graph.edg, default options -> converges to loss exactly 0 like the reference."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "small_graph_seed1.npz"))
+    rp, col = device_lib.csr_from_edges(5, SMALL_GRAPH)
+    np.testing.assert_array_equal(rp, g["csr_row"])
+    np.testing.assert_array_equal(col, g["csr_col"])
+    dev = device_lib.DeviceEmbedder(rp, col, embedding_dimension=4, seed=1)
+    dev.set_weights(g["w"])
+    dev.set_coordinates(g["x0"])
+    iters, st = run_to_convergence(dev, {})
+    assert st["loss_attract"] + st["loss_repel"] == 0.0
+    assert 0.5 * int(g["iterations"]) <= iters <= 2.0 * int(g["iterations"]), (iters, int(g["iterations"]))

@@ -23,7 +23,7 @@ EXPORTS = (
     "wb_abi_version", "wb_build_info", "wb_last_error", "wb_device_count", "wb_options_default", "wb_create", "wb_destroy",
     "wb_set_coordinates", "wb_set_weights", "wb_get_coordinates", "wb_get_weights", "wb_get_forces", "wb_reset_optimizer",
     "wb_set_iteration", "wb_step", "wb_step_async", "wb_step_collect", "wb_synchronize", "wb_query_candidates",
-    "wb_enable_timing", "wb_get_phase_times",
+    "wb_enable_timing", "wb_get_phase_times", "wb_mark", "wb_elapsed_ms", "wb_launch_count",
 )
 
 
@@ -77,6 +77,8 @@ def lib():
         "wb_step_collect": (C.c_int, [H, C.POINTER(WbStepStats)]), "wb_synchronize": (C.c_int, [H]),
         "wb_query_candidates": (C.c_int, [H, i32, ip, lp, ip, i64]),
         "wb_enable_timing": (C.c_int, [H, C.c_int]), "wb_get_phase_times": (C.c_int, [H, dp]),
+        "wb_mark": (C.c_int, [H, C.c_int]), "wb_elapsed_ms": (C.c_int, [H, C.c_int, C.c_int, dp]),
+        "wb_launch_count": (C.c_int64, [H]),
     }
     for name, (res, args) in sig.items():
         f = getattr(l, name)
@@ -180,6 +182,17 @@ class DeviceEmbedder:
         out = np.empty(6, np.float64)
         self._check(self._l.wb_get_phase_times(self._h, _dp(out)))
         return dict(zip(("index", "attract_update", "repel", "optimizer", "recentre_observe", "total"), out.tolist()))
+
+    def mark(self, slot):
+        self._check(self._l.wb_mark(self._h, int(slot)))
+
+    def elapsed_ms(self, a, b):
+        out = C.c_double()
+        self._check(self._l.wb_elapsed_ms(self._h, int(a), int(b), C.byref(out)))
+        return out.value
+
+    def launch_count(self):
+        return int(self._l.wb_launch_count(self._h))
 
     def query_candidates(self, queries):
         q = np.ascontiguousarray(queries, dtype=np.int32)

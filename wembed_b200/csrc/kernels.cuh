@@ -363,6 +363,290 @@ __global__ void __launch_bounds__(256) k_repulse(const TreeView t, const int* __
 }
 
 // ---------------------------------------------------------------------------------------------
+// Repulsion, shared walk (the production variant).
+//
+// Why: the per-group walk above re-reads every box it tests from L2 (64 B + per test at d = 8) and is bound by
+// L2 -> SM bandwidth.  Queries that are adjacent in Morton order visit largely the same boxes (measured overlap at
+// n = 1e5, d = 8: 7x for boxes, 4x for points over 32 consecutive queries), so here ONE warp walks the hierarchy
+// once for its 32 queries.  A stack entry is (level, node, 32-bit mask of the queries that still need the node).
+// Popping a node, lane (g, c) = (lane / 8, lane % 8) loads child c once into registers; the queries of the mask are
+// tested four at a time (one per lane group g) against the eight children, reading the query from shared memory.
+// A child is pushed with the mask of the queries that passed it, so every query performs exactly the tests of its
+// own private walk - only the loads are shared.  At the point level the tester lane evaluates the exact predicate
+// and hands hits to the lane that owns the query, which applies the neighbour filter and accumulates in registers
+// in (pop, round, lane) order: no atomics, deterministic, no cross-lane reduction of forces.
+template <int V>
+__global__ void __launch_bounds__(256) k_repulse_shared(const TreeView t, const int* __restrict__ rowPtr, const int* __restrict__ col,
+                                                        int n, const ForceParams fp, float4* __restrict__ forceRep,
+                                                        float* __restrict__ lossRep, int* __restrict__ coincident,
+                                                        double* __restrict__ partials) {
+    constexpr int WARPS = 8, STACK = 8 * kMaxLevels;
+    __shared__ float4 sQ[WARPS][32][V];
+    __shared__ float sIw[WARPS][32];
+    __shared__ unsigned long long sStack[WARPS][STACK];
+    __shared__ int sList[WARPS][32];
+    __shared__ double smem[8 * 2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = lane & (kFan - 1), g = lane >> kFanLog2;
+    const uint32_t ltMask = (1u << lane) - 1u;
+    const int qBase = (blockIdx.x * WARPS + warp) * 32;
+    const int qi = qBase + lane;
+    const bool valid = qi < n;
+    float4 q[V];
+    float iwq = 1.f;
+    int v = -1, rowBegin = 0, rowEnd = 0;
+    if (valid) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) q[k] = __ldg(t.lo[0] + (int64_t)k * t.stride[0] + qi);
+        iwq = __ldg(t.bound[0] + qi);
+        v = __ldg(t.ids + qi);
+        rowBegin = __ldg(rowPtr + v);
+        rowEnd = __ldg(rowPtr + v + 1);
+    } else {
+#pragma unroll
+        for (int k = 0; k < V; ++k) q[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) sQ[warp][lane][k] = q[k];
+    sIw[warp][lane] = iwq;
+    float4 acc[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float loss = 0.f;
+    int nCoincident = 0, nPairs = 0, nTests = 0;
+    const float L = fp.edgeLength;
+
+    const uint32_t validMask = __ballot_sync(0xffffffffu, valid);
+    int sp = 0;
+    if (validMask != 0u) {
+        if (lane == 0) sStack[warp][0] = ((unsigned long long)(((uint32_t)(t.numLevels + 1) << 28) | 0u) << 32) | validMask;
+        sp = 1;
+    }
+    __syncwarp();
+    while (sp > 0) {
+        const unsigned long long entry = sStack[warp][--sp];
+        const uint32_t m = (uint32_t)entry, head = (uint32_t)(entry >> 32);
+        const int lv = (int)(head >> 28) - 1;                 // level of the children
+        const int idx = (int)(head & 0x0fffffffu) * kFan + c; // child of this lane
+        float4 lo[V], hi[V];
+        const int64_t st = t.stride[lv];
+#pragma unroll
+        for (int k = 0; k < V; ++k) lo[k] = __ldg(t.lo[lv] + k * st + idx);
+        if (lv == 0) {
+#pragma unroll
+            for (int k = 0; k < V; ++k) hi[k] = lo[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < V; ++k) hi[k] = __ldg(t.hi[lv] + k * st + idx);
+        }
+        const float bnd = __ldg(t.bound[lv] + idx);
+        const int p = __popc(m);
+        if ((m >> lane) & 1u) sList[warp][__popc(m & ltMask)] = lane;
+        __syncwarp();
+        uint32_t mine = 0u;
+        for (int r = 0; r * 4 < p; ++r) {
+            const int slot = r * 4 + g;
+            const bool active = slot < p;
+            const int qq = active ? sList[warp][slot] : 0;
+            float4 qv[V];
+#pragma unroll
+            for (int k = 0; k < V; ++k) qv[k] = sQ[warp][qq][k];
+            const float iwqq = sIw[warp][qq];
+            const float d2 = box_dist2<V>(qv, lo, hi);
+            const float s = iwqq * bnd;
+            const bool pass = active && (d2 * s * s <= fp.pruneL2);
+            if (lv > 0) {
+                if (pass) mine |= 1u << qq;
+            } else {
+                if (active) ++nTests;
+                bool hit = pass && (idx != qBase + qq);
+                if (hit) {
+                    const float dist = sqrtf(d2);
+                    if (dist > 0.f) hit = dist * s <= L;       // exact predicate; dist <= 0 is the coincident case
+                }
+                uint32_t hb = __ballot_sync(0xffffffffu, hit);
+                while (hb) {
+                    const int hl = __ffs(hb) - 1;
+                    hb &= hb - 1u;
+                    const int owner = __shfl_sync(0xffffffffu, qq, hl);
+                    const int pidx = __shfl_sync(0xffffffffu, idx, hl);
+                    if (lane == owner) {
+                        float4 pu[V];
+#pragma unroll
+                        for (int k = 0; k < V; ++k) pu[k] = __ldg(t.lo[0] + (int64_t)k * t.stride[0] + pidx);
+                        const float iwu = __ldg(t.bound[0] + pidx);
+                        const int u = __ldg(t.ids + pidx);
+                        const float e2 = box_dist2<V>(q, pu, pu);
+                        const float dist = sqrtf(e2);
+                        const float ws = iwq * iwu;
+                        if (dist <= 0.f) {
+                            if (!is_neighbor(col, rowBegin, rowEnd, u)) ++nCoincident;
+                        } else if (dist * ws <= L) {
+                            if (!is_neighbor(col, rowBegin, rowEnd, u)) {
+                                axpy_diff<V>(acc, fp.repulsionScale * ws / dist, q, pu);
+                                loss += L / ws - dist;
+                                ++nPairs;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lv > 0) {
+            mine |= __shfl_xor_sync(0xffffffffu, mine, 8);
+            mine |= __shfl_xor_sync(0xffffffffu, mine, 16);
+            const bool push = (g == 0) && (mine != 0u);
+            const uint32_t pb = __ballot_sync(0xffffffffu, push);
+            if (push) sStack[warp][sp + __popc(pb & ltMask)] = ((unsigned long long)(((uint32_t)lv << 28) | (uint32_t)idx) << 32) | mine;
+            sp += __popc(pb);
+            __syncwarp();
+        }
+    }
+    if (valid) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) forceRep[(int64_t)v * V + k] = acc[k];
+        lossRep[v] = loss;
+        coincident[v] = nCoincident;
+    }
+    double sums[2] = {(double)nPairs, (double)nTests};
+    block_sum<2, 256>(sums, smem, partials + (int64_t)blockIdx.x * 2);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Repulsion, pair-stack walk (variant 2).
+//
+// A warp owns 32 consecutive queries and one LIFO stack of (level, node, query) pairs in shared memory.  Every
+// round pops four pairs, one per 8-lane group; lane c of the group tests child c of the pair's node against the
+// pair's query (query coordinates come from shared memory, the child box from L1/L2).  Passing children are pushed
+// as new pairs, ordered child-major so that the four pairs popped together usually name the same node (one cache
+// line serves the four groups).  Every round performs 32 useful tests; a query performs exactly the tests of its
+// private depth-first walk.  Level-0 passes are exact-tested by the tester lane and handed to the owner lane of the
+// query, which applies the neighbour filter and accumulates in registers, in stack order: deterministic, no atomics.
+template <int V>
+__global__ void __launch_bounds__(256) k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __restrict__ col,
+                                                       int n, const ForceParams fp, float4* __restrict__ forceRep,
+                                                       float* __restrict__ lossRep, int* __restrict__ coincident,
+                                                       double* __restrict__ partials) {
+    constexpr int WARPS = 8, STACK = 28 * kMaxLevels + 36;   // LIFO bound: <= 28 leftovers per level + one push of 32
+    __shared__ float4 sQ[WARPS][32][V];
+    __shared__ float sIw[WARPS][32];
+    __shared__ uint32_t sStack[WARPS][STACK];    // (level << 28) | (query lane << 23) | node   (node < 2^23: n <= 6.7e7)
+    __shared__ double smem[8 * 2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = lane & (kFan - 1), g = lane >> kFanLog2;
+    // lanes that precede this one in child-major order (c, g)
+    uint32_t before = 0u;
+#pragma unroll
+    for (int l = 0; l < 32; ++l) {
+        const int lc = l & (kFan - 1), lg = l >> kFanLog2;
+        if (lc < c || (lc == c && lg < g)) before |= 1u << l;
+    }
+    const int qBase = (blockIdx.x * WARPS + warp) * 32;
+    const int qi = qBase + lane;
+    const bool valid = qi < n;
+    float4 q[V];
+    float iwq = 1.f;
+    int v = -1, rowBegin = 0, rowEnd = 0;
+    if (valid) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) q[k] = __ldg(t.lo[0] + (int64_t)k * t.stride[0] + qi);
+        iwq = __ldg(t.bound[0] + qi);
+        v = __ldg(t.ids + qi);
+        rowBegin = __ldg(rowPtr + v);
+        rowEnd = __ldg(rowPtr + v + 1);
+    } else {
+#pragma unroll
+        for (int k = 0; k < V; ++k) q[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float4* myQ = &sQ[warp][0][0];
+    float* myIw = &sIw[warp][0];
+    uint32_t* myStack = &sStack[warp][0];
+#pragma unroll
+    for (int k = 0; k < V; ++k) myQ[lane * V + k] = q[k];
+    myIw[lane] = iwq;
+    float4 acc[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float loss = 0.f;
+    int nCoincident = 0, nPairs = 0, nTests = 0;
+    const float L = fp.edgeLength;
+    const uint32_t ltMask = (1u << lane) - 1u;
+
+    const uint32_t validMask = __ballot_sync(0xffffffffu, valid);
+    if (valid) myStack[__popc(validMask & ltMask)] = ((uint32_t)(t.numLevels + 1) << 28) | ((uint32_t)lane << 23);
+    int sp = __popc(validMask);
+    __syncwarp();
+    while (sp > 0) {
+        const int take = min(4, sp);
+        const bool active = g < take;
+        const uint32_t entry = myStack[active ? sp - 1 - g : 0];
+        sp -= take;
+        const int lv = active ? (int)(entry >> 28) - 1 : 0;
+        const int idx = active ? (int)(entry & 0x007fffffu) * kFan + c : 0;
+        const int qq = (int)((entry >> 23) & 31u);
+        float4 lo[V], hi[V], qv[V];
+        const int64_t st = t.stride[lv];
+        const float4* loP = t.lo[lv];
+        const float4* hiP = t.hi[lv];         // == lo for level 0
+#pragma unroll
+        for (int k = 0; k < V; ++k) lo[k] = __ldg(loP + k * st + idx);
+#pragma unroll
+        for (int k = 0; k < V; ++k) hi[k] = __ldg(hiP + k * st + idx);
+        const float bnd = __ldg(t.bound[lv] + idx);
+#pragma unroll
+        for (int k = 0; k < V; ++k) qv[k] = myQ[qq * V + k];
+        const float s = myIw[qq] * bnd;
+        const float d2 = box_dist2<V>(qv, lo, hi);
+        const bool pass = active && (d2 * s * s <= fp.pruneL2);
+        __syncwarp();                          // every lane has read its entry before the stack is overwritten
+        const bool toPush = pass && lv > 0;
+        const uint32_t pb = __ballot_sync(0xffffffffu, toPush);
+        if (toPush) myStack[sp + __popc(pb & before)] = ((uint32_t)lv << 28) | ((uint32_t)qq << 23) | (uint32_t)idx;
+        sp += __popc(pb);
+        bool hit = pass && lv == 0 && (idx != qBase + qq);
+        if (active && lv == 0) ++nTests;
+        if (hit) {
+            const float dist = sqrtf(d2);
+            if (dist > 0.f) hit = dist * s <= L;           // exact predicate; dist <= 0 is the coincident case
+        }
+        uint32_t hb = __ballot_sync(0xffffffffu, hit);
+        while (hb) {
+            const int hl = __ffs(hb) - 1;
+            hb &= hb - 1u;
+            const int owner = __shfl_sync(0xffffffffu, qq, hl);
+            const int pidx = __shfl_sync(0xffffffffu, idx, hl);
+            if (lane == owner) {
+                float4 pu[V];
+#pragma unroll
+                for (int k = 0; k < V; ++k) pu[k] = __ldg(t.lo[0] + (int64_t)k * t.stride[0] + pidx);
+                const float iwu = __ldg(t.bound[0] + pidx);
+                const int u = __ldg(t.ids + pidx);
+                const float e2 = box_dist2<V>(q, pu, pu);
+                const float dist = sqrtf(e2);
+                const float ws = iwq * iwu;
+                if (dist <= 0.f) {
+                    if (!is_neighbor(col, rowBegin, rowEnd, u)) ++nCoincident;
+                } else if (dist * ws <= L) {
+                    if (!is_neighbor(col, rowBegin, rowEnd, u)) {
+                        axpy_diff<V>(acc, fp.repulsionScale * ws / dist, q, pu);
+                        loss += L / ws - dist;
+                        ++nPairs;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (valid) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) forceRep[(int64_t)v * V + k] = acc[k];
+        lossRep[v] = loss;
+        coincident[v] = nCoincident;
+    }
+    double sums[2] = {(double)nPairs, (double)nTests};
+    block_sum<2, 256>(sums, smem, partials + (int64_t)blockIdx.x * 2);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Attraction + centre force + optimizer, fused (WembedEmbedder.cpp:260-272, 140-172, 296-301; AdamOptimizer.cpp:15-30).
 // G lanes share one vertex: they stride over its CSR row, reduce with a fixed butterfly, add the repulsive force
 // computed by k_repulse, then lane c updates chunk c of x / m / v.  Each block owns a fixed contiguous vertex range

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <limits>
@@ -60,6 +61,7 @@ struct wb_embedder {
     std::vector<double> weights;          // state.currentWeights
     std::vector<double> classMax;         // maxWeightOfClass[class(v)] (WeightedIndex.cpp:25-32), for the test hook
     int64_t iteration = 0;                // state.currentIteration
+    int repulseVariant = 2;               // 2 = pair-stack walk (production); 1 = shared-mask walk, 0 = per-group walk (WB_REPULSE_VARIANT, A/B only)
     int adamT = 0;                        // AdamOptimizer::t
 
     // spatial index
@@ -85,6 +87,8 @@ struct wb_embedder {
     std::deque<PendingStep> pending;
     std::vector<PendingStep> freeSlots;
 
+    cudaEvent_t marks[8] = {};
+    int64_t launches = 0;
     bool timing = false;
     cudaEvent_t ev[7] = {};
     double phaseMs[6] = {0, 0, 0, 0, 0, 0};
@@ -121,6 +125,7 @@ void free_all(wb_embedder* h) {
     for (auto& p : h->freeSlots) { cudaEventDestroy(p.done); cudaFreeHost(p.hostSums); }
     h->pending.clear(); h->freeSlots.clear();
     for (auto& e : h->ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+    for (auto& e : h->marks) if (e) { cudaEventDestroy(e); e = nullptr; }
     if (h->stream) cudaStreamDestroy(h->stream);
     h->stream = nullptr;
 }
@@ -207,6 +212,7 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
     h->sumsAll = dalloc<double>(h->sumsTotal);
     WB_CUDA(cudaMemsetAsync(h->sumsAll, 0, sizeof(double) * h->sumsTotal, h->stream));
     for (auto& e : h->ev) WB_CUDA(cudaEventCreate(&e));
+    for (auto& e : h->marks) WB_CUDA(cudaEventCreate(&e));
     WB_CUDA(cudaStreamSynchronize(h->stream));
 }
 
@@ -229,6 +235,7 @@ void enqueue_index(wb_embedder* h, const float* pointBound) {
                              h->lvlLo[l - 1], h->lvlHi[l - 1], h->lvlBound[l - 1], t.count[l - 1], t.stride[l - 1], h->lvlLo[l], h->lvlHi[l],
                              h->lvlBound[l], t.count[l], t.stride[l]));
     }
+    h->launches += 5 + (t.numLevels - 1);
     WB_CUDA(cudaGetLastError());
 }
 
@@ -279,9 +286,21 @@ void enqueue_step(wb_embedder* h, double learningRate) {
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[0], s));
     enqueue_index(h, h->iw);
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[1], s));
-    WB_DISPATCH_V(V, wb::k_repulse<V><<<h->repBlocks, 256, 0, s>>>(h->tree, h->rowPtr, h->col, n, fp, h->forceRep, h->lossRep,
-                                                                    h->coincident, h->partialsRep));
-    wb::k_reduce_partials<<<2, 256, 0, s>>>(h->partialsRep, h->repBlocks, 2, h->sumsAll + K);
+    int repBlocksUsed;
+    if (h->repulseVariant == 0) {
+        repBlocksUsed = h->repBlocks;
+        WB_DISPATCH_V(V, wb::k_repulse<V><<<repBlocksUsed, 256, 0, s>>>(h->tree, h->rowPtr, h->col, n, fp, h->forceRep, h->lossRep,
+                                                                         h->coincident, h->partialsRep));
+    } else if (h->repulseVariant == 2) {
+        repBlocksUsed = div_up(n, 256);
+        WB_DISPATCH_V(V, wb::k_repulse_pairs<V><<<repBlocksUsed, 256, 0, s>>>(h->tree, h->rowPtr, h->col, n, fp, h->forceRep, h->lossRep,
+                                                                               h->coincident, h->partialsRep));
+    } else {
+        repBlocksUsed = div_up(n, 256);
+        WB_DISPATCH_V(V, wb::k_repulse_shared<V><<<repBlocksUsed, 256, 0, s>>>(h->tree, h->rowPtr, h->col, n, fp, h->forceRep, h->lossRep,
+                                                                                h->coincident, h->partialsRep));
+    }
+    wb::k_reduce_partials<<<2, 256, 0, s>>>(h->partialsRep, repBlocksUsed, 2, h->sumsAll + K);
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[2], s));
     WB_DISPATCH_V(V, wb::k_attract_update<V, 8><<<h->forceBlocks, 256, 0, s>>>(
                          h->x, h->iw, h->rowPtr, h->col, n, h->forceVertsPerBlock, fp, h->forceRep, h->lossRep, h->coincident, h->xNew,
@@ -292,6 +311,7 @@ void enqueue_step(wb_embedder* h, double learningRate) {
                                                                               h->partialsObs));
     wb::k_reduce_partials<<<2, 256, 0, s>>>(h->partialsObs, h->obsBlocks, 2, h->sumsAll + K + 2);
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[4], s));
+    h->launches += 6;
     WB_CUDA(cudaGetLastError());
     WB_CUDA(cudaMemcpyAsync(slot.hostSums, h->sumsAll, sizeof(double) * h->sumsTotal, cudaMemcpyDeviceToHost, s));
     WB_CUDA(cudaEventRecord(slot.done, s));
@@ -432,6 +452,7 @@ int wb_create(wb_embedder** out, int32_t n, const int32_t* row_ptr, const int32_
     h->rowFloats = 4 * h->V;
     h->numDirected = row_ptr[n];
     h->opt = *opts;
+    if (const char* e = std::getenv("WB_REPULSE_VARIANT")) h->repulseVariant = std::atoi(e);
     const int rc = guarded(h, [&] { allocate(h, row_ptr, col); });
     if (rc != WB_OK) { free_all(h); delete h; return rc; }
     *out = h;
@@ -541,6 +562,23 @@ int wb_get_phase_times(wb_embedder* h, double* ms6) {
     std::copy(h->phaseMs, h->phaseMs + 6, ms6);
     return WB_OK;
 }
+
+int wb_mark(wb_embedder* h, int slot) {
+    if (h && (slot < 0 || slot >= 8)) return fail(WB_ERR_INVALID, "wb_mark: slot out of range");
+    return guarded(h, [&] { WB_CUDA(cudaEventRecord(h->marks[slot], h->stream)); });
+}
+
+int wb_elapsed_ms(wb_embedder* h, int from, int to, double* ms) {
+    if (h && (from < 0 || from >= 8 || to < 0 || to >= 8 || !ms)) return fail(WB_ERR_INVALID, "wb_elapsed_ms: bad arguments");
+    return guarded(h, [&] {
+        WB_CUDA(cudaEventSynchronize(h->marks[to]));
+        float f = 0.f;
+        WB_CUDA(cudaEventElapsedTime(&f, h->marks[from], h->marks[to]));
+        *ms = f;
+    });
+}
+
+int64_t wb_launch_count(wb_embedder* h) { return h ? h->launches : 0; }
 
 int wb_query_candidates(wb_embedder* h, int32_t nq, const int32_t* queries, int64_t* out_offsets, int32_t* out_ids, int64_t cap) {
     if (h && (nq < 0 || (nq > 0 && (!queries || !out_offsets)))) return fail(WB_ERR_INVALID, "wb_query_candidates: bad arguments");
