@@ -38,6 +38,7 @@ class StepParity:
         self.term = np.maximum(term, 1.0)[:, None]
         self.unstable = np.zeros((len(w), d), bool)
         self.max_flagged_frac = max_flagged_frac
+        self.coord_rtol = COORD_RTOL
         self.args = (w, rp, col, L)
 
     def check(self, flagged, f_ref, f_dev, x_ref, x_dev):
@@ -52,7 +53,7 @@ class StepParity:
         assert self.unstable.mean() <= 0.05, self.unstable.mean()
         xscale = max(1.0, np.abs(x_ref).max())
         xerr = np.where(self.unstable, 0.0, np.abs(x_ref - x_dev))
-        assert xerr.max() <= COORD_RTOL * xscale, (xerr.max(), xscale)
+        assert xerr.max() <= self.coord_rtol * xscale, (xerr.max(), xscale)
 
 
 def assert_step_close(xin, w, rp, col, f_ref, f_dev, x_ref, x_dev, L=1.0, max_flagged_frac=0.02, flagged=None, tracker=None):
@@ -111,7 +112,14 @@ def test_step_parity_heavy_tailed(device_lib, port_lib):
         flagged = cpu.near_threshold(1e-5)
         cpu.step()
         st = dev.step(lr_exponential(it))
+        if tracker is None:
+            tracker = StepParity(w, rp, col, d, 0.05)
+            # hub rows sum thousands of fp32 terms (degree ~ n/10): their optimizer input carries ~deg * 2^-24 relative
+            # error, which the Adam ratio m / sqrt(v) passes on to the coordinate.  1e-5 holds for every non-hub vertex.
+            tracker.coord_rtol = 5e-5
         tracker = assert_step_close(None, w, rp, col, cpu.forces(), dev.forces(), cpu.coordinates(), dev.coordinates(), max_flagged_frac=0.05, flagged=flagged, tracker=tracker)
+        hubs = np.diff(rp) > 256
+        assert np.abs(cpu.coordinates() - dev.coordinates())[~hubs & ~tracker.unstable.any(axis=1)].max() <= COORD_RTOL * max(1.0, np.abs(cpu.coordinates()).max())
         np.testing.assert_allclose(st["loss_attract"], cpu.stats()["loss_attract"], rtol=1e-5)
         cpu.set_coordinates(dev.coordinates())
 

@@ -94,6 +94,18 @@ __device__ __forceinline__ void axpy_diff(float4 (&acc)[V], float s, const float
     }
 }
 
+// acc (double) += s * (a - b), every term evaluated in fp32 like the rest of the pair arithmetic
+template <int V>
+__device__ __forceinline__ void axpy_diff_d(double (&acc)[4 * V], float s, const float4 (&a)[V], const float4 (&b)[V]) {
+#pragma unroll
+    for (int c = 0; c < V; ++c) {
+        acc[4 * c + 0] += (double)(s * (a[c].x - b[c].x));
+        acc[4 * c + 1] += (double)(s * (a[c].y - b[c].y));
+        acc[4 * c + 2] += (double)(s * (a[c].z - b[c].z));
+        acc[4 * c + 3] += (double)(s * (a[c].w - b[c].w));
+    }
+}
+
 __device__ __forceinline__ float4 shfl_xor4(float4 v, int laneMask) {
     v.x = __shfl_xor_sync(0xffffffffu, v.x, laneMask);
     v.y = __shfl_xor_sync(0xffffffffu, v.y, laneMask);
@@ -110,6 +122,12 @@ __device__ __forceinline__ float4 max4(float4 a, float4 b) { return make_float4(
 // the same value and the order of additions does not depend on scheduling.
 template <int G>
 __device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <int G>
+__device__ __forceinline__ double group_sum(double v) {
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;

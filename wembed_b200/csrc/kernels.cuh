@@ -290,230 +290,7 @@ __device__ __forceinline__ bool is_neighbor(const int* __restrict__ col, int beg
 }
 
 // ---------------------------------------------------------------------------------------------
-// Repulsion (WembedEmbedder.cpp:274-294 + 174-210).  Query order = sorted order, so neighbouring groups walk
-// similar paths.  Writes forceRep[v], lossRep[v], the number of coincident non-neighbours of v, and per-block
-// counters {pairs, point tests} for the statistics.
-template <int V>
-__global__ void __launch_bounds__(256) k_repulse(const TreeView t, const int* __restrict__ rowPtr, const int* __restrict__ col,
-                                                 int n, const ForceParams fp, float4* __restrict__ forceRep,
-                                                 float* __restrict__ lossRep, int* __restrict__ coincident,
-                                                 double* __restrict__ partials) {
-    __shared__ double smem[8 * 2];
-    const int lane = threadIdx.x & 31, j = lane & (kFan - 1);
-    const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> kFanLog2;
-    const bool valid = qi < n;
-    float4 q[V];
-    float iwq = 1.f;
-    int v = -1, rowBegin = 0, rowEnd = 0;
-    if (valid) {
-#pragma unroll
-        for (int c = 0; c < V; ++c) q[c] = __ldg(t.lo[0] + (int64_t)c * t.stride[0] + qi);
-        iwq = __ldg(t.bound[0] + qi);
-        v = __ldg(t.ids + qi);
-        rowBegin = __ldg(rowPtr + v);
-        rowEnd = __ldg(rowPtr + v + 1);
-    } else {
-#pragma unroll
-        for (int c = 0; c < V; ++c) q[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    float4 acc[V];
-#pragma unroll
-    for (int c = 0; c < V; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-    float loss = 0.f;
-    int nCoincident = 0, nPairs = 0, nTests = 0;
-    const float L = fp.edgeLength;
-
-    walk_tree<V>(
-        t, q, valid,
-        [&](int, int, float d2, float bnd) {
-            const float s = iwq * bnd;
-            return d2 * s * s <= fp.pruneL2;       // superset of dist * ws <= L
-        },
-        [&](int idx, float d2, float iwu, const float4 (&pu)[V]) {
-            const int u = __ldg(t.ids + idx);
-            if (u == v) return;                      // areInSameColorClass (colours are unique ids, Graph.cpp:152-156)
-            const float dist = sqrtf(d2);
-            const float ws = iwq * iwu;
-            if (dist <= 0.f) {
-                if (!is_neighbor(col, rowBegin, rowEnd, u)) ++nCoincident;   // random direction added by k_attract
-            } else if (dist * ws <= L) {
-                if (!is_neighbor(col, rowBegin, rowEnd, u)) {
-                    axpy_diff<V>(acc, fp.repulsionScale * ws / dist, q, pu);
-                    loss += L / ws - dist;
-                    ++nPairs;
-                }
-            }
-        },
-        nTests);
-
-#pragma unroll
-    for (int c = 0; c < V; ++c) acc[c] = group_sum<kFan>(acc[c]);
-    loss = group_sum<kFan>(loss);
-    nCoincident = group_sum<kFan>(nCoincident);
-    nPairs = group_sum<kFan>(nPairs);
-    nTests = group_sum<kFan>(nTests);
-    if (valid) {
-#pragma unroll
-        for (int c = 0; c < V; ++c)
-            if (j == c) forceRep[(int64_t)v * V + c] = acc[c];
-        if (j == kFan - 1) { lossRep[v] = loss; coincident[v] = nCoincident; }
-    }
-    double sums[2] = {(valid && j == 0) ? (double)nPairs : 0.0, (valid && j == 0) ? (double)nTests : 0.0};
-    block_sum<2, 256>(sums, smem, partials + (int64_t)blockIdx.x * 2);
-}
-
-// ---------------------------------------------------------------------------------------------
-// Repulsion, shared walk (the production variant).
-//
-// Why: the per-group walk above re-reads every box it tests from L2 (64 B + per test at d = 8) and is bound by
-// L2 -> SM bandwidth.  Queries that are adjacent in Morton order visit largely the same boxes (measured overlap at
-// n = 1e5, d = 8: 7x for boxes, 4x for points over 32 consecutive queries), so here ONE warp walks the hierarchy
-// once for its 32 queries.  A stack entry is (level, node, 32-bit mask of the queries that still need the node).
-// Popping a node, lane (g, c) = (lane / 8, lane % 8) loads child c once into registers; the queries of the mask are
-// tested four at a time (one per lane group g) against the eight children, reading the query from shared memory.
-// A child is pushed with the mask of the queries that passed it, so every query performs exactly the tests of its
-// own private walk - only the loads are shared.  At the point level the tester lane evaluates the exact predicate
-// and hands hits to the lane that owns the query, which applies the neighbour filter and accumulates in registers
-// in (pop, round, lane) order: no atomics, deterministic, no cross-lane reduction of forces.
-template <int V>
-__global__ void __launch_bounds__(256) k_repulse_shared(const TreeView t, const int* __restrict__ rowPtr, const int* __restrict__ col,
-                                                        int n, const ForceParams fp, float4* __restrict__ forceRep,
-                                                        float* __restrict__ lossRep, int* __restrict__ coincident,
-                                                        double* __restrict__ partials) {
-    constexpr int WARPS = 8, STACK = 8 * kMaxLevels;
-    __shared__ float4 sQ[WARPS][32][V];
-    __shared__ float sIw[WARPS][32];
-    __shared__ unsigned long long sStack[WARPS][STACK];
-    __shared__ int sList[WARPS][32];
-    __shared__ double smem[8 * 2];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = lane & (kFan - 1), g = lane >> kFanLog2;
-    const uint32_t ltMask = (1u << lane) - 1u;
-    const int qBase = (blockIdx.x * WARPS + warp) * 32;
-    const int qi = qBase + lane;
-    const bool valid = qi < n;
-    float4 q[V];
-    float iwq = 1.f;
-    int v = -1, rowBegin = 0, rowEnd = 0;
-    if (valid) {
-#pragma unroll
-        for (int k = 0; k < V; ++k) q[k] = __ldg(t.lo[0] + (int64_t)k * t.stride[0] + qi);
-        iwq = __ldg(t.bound[0] + qi);
-        v = __ldg(t.ids + qi);
-        rowBegin = __ldg(rowPtr + v);
-        rowEnd = __ldg(rowPtr + v + 1);
-    } else {
-#pragma unroll
-        for (int k = 0; k < V; ++k) q[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int k = 0; k < V; ++k) sQ[warp][lane][k] = q[k];
-    sIw[warp][lane] = iwq;
-    float4 acc[V];
-#pragma unroll
-    for (int k = 0; k < V; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    float loss = 0.f;
-    int nCoincident = 0, nPairs = 0, nTests = 0;
-    const float L = fp.edgeLength;
-
-    const uint32_t validMask = __ballot_sync(0xffffffffu, valid);
-    int sp = 0;
-    if (validMask != 0u) {
-        if (lane == 0) sStack[warp][0] = ((unsigned long long)(((uint32_t)(t.numLevels + 1) << 28) | 0u) << 32) | validMask;
-        sp = 1;
-    }
-    __syncwarp();
-    while (sp > 0) {
-        const unsigned long long entry = sStack[warp][--sp];
-        const uint32_t m = (uint32_t)entry, head = (uint32_t)(entry >> 32);
-        const int lv = (int)(head >> 28) - 1;                 // level of the children
-        const int idx = (int)(head & 0x0fffffffu) * kFan + c; // child of this lane
-        float4 lo[V], hi[V];
-        const int64_t st = t.stride[lv];
-#pragma unroll
-        for (int k = 0; k < V; ++k) lo[k] = __ldg(t.lo[lv] + k * st + idx);
-        if (lv == 0) {
-#pragma unroll
-            for (int k = 0; k < V; ++k) hi[k] = lo[k];
-        } else {
-#pragma unroll
-            for (int k = 0; k < V; ++k) hi[k] = __ldg(t.hi[lv] + k * st + idx);
-        }
-        const float bnd = __ldg(t.bound[lv] + idx);
-        const int p = __popc(m);
-        if ((m >> lane) & 1u) sList[warp][__popc(m & ltMask)] = lane;
-        __syncwarp();
-        uint32_t mine = 0u;
-        for (int r = 0; r * 4 < p; ++r) {
-            const int slot = r * 4 + g;
-            const bool active = slot < p;
-            const int qq = active ? sList[warp][slot] : 0;
-            float4 qv[V];
-#pragma unroll
-            for (int k = 0; k < V; ++k) qv[k] = sQ[warp][qq][k];
-            const float iwqq = sIw[warp][qq];
-            const float d2 = box_dist2<V>(qv, lo, hi);
-            const float s = iwqq * bnd;
-            const bool pass = active && (d2 * s * s <= fp.pruneL2);
-            if (lv > 0) {
-                if (pass) mine |= 1u << qq;
-            } else {
-                if (active) ++nTests;
-                bool hit = pass && (idx != qBase + qq);
-                if (hit) {
-                    const float dist = sqrtf(d2);
-                    if (dist > 0.f) hit = dist * s <= L;       // exact predicate; dist <= 0 is the coincident case
-                }
-                uint32_t hb = __ballot_sync(0xffffffffu, hit);
-                while (hb) {
-                    const int hl = __ffs(hb) - 1;
-                    hb &= hb - 1u;
-                    const int owner = __shfl_sync(0xffffffffu, qq, hl);
-                    const int pidx = __shfl_sync(0xffffffffu, idx, hl);
-                    if (lane == owner) {
-                        float4 pu[V];
-#pragma unroll
-                        for (int k = 0; k < V; ++k) pu[k] = __ldg(t.lo[0] + (int64_t)k * t.stride[0] + pidx);
-                        const float iwu = __ldg(t.bound[0] + pidx);
-                        const int u = __ldg(t.ids + pidx);
-                        const float e2 = box_dist2<V>(q, pu, pu);
-                        const float dist = sqrtf(e2);
-                        const float ws = iwq * iwu;
-                        if (dist <= 0.f) {
-                            if (!is_neighbor(col, rowBegin, rowEnd, u)) ++nCoincident;
-                        } else if (dist * ws <= L) {
-                            if (!is_neighbor(col, rowBegin, rowEnd, u)) {
-                                axpy_diff<V>(acc, fp.repulsionScale * ws / dist, q, pu);
-                                loss += L / ws - dist;
-                                ++nPairs;
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        if (lv > 0) {
-            mine |= __shfl_xor_sync(0xffffffffu, mine, 8);
-            mine |= __shfl_xor_sync(0xffffffffu, mine, 16);
-            const bool push = (g == 0) && (mine != 0u);
-            const uint32_t pb = __ballot_sync(0xffffffffu, push);
-            if (push) sStack[warp][sp + __popc(pb & ltMask)] = ((unsigned long long)(((uint32_t)lv << 28) | (uint32_t)idx) << 32) | mine;
-            sp += __popc(pb);
-            __syncwarp();
-        }
-    }
-    if (valid) {
-#pragma unroll
-        for (int k = 0; k < V; ++k) forceRep[(int64_t)v * V + k] = acc[k];
-        lossRep[v] = loss;
-        coincident[v] = nCoincident;
-    }
-    double sums[2] = {(double)nPairs, (double)nTests};
-    block_sum<2, 256>(sums, smem, partials + (int64_t)blockIdx.x * 2);
-}
-
-// ---------------------------------------------------------------------------------------------
-// Repulsion, pair-stack walk (variant 2).
+// Repulsion (WembedEmbedder.cpp:274-294 + 174-210): pair-stack walk.
 //
 // A warp owns 32 consecutive queries and one LIFO stack of (level, node, query) pairs in shared memory.  Every
 // round pops four pairs, one per 8-lane group; lane c of the group tests child c of the pair's node against the
@@ -524,7 +301,7 @@ __global__ void __launch_bounds__(256) k_repulse_shared(const TreeView t, const 
 // query, which applies the neighbour filter and accumulates in registers, in stack order: deterministic, no atomics.
 template <int V>
 __global__ void __launch_bounds__(256) k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __restrict__ col,
-                                                       int n, const ForceParams fp, float4* __restrict__ forceRep,
+                                                       int n, const ForceParams fp, double* __restrict__ forceRep,
                                                        float* __restrict__ lossRep, int* __restrict__ coincident,
                                                        double* __restrict__ partials) {
     constexpr int WARPS = 8, STACK = 28 * kMaxLevels + 36;   // LIFO bound: <= 28 leftovers per level + one push of 32
@@ -563,10 +340,12 @@ __global__ void __launch_bounds__(256) k_repulse_pairs(const TreeView t, const i
 #pragma unroll
     for (int k = 0; k < V; ++k) myQ[lane * V + k] = q[k];
     myIw[lane] = iwq;
-    float4 acc[V];
+    // Forces are summed in double: a vertex can own hundreds of repulsive terms in a collapsed layout, and the optimizer
+    // normalises every component, so a component that is a cancellation residue must keep the accuracy of its terms.
+    double acc[4 * V];
 #pragma unroll
-    for (int k = 0; k < V; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    float loss = 0.f;
+    for (int k = 0; k < 4 * V; ++k) acc[k] = 0.0;
+    double loss = 0.0;
     int nCoincident = 0, nPairs = 0, nTests = 0;
     const float L = fp.edgeLength;
     const uint32_t ltMask = (1u << lane) - 1u;
@@ -627,8 +406,8 @@ __global__ void __launch_bounds__(256) k_repulse_pairs(const TreeView t, const i
                     if (!is_neighbor(col, rowBegin, rowEnd, u)) ++nCoincident;
                 } else if (dist * ws <= L) {
                     if (!is_neighbor(col, rowBegin, rowEnd, u)) {
-                        axpy_diff<V>(acc, fp.repulsionScale * ws / dist, q, pu);
-                        loss += L / ws - dist;
+                        axpy_diff_d<V>(acc, fp.repulsionScale * ws / dist, q, pu);
+                        loss += (double)(L / ws - dist);
                         ++nPairs;
                     }
                 }
@@ -638,8 +417,8 @@ __global__ void __launch_bounds__(256) k_repulse_pairs(const TreeView t, const i
     }
     if (valid) {
 #pragma unroll
-        for (int k = 0; k < V; ++k) forceRep[(int64_t)v * V + k] = acc[k];
-        lossRep[v] = loss;
+        for (int k = 0; k < 4 * V; ++k) forceRep[(int64_t)v * 4 * V + k] = acc[k];
+        lossRep[v] = (float)loss;
         coincident[v] = nCoincident;
     }
     double sums[2] = {(double)nPairs, (double)nTests};
@@ -655,7 +434,7 @@ template <int V, int G>
 __global__ void __launch_bounds__(256) k_attract_update(const float4* __restrict__ x, const float* __restrict__ iw,
                                                         const int* __restrict__ rowPtr, const int* __restrict__ col, int n,
                                                         int vertsPerBlock, const ForceParams fp,
-                                                        const float4* __restrict__ forceRep, const float* __restrict__ lossRep,
+                                                        const double* __restrict__ forceRep, const float* __restrict__ lossRep,
                                                         const int* __restrict__ coincidentRep, float4* __restrict__ xNew,
                                                         float4* __restrict__ mom1, float4* __restrict__ mom2,
                                                         float4* __restrict__ forceOut, double* __restrict__ partials) {
@@ -674,10 +453,12 @@ __global__ void __launch_bounds__(256) k_attract_update(const float4* __restrict
     for (int vBase = vBegin; vBase < vEnd; vBase += GROUPS_PER_BLOCK) {
         const int v = vBase + threadIdx.x / G;
         const bool valid = v < vEnd;
-        float4 xv[V], acc[V];
+        float4 xv[V];
+        double acc[4 * V];      // summed in double, see k_repulse_pairs
 #pragma unroll
-        for (int c = 0; c < V; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-        float loss = 0.f, iwv = 1.f;
+        for (int k = 0; k < 4 * V; ++k) acc[k] = 0.0;
+        double loss = 0.0;
+        float iwv = 1.f;
         int nCoincident = 0;
         if (valid) {
             load_row<V>(x, v, xv);
@@ -693,8 +474,8 @@ __global__ void __launch_bounds__(256) k_attract_update(const float4* __restrict
                 if (dist <= 0.f) { ++nCoincident; continue; }     // :150-155
                 const float ws = iwv * __ldg(iw + u);
                 if (dist * ws > L) {                               // :163-168
-                    axpy_diff<V>(acc, fp.attractionScale * ws / dist, xu, xv);
-                    loss += dist - L / ws;
+                    axpy_diff_d<V>(acc, fp.attractionScale * ws / dist, xu, xv);
+                    loss += (double)(dist - L / ws);
                 }
             }
         } else {
@@ -702,7 +483,7 @@ __global__ void __launch_bounds__(256) k_attract_update(const float4* __restrict
             for (int c = 0; c < V; ++c) xv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int c = 0; c < V; ++c) acc[c] = group_sum<G>(acc[c]);
+        for (int k = 0; k < 4 * V; ++k) acc[k] = group_sum<G>(acc[k]);
         loss = group_sum<G>(loss);
         nCoincident = group_sum<G>(nCoincident);
         if (valid) nCoincident += __ldg(coincidentRep + v);
@@ -717,23 +498,21 @@ __global__ void __launch_bounds__(256) k_attract_update(const float4* __restrict
             if (nCoincident > 0) {
                 const double* uvec = unitBuf[warp][gInWarp];
 #pragma unroll
-                for (int c = 0; c < V; ++c) {
-                    acc[c].x += (4 * c + 0 < fp.dim) ? (float)(nCoincident * uvec[4 * c + 0]) : 0.f;
-                    acc[c].y += (4 * c + 1 < fp.dim) ? (float)(nCoincident * uvec[4 * c + 1]) : 0.f;
-                    acc[c].z += (4 * c + 2 < fp.dim) ? (float)(nCoincident * uvec[4 * c + 2]) : 0.f;
-                    acc[c].w += (4 * c + 3 < fp.dim) ? (float)(nCoincident * uvec[4 * c + 3]) : 0.f;
-                }
+                for (int k = 0; k < 4 * V; ++k)
+                    if (k < fp.dim) acc[k] += nCoincident * uvec[k];
             }
             __syncwarp();
         }
 
         if (valid) {
-            if (lig == 0) { sums[0] += (double)loss; sums[1] += (double)__ldg(lossRep + v); }
+            if (lig == 0) { sums[0] += loss; sums[1] += (double)__ldg(lossRep + v); }
 #pragma unroll
             for (int c = 0; c < V; ++c) {
                 if ((c % G) == lig) {
                     const int64_t at = (int64_t)v * V + c;
-                    float4 f = add4(acc[c], __ldg(forceRep + at));
+                    const double* fr = forceRep + at * 4;
+                    float4 f = make_float4((float)(acc[4 * c] + fr[0]), (float)(acc[4 * c + 1] + fr[1]), (float)(acc[4 * c + 2] + fr[2]),
+                                           (float)(acc[4 * c + 3] + fr[3]));
                     if (fp.centreScale != 0.f) {                   // :296-301
                         f.x = fmaf(-fp.centreScale, xv[c].x, f.x); f.y = fmaf(-fp.centreScale, xv[c].y, f.y);
                         f.z = fmaf(-fp.centreScale, xv[c].z, f.z); f.w = fmaf(-fp.centreScale, xv[c].w, f.w);

@@ -55,13 +55,13 @@ struct wb_embedder {
     int *rowPtr = nullptr, *col = nullptr;
 
     // layout state
-    float4 *x = nullptr, *xNew = nullptr, *mom1 = nullptr, *mom2 = nullptr, *forceRep = nullptr, *force = nullptr;
+    float4 *x = nullptr, *xNew = nullptr, *mom1 = nullptr, *mom2 = nullptr, *force = nullptr;
+    double* forceRep = nullptr;           // repulsive partial force, n x 4V doubles
     float *iw = nullptr, *lossRep = nullptr;
     int* coincident = nullptr;
     std::vector<double> weights;          // state.currentWeights
     std::vector<double> classMax;         // maxWeightOfClass[class(v)] (WeightedIndex.cpp:25-32), for the test hook
     int64_t iteration = 0;                // state.currentIteration
-    int repulseVariant = 2;               // 2 = pair-stack walk (production); 1 = shared-mask walk, 0 = per-group walk (WB_REPULSE_VARIANT, A/B only)
     int adamT = 0;                        // AdamOptimizer::t
 
     // spatial index
@@ -139,7 +139,9 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
     if (h->numDirected) WB_CUDA(cudaMemcpyAsync(h->col, col, sizeof(int) * h->numDirected, cudaMemcpyHostToDevice, h->stream));
 
     const size_t rows = (size_t)n * V;
-    for (float4** p : {&h->x, &h->xNew, &h->mom1, &h->mom2, &h->forceRep, &h->force}) {
+    h->forceRep = dalloc<double>(std::max<size_t>(rows, 1) * 4);
+    WB_CUDA(cudaMemsetAsync(h->forceRep, 0, std::max<size_t>(rows, 1) * 4 * sizeof(double), h->stream));
+    for (float4** p : {&h->x, &h->xNew, &h->mom1, &h->mom2, &h->force}) {
         *p = dalloc<float4>(rows);
         WB_CUDA(cudaMemsetAsync(*p, 0, std::max<size_t>(rows, 1) * sizeof(float4), h->stream));
     }
@@ -286,20 +288,9 @@ void enqueue_step(wb_embedder* h, double learningRate) {
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[0], s));
     enqueue_index(h, h->iw);
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[1], s));
-    int repBlocksUsed;
-    if (h->repulseVariant == 0) {
-        repBlocksUsed = h->repBlocks;
-        WB_DISPATCH_V(V, wb::k_repulse<V><<<repBlocksUsed, 256, 0, s>>>(h->tree, h->rowPtr, h->col, n, fp, h->forceRep, h->lossRep,
-                                                                         h->coincident, h->partialsRep));
-    } else if (h->repulseVariant == 2) {
-        repBlocksUsed = div_up(n, 256);
-        WB_DISPATCH_V(V, wb::k_repulse_pairs<V><<<repBlocksUsed, 256, 0, s>>>(h->tree, h->rowPtr, h->col, n, fp, h->forceRep, h->lossRep,
-                                                                               h->coincident, h->partialsRep));
-    } else {
-        repBlocksUsed = div_up(n, 256);
-        WB_DISPATCH_V(V, wb::k_repulse_shared<V><<<repBlocksUsed, 256, 0, s>>>(h->tree, h->rowPtr, h->col, n, fp, h->forceRep, h->lossRep,
-                                                                                h->coincident, h->partialsRep));
-    }
+    const int repBlocksUsed = div_up(n, 256);
+    WB_DISPATCH_V(V, wb::k_repulse_pairs<V><<<repBlocksUsed, 256, 0, s>>>(h->tree, h->rowPtr, h->col, n, fp, h->forceRep, h->lossRep,
+                                                                           h->coincident, h->partialsRep));
     wb::k_reduce_partials<<<2, 256, 0, s>>>(h->partialsRep, repBlocksUsed, 2, h->sumsAll + K);
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[2], s));
     WB_DISPATCH_V(V, wb::k_attract_update<V, 8><<<h->forceBlocks, 256, 0, s>>>(
@@ -452,7 +443,6 @@ int wb_create(wb_embedder** out, int32_t n, const int32_t* row_ptr, const int32_
     h->rowFloats = 4 * h->V;
     h->numDirected = row_ptr[n];
     h->opt = *opts;
-    if (const char* e = std::getenv("WB_REPULSE_VARIANT")) h->repulseVariant = std::atoi(e);
     const int rc = guarded(h, [&] { allocate(h, row_ptr, col); });
     if (rc != WB_OK) { free_all(h); delete h; return rc; }
     *out = h;
