@@ -59,6 +59,7 @@ struct wb_embedder {
     double* forceRep = nullptr;           // repulsive partial force, n x 4V doubles
     float *iw = nullptr, *lossRep = nullptr;
     int* coincident = nullptr;
+    int* chunkCounter = nullptr;          // work counter of the persistent repulsion kernel
     std::vector<double> weights;          // state.currentWeights
     std::vector<double> classMax;         // maxWeightOfClass[class(v)] (WeightedIndex.cpp:25-32), for the test hook
     int64_t iteration = 0;                // state.currentIteration
@@ -117,7 +118,7 @@ inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 void free_all(wb_embedder* h) {
     auto F = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
     F(h->rowPtr); F(h->col); F(h->x); F(h->xNew); F(h->mom1); F(h->mom2); F(h->forceRep); F(h->force);
-    F(h->iw); F(h->lossRep); F(h->coincident); F(h->keysIn); F(h->keysOut); F(h->valsIn); F(h->valsOut);
+    F(h->iw); F(h->lossRep); F(h->coincident); F(h->chunkCounter); F(h->keysIn); F(h->keysOut); F(h->valsIn); F(h->valsOut);
     F(h->cubTemp); F(h->momentPartials); F(h->quant); F(h->ids);
     for (int l = 0; l < wb::kMaxLevels; ++l) { F(h->lvlLo[l]); if (l > 0) F(h->lvlHi[l]); F(h->lvlBound[l]); }
     F(h->partialsForce); F(h->partialsRep); F(h->partialsObs); F(h->sumsAll);
@@ -202,14 +203,19 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
     h->forceBlocks = std::max(1, std::min(div_up(n, groupsPerBlock), 148 * 16));
     h->forceVertsPerBlock = std::max(groupsPerBlock, div_up(div_up(n, h->forceBlocks), groupsPerBlock) * groupsPerBlock);
     h->forceBlocks = std::max(1, div_up(n, h->forceVertsPerBlock));
-    h->repBlocks = std::max(1, div_up((int64_t)n * kFan, 256));
+    {   // persistent repulsion grid: enough resident blocks to fill every SM, never more than there are chunks
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->opt.device);
+        h->repBlocks = std::max(1, std::min(div_up(div_up(n, 32), 8), sms * 4));
+    }
+    h->chunkCounter = dalloc<int>(1);
     h->obsBlocks = std::max(1, std::min(div_up(n, 256), 148 * 8));
     h->obsVertsPerBlock = std::max(256, div_up(div_up(n, h->obsBlocks), 256) * 256);
     h->obsBlocks = std::max(1, div_up(n, h->obsVertsPerBlock));
     const int K = 2 + 4 * V;
     h->sumsTotal = K + 4;
     h->partialsForce = dalloc<double>((size_t)h->forceBlocks * K);
-    h->partialsRep = dalloc<double>((size_t)h->repBlocks * 2);
+    h->partialsRep = dalloc<double>((size_t)h->repBlocks * 8 * 2);
     h->partialsObs = dalloc<double>((size_t)h->obsBlocks * 2);
     h->sumsAll = dalloc<double>(h->sumsTotal);
     WB_CUDA(cudaMemsetAsync(h->sumsAll, 0, sizeof(double) * h->sumsTotal, h->stream));
@@ -288,10 +294,10 @@ void enqueue_step(wb_embedder* h, double learningRate) {
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[0], s));
     enqueue_index(h, h->iw);
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[1], s));
-    const int repBlocksUsed = div_up(n, 256);
-    WB_DISPATCH_V(V, wb::k_repulse_pairs<V><<<repBlocksUsed, 256, 0, s>>>(h->tree, h->rowPtr, h->col, n, fp, h->forceRep, h->lossRep,
-                                                                           h->coincident, h->partialsRep));
-    wb::k_reduce_partials<<<2, 256, 0, s>>>(h->partialsRep, repBlocksUsed, 2, h->sumsAll + K);
+    WB_CUDA(cudaMemsetAsync(h->chunkCounter, 0, sizeof(int), s));
+    WB_DISPATCH_V(V, wb::k_repulse_pairs<V><<<h->repBlocks, 256, 0, s>>>(h->tree, h->rowPtr, h->col, n, fp, h->forceRep, h->lossRep,
+                                                                          h->coincident, h->chunkCounter, h->partialsRep));
+    wb::k_reduce_partials<<<2, 256, 0, s>>>(h->partialsRep, h->repBlocks * 8, 2, h->sumsAll + K);
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[2], s));
     WB_DISPATCH_V(V, wb::k_attract_update<V, 8><<<h->forceBlocks, 256, 0, s>>>(
                          h->x, h->iw, h->rowPtr, h->col, n, h->forceVertsPerBlock, fp, h->forceRep, h->lossRep, h->coincident, h->xNew,
