@@ -163,6 +163,21 @@ int wb_query_candidates(wb_embedder* h, int32_t nq, const int32_t* queries, int6
 int wb_enable_timing(wb_embedder* h, int enable);
 int wb_get_phase_times(wb_embedder* h, double* ms6);
 
+/* -- multi-GPU: one graph sharded by vertex range over the GPUs of one node ----------------------- */
+
+/*
+ * One process (or thread) per GPU creates the SAME problem (same CSR, weights, coordinates) on its device and then
+ * joins a communicator: rank 0 calls wb_comm_unique_id and ships the 128 bytes to the other ranks by any means
+ * (bench.py uses torch.distributed), every rank calls wb_comm_init.  From then on wb_step computes the forces and
+ * the optimizer update only for the vertices [rank * ceil(n / world), ...) it owns; positions stay replicated: the
+ * owners' updated rows are all-gathered (NCCL over NVLink) at the end of every step, the scalar sums (losses,
+ * centroid, displacement) are all-gathered and added in rank order, so all ranks return identical statistics.
+ * The reference has no distributed code; this is the multi-GPU form of its OpenMP `parallel for` over vertices
+ * (WembedEmbedder.cpp:262,279), every vertex still being written by exactly one owner.
+ */
+int wb_comm_unique_id(char* id128);
+int wb_comm_init(wb_embedder* h, const char* id128, int32_t rank, int32_t world);
+
 /* -- measurement ------------------------------------------------------------------------- */
 
 /* Records CUDA event `slot` (0..7) on the handle's stream; wb_elapsed_ms waits for event `to` and returns the

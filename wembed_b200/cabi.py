@@ -23,7 +23,7 @@ EXPORTS = (
     "wb_abi_version", "wb_build_info", "wb_last_error", "wb_device_count", "wb_options_default", "wb_create", "wb_destroy",
     "wb_set_coordinates", "wb_set_weights", "wb_get_coordinates", "wb_get_weights", "wb_get_forces", "wb_reset_optimizer",
     "wb_set_iteration", "wb_step", "wb_step_async", "wb_step_collect", "wb_synchronize", "wb_query_candidates",
-    "wb_enable_timing", "wb_get_phase_times", "wb_mark", "wb_elapsed_ms", "wb_launch_count",
+    "wb_enable_timing", "wb_get_phase_times", "wb_mark", "wb_elapsed_ms", "wb_launch_count", "wb_comm_unique_id", "wb_comm_init",
 )
 
 
@@ -79,12 +79,21 @@ def lib():
         "wb_enable_timing": (C.c_int, [H, C.c_int]), "wb_get_phase_times": (C.c_int, [H, dp]),
         "wb_mark": (C.c_int, [H, C.c_int]), "wb_elapsed_ms": (C.c_int, [H, C.c_int, C.c_int, dp]),
         "wb_launch_count": (C.c_int64, [H]),
+        "wb_comm_unique_id": (C.c_int, [C.c_char_p]), "wb_comm_init": (C.c_int, [H, C.c_char_p, i32, i32]),
     }
     for name, (res, args) in sig.items():
         f = getattr(l, name)
         f.restype, f.argtypes = res, args
     _lib = l
     return l
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    rc = lib().wb_comm_unique_id(buf)
+    if rc != WB_OK:
+        raise WbError(rc, lib().wb_last_error().decode())
+    return buf.raw
 
 
 def default_options(**kw) -> WbOptions:
@@ -193,6 +202,11 @@ class DeviceEmbedder:
 
     def launch_count(self):
         return int(self._l.wb_launch_count(self._h))
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        """Join the vertex-sharded multi-GPU step (see include/wembed_b200.h)."""
+        assert len(unique_id) == 128
+        self._check(self._l.wb_comm_init(self._h, unique_id, int(rank), int(world)))
 
     def query_candidates(self, queries):
         q = np.ascontiguousarray(queries, dtype=np.int32)

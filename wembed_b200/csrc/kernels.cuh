@@ -308,10 +308,11 @@ template <int V>
 __global__ void __launch_bounds__(256, (V <= 2 ? 4 : (V <= 4 ? 2 : 1)))
 k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __restrict__ col, int n, const ForceParams fp,
                 double* __restrict__ forceRep, float* __restrict__ lossRep, int* __restrict__ coincident, int* __restrict__ chunkCounter,
-                double* __restrict__ partials) {
+                const int* __restrict__ queryList, int numQueries, double* __restrict__ partials) {
     constexpr int WARPS = 8, STACK = 28 * kMaxLevels + 36;   // LIFO bound: <= 28 leftovers per level + one push of 32
     __shared__ float4 sQ[WARPS][32][V];
     __shared__ float sIw[WARPS][32];
+    __shared__ int sPos[WARPS][32];              // sorted position of each query (differs from qBase + lane when sharded)
     __shared__ uint32_t sStack[WARPS][STACK];    // (level << 28) | (query lane << 23) | node   (node < 2^23: n <= 6.7e7)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = lane & (kFan - 1), g = lane >> kFanLog2;
     // lanes that precede this one in child-major order (c, g)
@@ -326,16 +327,19 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
     uint32_t* myStack = &sStack[warp][0];
     const float L = fp.edgeLength;
     const uint32_t ltMask = (1u << lane) - 1u;
-    const int numChunks = (n + 31) >> 5;
+    // queryList == nullptr: the queries are all sorted positions 0..n-1; otherwise (vertex-sharded multi-GPU step) the
+    // sorted positions of the vertices this rank owns, in sorted order
+    const int numChunks = (numQueries + 31) >> 5;
+    int* myPos = &sPos[warp][0];
     double totalPairs = 0.0, totalTests = 0.0;
   for (;;) {
     int chunk = 0;
     if (lane == 0) chunk = atomicAdd(chunkCounter, 1);
     chunk = __shfl_sync(0xffffffffu, chunk, 0);
     if (chunk >= numChunks) break;
-    const int qBase = chunk * 32;
-    const int qi = qBase + lane;
-    const bool valid = qi < n;
+    const int slot = chunk * 32 + lane;
+    const bool valid = slot < numQueries;
+    const int qi = valid ? (queryList ? __ldg(queryList + slot) : slot) : -1;
     float4 q[V];
     float iwq = 1.f;
     int v = -1, rowBegin = 0, rowEnd = 0;
@@ -353,6 +357,7 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
 #pragma unroll
     for (int k = 0; k < V; ++k) myQ[lane * V + k] = q[k];
     myIw[lane] = iwq;
+    myPos[lane] = qi;
     // Forces are summed in double: a vertex can own hundreds of repulsive terms in a collapsed layout, and the optimizer
     // normalises every component, so a component that is a cancellation residue must keep the accuracy of its terms.
     double acc[4 * V];
@@ -392,7 +397,7 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
         const uint32_t pb = __ballot_sync(0xffffffffu, toPush);
         if (toPush) myStack[sp + __popc(pb & before)] = ((uint32_t)lv << 28) | ((uint32_t)qq << 23) | (uint32_t)idx;
         sp += __popc(pb);
-        bool hit = pass && lv == 0 && (idx != qBase + qq);
+        bool hit = pass && lv == 0 && (idx != myPos[qq]);
         if (active && lv == 0) ++nTests;
         if (hit) {
             const float dist = sqrtf(d2);
@@ -456,8 +461,8 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
 // and emits the sums {lossA, lossR, sum_v xnew[v][k]} for the deterministic reducer.
 template <int V, int G>
 __global__ void __launch_bounds__(256) k_attract_update(const float4* __restrict__ x, const float* __restrict__ iw,
-                                                        const int* __restrict__ rowPtr, const int* __restrict__ col, int n,
-                                                        int vertsPerBlock, const ForceParams fp,
+                                                        const int* __restrict__ rowPtr, const int* __restrict__ col, int rangeBegin,
+                                                        int rangeEnd, int vertsPerBlock, const ForceParams fp,
                                                         const double* __restrict__ forceRep, const float* __restrict__ lossRep,
                                                         const int* __restrict__ coincidentRep, float4* __restrict__ xNew,
                                                         float4* __restrict__ mom1, float4* __restrict__ mom2,
@@ -467,8 +472,8 @@ __global__ void __launch_bounds__(256) k_attract_update(const float4* __restrict
     __shared__ double unitBuf[8][GROUPS_PER_WARP][4 * V];
     __shared__ double redBuf[8 * K];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, lig = lane % G, gInWarp = lane / G;
-    const int vBegin = blockIdx.x * vertsPerBlock;
-    const int vEnd = min(n, vBegin + vertsPerBlock);
+    const int vBegin = rangeBegin + blockIdx.x * vertsPerBlock;     // [rangeBegin, rangeEnd): the vertices this rank owns
+    const int vEnd = min(rangeEnd, vBegin + vertsPerBlock);
     double sums[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) sums[k] = 0.0;
@@ -597,14 +602,14 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const double* __restric
 // applyGravityCentre + observeDisplacement (WembedEmbedder.cpp:303-352): x = xnew - centroid, and the sums of
 // ||x - xprev|| and ||x||^2.  forceSums = output of the reducer for k_attract_update ({lossA, lossR, sum xnew[k]}).
 template <int V>
-__global__ void __launch_bounds__(256) k_recentre_observe(float4* __restrict__ x, const float4* __restrict__ xNew, int n,
-                                                          int vertsPerBlock, int dim, const double* __restrict__ forceSums,
+__global__ void __launch_bounds__(256) k_recentre_observe(float4* __restrict__ x, const float4* __restrict__ xNew, int n, int rangeBegin,
+                                                          int rangeEnd, int vertsPerBlock, int dim, const double* __restrict__ forceSums,
                                                           double* __restrict__ partials) {
     __shared__ double redBuf[8 * 2];
     float cen[4 * V];
 #pragma unroll
     for (int k = 0; k < 4 * V; ++k) cen[k] = (k < dim) ? (float)(forceSums[2 + k] / (double)n) : 0.f;
-    const int vBegin = blockIdx.x * vertsPerBlock, vEnd = min(n, vBegin + vertsPerBlock);
+    const int vBegin = rangeBegin + blockIdx.x * vertsPerBlock, vEnd = min(rangeEnd, vBegin + vertsPerBlock);
     double sums[2] = {0.0, 0.0};
     for (int v = vBegin + threadIdx.x; v < vEnd; v += 256) {
         float disp2 = 0.f, rad2 = 0.f;
@@ -623,6 +628,26 @@ __global__ void __launch_bounds__(256) k_recentre_observe(float4* __restrict__ x
     }
     block_sum<2, 256>(sums, redBuf, partials + (int64_t)blockIdx.x * 2);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Multi-GPU: every rank contributes `cols` partial sums; all ranks add them in rank order, so the totals are identical
+// on every rank and do not depend on arrival order.
+__global__ void k_sum_ranks(const double* __restrict__ gathered, int world, int cols, double* __restrict__ out) {
+    const int k = threadIdx.x;
+    if (k >= cols) return;
+    double s = 0.0;
+    for (int r = 0; r < world; ++r) s += gathered[r * cols + k];
+    out[k] = s;
+}
+
+struct OwnedPosition {        // predicate of the owned-query compaction: sorted position -> is its vertex in [lo, hi)?
+    const int* ids;
+    int lo, hi;
+    __device__ __forceinline__ bool operator()(int pos) const {
+        const int v = ids[pos];
+        return v >= lo && v < hi;
+    }
+};
 
 // ---------------------------------------------------------------------------------------------
 // Boundary conversions (coordinates cross the C ABI as row-major n x d doubles).

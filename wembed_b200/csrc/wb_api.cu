@@ -4,6 +4,9 @@
 // kernel launches on that stream (see enqueue_step); the only host<->device traffic per step is one
 // small D2H copy of the reduced sums.  There is no CPU fallback anywhere in this file.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+#include <nccl.h>
 
 #include <algorithm>
 #include <cmath>
@@ -85,6 +88,17 @@ struct wb_embedder {
     double *partialsForce = nullptr, *partialsRep = nullptr, *partialsObs = nullptr, *sumsAll = nullptr;
     int sumsTotal = 0;
 
+    // vertex-sharded multi-GPU step (wb_comm_init): this rank owns vertices [ownBegin, ownEnd); x is replicated and
+    // re-assembled by an all-gather of the owners' rows at the end of every step
+    ncclComm_t comm = nullptr;
+    int world = 1, rank = 0, ownBegin = 0, ownEnd = 0, rowsPerRank = 0;
+    int* ownedList = nullptr;             // sorted positions of the owned vertices, rebuilt every step
+    int* ownedCount = nullptr;
+    void* selectTemp = nullptr;
+    size_t selectBytes = 0;
+    double* gathered = nullptr;           // world x sumsTotal doubles
+    double* localSums = nullptr;          // this rank's share of sumsAll
+
     std::deque<PendingStep> pending;
     std::vector<PendingStep> freeSlots;
 
@@ -121,7 +135,8 @@ void free_all(wb_embedder* h) {
     F(h->iw); F(h->lossRep); F(h->coincident); F(h->chunkCounter); F(h->keysIn); F(h->keysOut); F(h->valsIn); F(h->valsOut);
     F(h->cubTemp); F(h->momentPartials); F(h->quant); F(h->ids);
     for (int l = 0; l < wb::kMaxLevels; ++l) { F(h->lvlLo[l]); if (l > 0) F(h->lvlHi[l]); F(h->lvlBound[l]); }
-    F(h->partialsForce); F(h->partialsRep); F(h->partialsObs); F(h->sumsAll);
+    F(h->partialsForce); F(h->partialsRep); F(h->partialsObs); F(h->sumsAll); F(h->ownedList); F(h->ownedCount); F(h->selectTemp); F(h->gathered); F(h->localSums);
+    if (h->comm) { ncclCommDestroy(h->comm); h->comm = nullptr; }
     for (auto& p : h->pending) { cudaEventDestroy(p.done); cudaFreeHost(p.hostSums); }
     for (auto& p : h->freeSlots) { cudaEventDestroy(p.done); cudaFreeHost(p.hostSums); }
     h->pending.clear(); h->freeSlots.clear();
@@ -212,6 +227,7 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
     h->obsBlocks = std::max(1, std::min(div_up(n, 256), 148 * 8));
     h->obsVertsPerBlock = std::max(256, div_up(div_up(n, h->obsBlocks), 256) * 256);
     h->obsBlocks = std::max(1, div_up(n, h->obsVertsPerBlock));
+    h->ownBegin = 0; h->ownEnd = n; h->rowsPerRank = n;
     const int K = 2 + 4 * V;
     h->sumsTotal = K + 4;
     h->partialsForce = dalloc<double>((size_t)h->forceBlocks * K);
@@ -291,22 +307,48 @@ void enqueue_step(wb_embedder* h, double learningRate) {
     fp.keepForces = h->opt.keep_forces;
     const int K = 2 + 4 * V;
 
+    const bool sharded = h->world > 1;
+    double* sums = sharded ? h->localSums : h->sumsAll;      // a sharded step reduces locally first, then across ranks
+    const int ownCount = std::max(0, h->ownEnd - h->ownBegin);
+
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[0], s));
     enqueue_index(h, h->iw);
+    const int* queryList = nullptr;
+    if (sharded) {   // the queries of this rank: sorted positions whose vertex it owns, in sorted order
+        wb::OwnedPosition pred{h->ids, h->ownBegin, h->ownEnd};
+        WB_CUDA(cub::DeviceSelect::If(h->selectTemp, h->selectBytes, cub::CountingInputIterator<int>(0), h->ownedList, h->ownedCount, n, pred, s));
+        queryList = h->ownedList;
+        h->launches += 1;
+    }
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[1], s));
     WB_CUDA(cudaMemsetAsync(h->chunkCounter, 0, sizeof(int), s));
     WB_DISPATCH_V(V, wb::k_repulse_pairs<V><<<h->repBlocks, 256, 0, s>>>(h->tree, h->rowPtr, h->col, n, fp, h->forceRep, h->lossRep,
-                                                                          h->coincident, h->chunkCounter, h->partialsRep));
-    wb::k_reduce_partials<<<2, 256, 0, s>>>(h->partialsRep, h->repBlocks * 8, 2, h->sumsAll + K);
+                                                                          h->coincident, h->chunkCounter, queryList, sharded ? ownCount : n,
+                                                                          h->partialsRep));
+    wb::k_reduce_partials<<<2, 256, 0, s>>>(h->partialsRep, h->repBlocks * 8, 2, sums + K);
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[2], s));
     WB_DISPATCH_V(V, wb::k_attract_update<V, 8><<<h->forceBlocks, 256, 0, s>>>(
-                         h->x, h->iw, h->rowPtr, h->col, n, h->forceVertsPerBlock, fp, h->forceRep, h->lossRep, h->coincident, h->xNew,
-                         h->mom1, h->mom2, h->force, h->partialsForce));
-    wb::k_reduce_partials<<<K, 256, 0, s>>>(h->partialsForce, h->forceBlocks, K, h->sumsAll);
+                         h->x, h->iw, h->rowPtr, h->col, h->ownBegin, h->ownEnd, h->forceVertsPerBlock, fp, h->forceRep, h->lossRep,
+                         h->coincident, h->xNew, h->mom1, h->mom2, h->force, h->partialsForce));
+    wb::k_reduce_partials<<<K, 256, 0, s>>>(h->partialsForce, h->forceBlocks, K, sums);
+    if (sharded) {   // {lossA, lossR, sum xnew[k], pairs, tests}: all-gather, then every rank adds in rank order
+        if (ncclAllGather(sums, h->gathered, K + 2, ncclDouble, h->comm, s) != ncclSuccess) throw std::runtime_error("ncclAllGather (force sums) failed");
+        wb::k_sum_ranks<<<1, 256, 0, s>>>(h->gathered, h->world, K + 2, h->sumsAll);
+    }
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[3], s));
-    WB_DISPATCH_V(V, wb::k_recentre_observe<V><<<h->obsBlocks, 256, 0, s>>>(h->x, h->xNew, n, h->obsVertsPerBlock, h->dim, h->sumsAll,
-                                                                              h->partialsObs));
-    wb::k_reduce_partials<<<2, 256, 0, s>>>(h->partialsObs, h->obsBlocks, 2, h->sumsAll + K + 2);
+    WB_DISPATCH_V(V, wb::k_recentre_observe<V><<<h->obsBlocks, 256, 0, s>>>(h->x, h->xNew, n, h->ownBegin, h->ownEnd, h->obsVertsPerBlock, h->dim,
+                                                                              h->sumsAll, h->partialsObs));
+    wb::k_reduce_partials<<<2, 256, 0, s>>>(h->partialsObs, h->obsBlocks, 2, sums + K + 2);
+    if (sharded) {
+        if (ncclAllGather(sums + K + 2, h->gathered, 2, ncclDouble, h->comm, s) != ncclSuccess) throw std::runtime_error("ncclAllGather (observe sums) failed");
+        wb::k_sum_ranks<<<1, 256, 0, s>>>(h->gathered, h->world, 2, h->sumsAll + K + 2);
+        // publish the owners' updated rows: x is replicated again for the next step's index build and gathers
+        const size_t rowFloats = (size_t)h->rowsPerRank * h->rowFloats;
+        float* xf = reinterpret_cast<float*>(h->x);
+        if (ncclAllGather(xf + (size_t)h->rank * rowFloats, xf, rowFloats, ncclFloat, h->comm, s) != ncclSuccess)
+            throw std::runtime_error("ncclAllGather (coordinates) failed");
+        h->launches += 2;
+    }
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[4], s));
     h->launches += 6;
     WB_CUDA(cudaGetLastError());
@@ -557,6 +599,63 @@ int wb_get_phase_times(wb_embedder* h, double* ms6) {
     if (!h->havePhase) return fail(WB_ERR_INVALID, "wb_get_phase_times: enable timing and run a synchronous step first");
     std::copy(h->phaseMs, h->phaseMs + 6, ms6);
     return WB_OK;
+}
+
+int wb_comm_unique_id(char* id128) {
+    if (!id128) return fail(WB_ERR_INVALID, "wb_comm_unique_id: null buffer");
+    static_assert(sizeof(ncclUniqueId) <= 128, "ncclUniqueId does not fit the ABI buffer");
+    ncclUniqueId id;
+    if (ncclGetUniqueId(&id) != ncclSuccess) return fail(WB_ERR_CUDA, "ncclGetUniqueId failed");
+    std::memset(id128, 0, 128);
+    std::memcpy(id128, &id, sizeof(id));
+    return WB_OK;
+}
+
+int wb_comm_init(wb_embedder* h, const char* id128, int32_t rank, int32_t world) {
+    if (h && (!id128 || world < 1 || rank < 0 || rank >= world)) return fail(WB_ERR_INVALID, "wb_comm_init: bad arguments");
+    if (h && h->comm) return fail(WB_ERR_INVALID, "wb_comm_init: already initialised");
+    if (h && !h->pending.empty()) return fail(WB_ERR_INVALID, "wb_comm_init: steps in flight");
+    return guarded(h, [&] {
+        if (world == 1) return;
+        ncclUniqueId id;
+        std::memcpy(&id, id128, sizeof(id));
+        if (ncclCommInitRank(&h->comm, world, id, rank) != ncclSuccess) throw std::runtime_error("ncclCommInitRank failed");
+        const int n = h->n, V = h->V;
+        h->world = world;
+        h->rank = rank;
+        h->rowsPerRank = div_up(std::max(n, 1), world);
+        h->ownBegin = std::min(n, rank * h->rowsPerRank);
+        h->ownEnd = std::min(n, h->ownBegin + h->rowsPerRank);
+        // x / xNew need world * rowsPerRank rows so the in-place all-gather has equal chunks
+        const size_t rows = (size_t)n * V, padded = (size_t)h->rowsPerRank * world * V;
+        for (float4** p : {&h->x, &h->xNew}) {
+            float4* q = dalloc<float4>(padded);
+            WB_CUDA(cudaMemsetAsync(q, 0, std::max<size_t>(padded, 1) * sizeof(float4), h->stream));
+            if (rows) WB_CUDA(cudaMemcpyAsync(q, *p, rows * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
+            WB_CUDA(cudaStreamSynchronize(h->stream));
+            cudaFree(*p);
+            *p = q;
+        }
+        // block -> vertex-range assignment over the owned range
+        const int own = std::max(1, h->ownEnd - h->ownBegin), groupsPerBlock = 256 / 8, K = 2 + 4 * V;
+        h->forceBlocks = std::max(1, std::min(div_up(own, groupsPerBlock), 148 * 16));
+        h->forceVertsPerBlock = std::max(groupsPerBlock, div_up(div_up(own, h->forceBlocks), groupsPerBlock) * groupsPerBlock);
+        h->forceBlocks = std::max(1, div_up(own, h->forceVertsPerBlock));
+        h->obsBlocks = std::max(1, std::min(div_up(own, 256), 148 * 8));
+        h->obsVertsPerBlock = std::max(256, div_up(div_up(own, h->obsBlocks), 256) * 256);
+        h->obsBlocks = std::max(1, div_up(own, h->obsVertsPerBlock));
+        h->ownedList = dalloc<int>(n);
+        h->ownedCount = dalloc<int>(1);
+        h->selectBytes = 0;
+        wb::OwnedPosition pred{h->ids, h->ownBegin, h->ownEnd};
+        WB_CUDA(cub::DeviceSelect::If(nullptr, h->selectBytes, cub::CountingInputIterator<int>(0), h->ownedList, h->ownedCount, std::max(n, 1), pred, h->stream));
+        h->selectTemp = dalloc<char>(h->selectBytes);
+        h->gathered = dalloc<double>((size_t)world * h->sumsTotal);
+        h->localSums = dalloc<double>(h->sumsTotal);
+        WB_CUDA(cudaMemsetAsync(h->localSums, 0, sizeof(double) * h->sumsTotal, h->stream));
+        WB_CUDA(cudaStreamSynchronize(h->stream));
+        (void)K;
+    });
 }
 
 int wb_mark(wb_embedder* h, int slot) {
