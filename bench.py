@@ -54,17 +54,19 @@ def make_workload(name, rank=0, world=1):
     from wembed_b200.datasets import degree_weights, geometric_graph, heavy_tailed_graph, initial_coordinates
     n, deg, d, family = WORKLOADS[name]
     seed = 42         # every rank builds the same graph: at N > 1 it is sharded by vertex range (strong scaling)
-    cache = os.path.join(ROOT, "gpurun_out", f"_wl_{name}_{seed}.npz")
+    cache = os.path.join(ROOT, "gpurun_out", f"_wl_{name}_{seed}.npy")
     if os.path.exists(cache):
-        z = np.load(cache)
-        edges = z["edges"]
+        edges = np.load(cache)
     else:
         edges = geometric_graph(n, deg, seed)[0] if family == "geometric" else heavy_tailed_graph(n, deg, seed=seed)[0]
-        try:
-            os.makedirs(os.path.dirname(cache), exist_ok=True)
-            np.savez(cache, edges=edges)
-        except OSError:
-            pass
+        if rank == 0:
+            try:
+                os.makedirs(os.path.dirname(cache), exist_ok=True)
+                tmp = cache + f".tmp{os.getpid()}.npy"
+                np.save(tmp, edges)
+                os.replace(tmp, cache)      # atomic: other ranks either see the whole file or none
+            except OSError:
+                pass
     rp, col = cabi.csr_from_edges(n, edges)
     w = degree_weights(n, edges, d)
     x0 = initial_coordinates(n, d, seed=1234)
@@ -138,20 +140,47 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    dev = cabi.DeviceEmbedder(wl["row_ptr"], wl["col"], embedding_dimension=d, device=local, seed=1234)
-    dev.set_weights(wl["weights"])
-    dev.set_coordinates(wl["x0"])
-    if world > 1:   # one graph, vertices range-partitioned over the GPUs, NCCL all-gather of the updated rows every step
-        from wembed_b200 import sharding
-        sharding.shard_embedder(dev, rank, world, torch.device("cuda", local))
-    it = 0
-    for _ in range(args.warmup):
+    def fresh():
+        """A new handle advanced by the W warm-up steps: every measurement below starts from the same layout AND the same
+        optimizer state (the Adam moments cannot be restored through the ABI, so the warm-up is simply repeated)."""
+        dev = cabi.DeviceEmbedder(wl["row_ptr"], wl["col"], embedding_dimension=d, device=local, seed=1234)
+        dev.set_weights(wl["weights"])
+        dev.set_coordinates(wl["x0"])
+        if world > 1:   # one graph, vertices range-partitioned over the GPUs, NCCL all-gather of the updated rows every step
+            from wembed_b200 import sharding
+            sharding.shard_embedder(dev, rank, world, torch.device("cuda", local))
+        for i in range(1, args.warmup + 1):
+            dev.step(lr_schedule(i))
+        return dev
+
+    def max_over_ranks(seconds):
+        t = torch.tensor([seconds], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- e2e: blocking C ABI, host buffers in and out ---------------------------------------------------------
+    dev = fresh()
+    x_start = dev.coordinates()          # layout at the start of the timed window (also the CPU baseline's input)
+    it = args.warmup
+    barrier()
+    t0 = time.perf_counter()
+    dev.mark(2)
+    dev.set_coordinates(x_start)
+    for _ in range(args.steps):
         it += 1
         dev.step(lr_schedule(it))
-    x_start = dev.coordinates()          # state at the start of the timed window (also the CPU baseline's input)
-    launches_per_step = None
+    x_end = dev.coordinates()
+    dev.mark(3)
+    de_events = dev.elapsed_ms(2, 3) * 1e-3
+    barrier()
+    de = max_over_ranks(max(time.perf_counter() - t0, de_events))   # host-visible time of the blocking calls (>= the device time)
+    assert np.isfinite(x_end).all()
+    dev.close()
 
-    # ---- value: device-resident, K async steps, one collect at the end --------------------------------------
+    # ---- value: device-resident, K asynchronous steps, CUDA events on the handle's stream ---------------------
+    dev = fresh()
+    it = args.warmup
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
@@ -170,46 +199,24 @@ def run_ours(args):
     while inflight:
         stats.append(dev.step_collect())
         inflight -= 1
-    dt = dev.elapsed_ms(0, 1) * 1e-3     # CUDA events on the stream the kernels are launched on
+    dt = dev.elapsed_ms(0, 1) * 1e-3
     launches = dev.launch_count() - launches0
     barrier()
     clocks = sampler.stop()
-    t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dt = float(t.item())
+    dt = max_over_ranks(dt)
+    dev.close()
 
-    # ---- per-phase device times (CUDA events on the handle's stream) over the same trajectory window -------
-    dev.set_coordinates(x_start)
+    # ---- per-phase device times (CUDA events around each phase) over the same window -----------------------------
+    dev = fresh()
     dev.enable_timing(True)
-    it_p = args.warmup
+    it = args.warmup
     phases = []
-    for _ in range(min(args.steps, 20)):
-        it_p += 1
-        dev.step(lr_schedule(it_p))
-        phases.append(dev.phase_times())
-    dev.enable_timing(False)
-    ph = {k: float(np.mean([p[k] for p in phases])) for k in phases[0]}
-
-    # ---- e2e: blocking C ABI, host buffers in and out ---------------------------------------------------------
-    it_e = args.warmup
-    barrier()
-    t0 = time.perf_counter()
-    dev.mark(2)
-    dev.set_coordinates(x_start)
     for _ in range(args.steps):
-        it_e += 1
-        dev.step(lr_schedule(it_e))
-    x_end = dev.coordinates()
-    dev.mark(3)
-    de_events = dev.elapsed_ms(2, 3) * 1e-3
-    barrier()
-    de = max(time.perf_counter() - t0, de_events)   # host-visible time of the blocking calls (>= the device time)
-    t = torch.tensor([de], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    de = float(t.item())
-    assert np.isfinite(x_end).all()
+        it += 1
+        dev.step(lr_schedule(it))
+        phases.append(dev.phase_times())
+    ph = {k: float(np.mean([p[k] for p in phases])) for k in phases[0]}
+    dev.close()
 
     if rank != 0:
         return

@@ -78,7 +78,8 @@ typedef struct wb_step_stats {
     double rel_displacement;   /* state.lastRelDisplacement (:347-350)               */
     double num_repulsion_pairs;/* pairs that passed the neighbour filter and the     */
                                /*   exact weighted-distance test                      */
-    double num_candidates;     /* distance evaluations done by the repulsion walk    */
+    double num_candidates;     /* point (exact distance) tests of the repulsion walk */
+    double num_box_tests;      /* box tests of the repulsion walk                    */
     double centroid[32];       /* per-dimension mean removed by applyGravityCentre   */
     int64_t iteration;         /* state.currentIteration after the step              */
 } wb_step_stats;

@@ -41,7 +41,7 @@ class WbStepStats(C.Structure):
     _fields_ = [
         ("loss_attract", C.c_double), ("loss_repel", C.c_double), ("sum_displacement", C.c_double),
         ("sum_radius_sq", C.c_double), ("rel_displacement", C.c_double), ("num_repulsion_pairs", C.c_double),
-        ("num_candidates", C.c_double), ("centroid", C.c_double * 32), ("iteration", C.c_int64),
+        ("num_candidates", C.c_double), ("num_box_tests", C.c_double), ("centroid", C.c_double * 32), ("iteration", C.c_int64),
     ]
 
     def as_dict(self):

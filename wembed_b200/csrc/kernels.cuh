@@ -110,11 +110,11 @@ __global__ void k_quant_params(const float* __restrict__ partial, int numBlocks,
     qp->invCell[k] = (float)(1u << bits) / (hi - lo);
 }
 
-// Index, stage 3: Morton key of every vertex (bit b of dimension k -> key bit b*dim + k).
+// Index, stage 3: Morton key of every vertex (bit b of dimension k -> key bit b*dim + k), weight band on top.
 template <int V>
 __global__ void __launch_bounds__(256) k_morton_keys(const float4* __restrict__ x, int n, int dim, int bits,
-                                                     const QuantParams* __restrict__ qp, uint32_t* __restrict__ keys,
-                                                     int* __restrict__ vals) {
+                                                     const QuantParams* __restrict__ qp, const uint8_t* __restrict__ band,
+                                                     uint32_t* __restrict__ keys, int* __restrict__ vals) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n) return;
     const uint32_t qmax = (1u << bits) - 1u;
@@ -133,6 +133,9 @@ __global__ void __launch_bounds__(256) k_morton_keys(const float4* __restrict__ 
             }
         }
     }
+    // weight band in the top bits (bits * dim .. ): points whose interaction radius differs by more than a factor of two
+    // live in separate subtrees, so one heavy vertex cannot inflate the pruning bound of a subtree of light ones
+    if (band) key |= (uint32_t)band[v] << (bits * dim);
     keys[v] = key;
     vals[v] = v;
 }
@@ -304,15 +307,19 @@ __device__ __forceinline__ bool is_neighbor(const int* __restrict__ col, int beg
 // left, so warps whose queries need long walks do not hold finished warps of the same block hostage (measured: 28 %
 // of all stall samples sat on the final block barrier before).  Which warp handles which chunk does not influence
 // any result: a query's force depends only on its own walk, and the two statistics counters are integers.
+// warps per block of k_repulse_pairs: the per-warp shared memory (queries + stack) grows with V
+__host__ __device__ constexpr int repulse_warps(int V) { return V <= 4 ? 8 : 4; }
+
 template <int V>
 __global__ void __launch_bounds__(256, (V <= 2 ? 4 : (V <= 4 ? 2 : 1)))
 k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __restrict__ col, int n, const ForceParams fp,
                 double* __restrict__ forceRep, float* __restrict__ lossRep, int* __restrict__ coincident, int* __restrict__ chunkCounter,
                 const int* __restrict__ queryList, int numQueries, double* __restrict__ partials) {
-    constexpr int WARPS = 8, STACK = 28 * kMaxLevels + 36;   // LIFO bound: <= 28 leftovers per level + one push of 32
+    constexpr int WARPS = repulse_warps(V), STACK = 56 * kMaxLevels + 72;   // LIFO bound: <= 56 leftovers per level + one push of 64
     __shared__ float4 sQ[WARPS][32][V];
     __shared__ float sIw[WARPS][32];
-    __shared__ int sPos[WARPS][32];              // sorted position of each query (differs from qBase + lane when sharded)
+    __shared__ int sPos[WARPS][32];              // sorted position of each query (differs from chunk * 32 + lane when sharded)
+    __shared__ int sVert[WARPS][32];             // vertex id of each query
     __shared__ uint32_t sStack[WARPS][STACK];    // (level << 28) | (query lane << 23) | node   (node < 2^23: n <= 6.7e7)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = lane & (kFan - 1), g = lane >> kFanLog2;
     // lanes that precede this one in child-major order (c, g)
@@ -324,154 +331,220 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
     }
     float4* myQ = &sQ[warp][0][0];
     float* myIw = &sIw[warp][0];
+    int* myPos = &sPos[warp][0];
+    int* myVert = &sVert[warp][0];
     uint32_t* myStack = &sStack[warp][0];
     const float L = fp.edgeLength;
     const uint32_t ltMask = (1u << lane) - 1u;
     // queryList == nullptr: the queries are all sorted positions 0..n-1; otherwise (vertex-sharded multi-GPU step) the
     // sorted positions of the vertices this rank owns, in sorted order
     const int numChunks = (numQueries + 31) >> 5;
-    int* myPos = &sPos[warp][0];
-    double totalPairs = 0.0, totalTests = 0.0;
-  for (;;) {
-    int chunk = 0;
-    if (lane == 0) chunk = atomicAdd(chunkCounter, 1);
-    chunk = __shfl_sync(0xffffffffu, chunk, 0);
-    if (chunk >= numChunks) break;
-    const int slot = chunk * 32 + lane;
-    const bool valid = slot < numQueries;
-    const int qi = valid ? (queryList ? __ldg(queryList + slot) : slot) : -1;
-    float4 q[V];
-    float iwq = 1.f;
-    int v = -1, rowBegin = 0, rowEnd = 0;
-    if (valid) {
-#pragma unroll
-        for (int k = 0; k < V; ++k) q[k] = __ldg(t.lo[0] + (int64_t)k * t.stride[0] + qi);
-        iwq = __ldg(t.bound[0] + qi);
-        v = __ldg(t.ids + qi);
-        rowBegin = __ldg(rowPtr + v);
-        rowEnd = __ldg(rowPtr + v + 1);
-    } else {
-#pragma unroll
-        for (int k = 0; k < V; ++k) q[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int k = 0; k < V; ++k) myQ[lane * V + k] = q[k];
-    myIw[lane] = iwq;
-    myPos[lane] = qi;
-    // Forces are summed in double: a vertex can own hundreds of repulsive terms in a collapsed layout, and the optimizer
-    // normalises every component, so a component that is a cancellation residue must keep the accuracy of its terms.
-    double acc[4 * V];
-#pragma unroll
-    for (int k = 0; k < 4 * V; ++k) acc[k] = 0.0;
-    double loss = 0.0;
-    int nCoincident = 0, nPairs = 0, nTests = 0;
+    int nPairs = 0, nTests = 0, nBoxTests = 0;
 
-    const uint32_t validMask = __ballot_sync(0xffffffffu, valid);
-    if (valid) myStack[__popc(validMask & ltMask)] = ((uint32_t)(t.numLevels + 1) << 28) | ((uint32_t)lane << 23);
-    int sp = __popc(validMask);
-    __syncwarp();
-    while (sp > 0) {
-        const int take = min(4, sp);
-        const bool active = g < take;
-        const uint32_t entry = myStack[active ? sp - 1 - g : 0];
-        sp -= take;
-        const int lv = active ? (int)(entry >> 28) - 1 : 0;
-        const int idx = active ? (int)(entry & 0x007fffffu) * kFan + c : 0;
-        const int qq = (int)((entry >> 23) & 31u);
+    // One (node, query) pair of the round: lane c tests child c.  Returns pass; lv / idx / qq / d2 / s describe the test.
+    struct Slot { int lv, idx, qq; float d2, s; bool active, pass; };
+    auto testEntry = [&](uint32_t entry, bool active) {
+        Slot r;
+        r.active = active;
+        r.lv = active ? (int)(entry >> 28) - 1 : 0;
+        r.idx = active ? (int)(entry & 0x007fffffu) * kFan + c : 0;
+        r.qq = (int)((entry >> 23) & 31u);
         float4 lo[V], hi[V], qv[V];
-        const int64_t st = t.stride[lv];
-        const float4* loP = t.lo[lv];
-        const float4* hiP = t.hi[lv];         // == lo for level 0
+        const int64_t st = t.stride[r.lv];
+        const float4* loP = t.lo[r.lv];
+        const float4* hiP = t.hi[r.lv];         // == lo for level 0
 #pragma unroll
-        for (int k = 0; k < V; ++k) lo[k] = __ldg(loP + k * st + idx);
+        for (int k = 0; k < V; ++k) lo[k] = __ldg(loP + k * st + r.idx);
 #pragma unroll
-        for (int k = 0; k < V; ++k) hi[k] = __ldg(hiP + k * st + idx);
-        const float bnd = __ldg(t.bound[lv] + idx);
+        for (int k = 0; k < V; ++k) hi[k] = __ldg(hiP + k * st + r.idx);
+        const float bnd = __ldg(t.bound[r.lv] + r.idx);
 #pragma unroll
-        for (int k = 0; k < V; ++k) qv[k] = myQ[qq * V + k];
-        const float s = myIw[qq] * bnd;
-        const float d2 = box_dist2<V>(qv, lo, hi);
-        const bool pass = active && (d2 * s * s <= fp.pruneL2);
-        __syncwarp();                          // every lane has read its entry before the stack is overwritten
-        const bool toPush = pass && lv > 0;
-        const uint32_t pb = __ballot_sync(0xffffffffu, toPush);
-        if (toPush) myStack[sp + __popc(pb & before)] = ((uint32_t)lv << 28) | ((uint32_t)qq << 23) | (uint32_t)idx;
-        sp += __popc(pb);
-        bool hit = pass && lv == 0 && (idx != myPos[qq]);
-        if (active && lv == 0) ++nTests;
+        for (int k = 0; k < V; ++k) qv[k] = myQ[r.qq * V + k];
+        r.s = myIw[r.qq] * bnd;
+        r.d2 = box_dist2<V>(qv, lo, hi);
+        r.pass = active && (r.d2 * r.s * r.s <= fp.pruneL2);
+        return r;
+    };
+    // Level-0 passes: the tester lane evaluates the exact predicate, the owner lane of the query applies the neighbour filter
+    // and accumulates into its row of forceRep (read-modify-write in global memory: hits are rare - a handful per query -
+    // and keeping the accumulators out of registers buys occupancy for the walk).
+    auto resolveHits = [&](const Slot& r) {
+        bool hit = r.pass && r.lv == 0 && (r.idx != myPos[r.qq]);
         if (hit) {
-            const float dist = sqrtf(d2);
-            if (dist > 0.f) hit = dist * s <= L;           // exact predicate; dist <= 0 is the coincident case
+            const float dist = sqrtf(r.d2);
+            if (dist > 0.f) hit = dist * r.s <= L;           // exact predicate; dist <= 0 is the coincident case
         }
         uint32_t hb = __ballot_sync(0xffffffffu, hit);
         while (hb) {
             const int hl = __ffs(hb) - 1;
             hb &= hb - 1u;
-            const int owner = __shfl_sync(0xffffffffu, qq, hl);
-            const int pidx = __shfl_sync(0xffffffffu, idx, hl);
+            const int owner = __shfl_sync(0xffffffffu, r.qq, hl);
+            const int pidx = __shfl_sync(0xffffffffu, r.idx, hl);
             if (lane == owner) {
-                float4 pu[V];
+                float4 q[V], pu[V];
 #pragma unroll
-                for (int k = 0; k < V; ++k) pu[k] = __ldg(t.lo[0] + (int64_t)k * t.stride[0] + pidx);
+                for (int k = 0; k < V; ++k) { q[k] = myQ[lane * V + k]; pu[k] = __ldg(t.lo[0] + (int64_t)k * t.stride[0] + pidx); }
                 const float iwu = __ldg(t.bound[0] + pidx);
                 const int u = __ldg(t.ids + pidx);
-                const float e2 = box_dist2<V>(q, pu, pu);
-                const float dist = sqrtf(e2);
-                const float ws = iwq * iwu;
+                const int v = myVert[lane];
+                const float dist = sqrtf(box_dist2<V>(q, pu, pu));
+                const float ws = myIw[lane] * iwu;
                 if (dist <= 0.f) {
-                    if (!is_neighbor(col, rowBegin, rowEnd, u)) ++nCoincident;
+                    if (!is_neighbor(col, __ldg(rowPtr + v), __ldg(rowPtr + v + 1), u)) coincident[v] += 1;
                 } else if (dist * ws <= L) {
-                    if (!is_neighbor(col, rowBegin, rowEnd, u)) {
-                        axpy_diff_d<V>(acc, fp.repulsionScale * ws / dist, q, pu);
-                        loss += (double)(L / ws - dist);
+                    if (!is_neighbor(col, __ldg(rowPtr + v), __ldg(rowPtr + v + 1), u)) {
+                        // summed in double: a vertex can own hundreds of repulsive terms in a collapsed layout and the optimizer
+                        // normalises every component, so a cancellation residue must keep the accuracy of its terms
+                        double* fr = forceRep + (int64_t)v * 4 * V;
+                        const float sc = fp.repulsionScale * ws / dist;
+#pragma unroll
+                        for (int k = 0; k < V; ++k) {
+                            fr[4 * k + 0] += (double)(sc * (q[k].x - pu[k].x));
+                            fr[4 * k + 1] += (double)(sc * (q[k].y - pu[k].y));
+                            fr[4 * k + 2] += (double)(sc * (q[k].z - pu[k].z));
+                            fr[4 * k + 3] += (double)(sc * (q[k].w - pu[k].w));
+                        }
+                        lossRep[v] += L / ws - dist;
                         ++nPairs;
                     }
                 }
             }
         }
-        __syncwarp();
-    }
-    if (valid) {
+    };
+
+    for (;;) {
+        int chunk = 0;
+        if (lane == 0) chunk = atomicAdd(chunkCounter, 1);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if (chunk >= numChunks) break;
+        const int slot = chunk * 32 + lane;
+        const bool valid = slot < numQueries;
+        const int qi = valid ? (queryList ? __ldg(queryList + slot) : slot) : -1;
+        if (valid) {
 #pragma unroll
-        for (int k = 0; k < 4 * V; ++k) forceRep[(int64_t)v * 4 * V + k] = acc[k];
-        lossRep[v] = (float)loss;
-        coincident[v] = nCoincident;
+            for (int k = 0; k < V; ++k) myQ[lane * V + k] = __ldg(t.lo[0] + (int64_t)k * t.stride[0] + qi);
+            myIw[lane] = __ldg(t.bound[0] + qi);
+            const int v = __ldg(t.ids + qi);
+            myVert[lane] = v;
+            double* fr = forceRep + (int64_t)v * 4 * V;
+#pragma unroll
+            for (int k = 0; k < 4 * V; ++k) fr[k] = 0.0;
+            lossRep[v] = 0.f;
+            coincident[v] = 0;
+        }
+        myPos[lane] = qi;
+        const uint32_t validMask = __ballot_sync(0xffffffffu, valid);
+        if (valid) myStack[__popc(validMask & ltMask)] = ((uint32_t)(t.numLevels + 1) << 28) | ((uint32_t)lane << 23);
+        int sp = __popc(validMask);
+        __syncwarp();
+        while (sp > 0) {
+            // a round pops up to eight pairs: two per 8-lane group, tested back to back so their loads overlap
+            const int take = min(8, sp);
+            const bool activeA = g < take, activeB = g + 4 < take;
+            const uint32_t entryA = myStack[activeA ? sp - 1 - g : 0];
+            const uint32_t entryB = myStack[activeB ? sp - 5 - g : 0];
+            sp -= take;
+            const Slot a = testEntry(entryA, activeA);
+            const Slot b = testEntry(entryB, activeB);
+            __syncwarp();                          // every lane has read its entries before the stack is overwritten
+            const bool pushA = a.pass && a.lv > 0, pushB = b.pass && b.lv > 0;
+            const uint32_t pa = __ballot_sync(0xffffffffu, pushA), pb = __ballot_sync(0xffffffffu, pushB);
+            if (pushA) myStack[sp + __popc(pa & before)] = ((uint32_t)a.lv << 28) | ((uint32_t)a.qq << 23) | (uint32_t)a.idx;
+            sp += __popc(pa);
+            if (pushB) myStack[sp + __popc(pb & before)] = ((uint32_t)b.lv << 28) | ((uint32_t)b.qq << 23) | (uint32_t)b.idx;
+            sp += __popc(pb);
+            nTests += (a.active && a.lv == 0) + (b.active && b.lv == 0);
+            nBoxTests += (a.active && a.lv > 0) + (b.active && b.lv > 0);
+            resolveHits(a);
+            resolveHits(b);
+            __syncwarp();
+        }
     }
-    totalPairs += (double)nPairs;
-    totalTests += (double)nTests;
-    __syncwarp();
-  }
     // per-warp statistics (integers, so the order in which warps took chunks cannot change the reduced value)
+    double totalPairs = (double)nPairs, totalTests = (double)nTests, totalBoxTests = (double)nBoxTests;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         totalPairs += __shfl_xor_sync(0xffffffffu, totalPairs, o);
         totalTests += __shfl_xor_sync(0xffffffffu, totalTests, o);
+        totalBoxTests += __shfl_xor_sync(0xffffffffu, totalBoxTests, o);
     }
     if (lane == 0) {
         const int64_t w = (int64_t)blockIdx.x * WARPS + warp;
-        partials[2 * w] = totalPairs;
-        partials[2 * w + 1] = totalTests;
+        partials[3 * w] = totalPairs;
+        partials[3 * w + 1] = totalTests;
+        partials[3 * w + 2] = totalBoxTests;
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Attraction + centre force + optimizer, fused (WembedEmbedder.cpp:260-272, 140-172, 296-301; AdamOptimizer.cpp:15-30).
-// G lanes share one vertex: they stride over its CSR row, reduce with a fixed butterfly, add the repulsive force
-// computed by k_repulse, then lane c updates chunk c of x / m / v.  Each block owns a fixed contiguous vertex range
-// and emits the sums {lossA, lossR, sum_v xnew[v][k]} for the deterministic reducer.
-template <int V, int G>
+// One attractive pair (attractionForce, WembedEmbedder.cpp:140-172): adds the force of u on v to acc, returns the loss.
+template <int V>
+__device__ __forceinline__ void attract_pair(const float4 (&xv)[V], float iwv, const float4 (&xu)[V], float iwu, float L, float scale,
+                                             double (&acc)[4 * V], double& loss, int& nCoincident) {
+    const float d2 = point_dist2<V>(xu, xv);
+    const float dist = sqrtf(d2);
+    if (dist <= 0.f) { ++nCoincident; return; }               // :150-155, resolved by the caller
+    const float ws = iwv * iwu;
+    if (dist * ws > L) {                                       // :163-168
+        axpy_diff_d<V>(acc, scale * ws / dist, xu, xv);
+        loss += (double)(dist - L / ws);
+    }
+}
+
+// Hub rows (degree > hubThreshold; heavy-tailed graphs have rows of 1e4-1e5 entries): one block per hub strides over the row,
+// sums in double and reduces in a fixed order; k_attract_update picks the result up instead of walking the row itself.
+template <int V>
+__global__ void __launch_bounds__(256) k_attract_hubs(const float4* __restrict__ x, const float* __restrict__ iw, const int* __restrict__ rowPtr,
+                                                      const int* __restrict__ col, const int* __restrict__ hubVertex, const ForceParams fp,
+                                                      double* __restrict__ hubForce /* [hub][4V + 2] */) {
+    constexpr int K = 4 * V + 2;
+    __shared__ double redBuf[8 * K];
+    const int v = hubVertex[blockIdx.x];
+    float4 xv[V];
+    load_row<V>(x, v, xv);
+    const float iwv = __ldg(iw + v);
+    double vals[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) vals[k] = 0.0;
+    double acc[4 * V], loss = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4 * V; ++k) acc[k] = 0.0;
+    int nCoincident = 0;
+    const int end = __ldg(rowPtr + v + 1);
+    for (int e = __ldg(rowPtr + v) + threadIdx.x; e < end; e += 256) {
+        const int u = __ldg(col + e);
+        if (u == v) continue;
+        float4 xu[V];
+        load_row<V>(x, u, xu);
+        attract_pair<V>(xv, iwv, xu, __ldg(iw + u), fp.edgeLength, fp.attractionScale, acc, loss, nCoincident);
+    }
+#pragma unroll
+    for (int k = 0; k < 4 * V; ++k) vals[k] = acc[k];
+    vals[4 * V] = loss;
+    vals[4 * V + 1] = (double)nCoincident;
+    block_sum<K, 256>(vals, redBuf, hubForce + (int64_t)blockIdx.x * K);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Attraction + centre force + optimizer, fused (WembedEmbedder.cpp:260-272, 140-172, 296-301; AdamOptimizer.cpp:15-30):
+// the north_star's "fused step kernel".  One thread owns one vertex: it walks the CSR row (two edges in flight), sums in
+// double, adds the repulsive force of k_repulse_pairs, the centre force and the tie-break vectors, and updates x / m / v of
+// its row (a warp reads and writes 32 consecutive rows: coalesced).  No shuffles, no idle lanes; rows longer than the hub
+// threshold are pre-summed by k_attract_hubs.  Each block owns a fixed contiguous vertex range and emits
+// {lossA, lossR, sum_v xnew[v][k]} for the deterministic reducer.
+template <int V>
 __global__ void __launch_bounds__(256) k_attract_update(const float4* __restrict__ x, const float* __restrict__ iw,
                                                         const int* __restrict__ rowPtr, const int* __restrict__ col, int rangeBegin,
                                                         int rangeEnd, int vertsPerBlock, const ForceParams fp,
                                                         const double* __restrict__ forceRep, const float* __restrict__ lossRep,
-                                                        const int* __restrict__ coincidentRep, float4* __restrict__ xNew,
+                                                        const int* __restrict__ coincidentRep, const int* __restrict__ hubSlot,
+                                                        const double* __restrict__ hubForce, float4* __restrict__ xNew,
                                                         float4* __restrict__ mom1, float4* __restrict__ mom2,
                                                         float4* __restrict__ forceOut, double* __restrict__ partials) {
-    constexpr int GROUPS_PER_WARP = 32 / G, GROUPS_PER_BLOCK = 256 / G, K = 2 + 4 * V;
+    constexpr int K = 2 + 4 * V;
     __shared__ uint32_t mtState[8][624];
-    __shared__ double unitBuf[8][GROUPS_PER_WARP][4 * V];
     __shared__ double redBuf[8 * K];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, lig = lane % G, gInWarp = lane / G;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int vBegin = rangeBegin + blockIdx.x * vertsPerBlock;     // [rangeBegin, rangeEnd): the vertices this rank owns
     const int vEnd = min(rangeEnd, vBegin + vertsPerBlock);
     double sums[K];
@@ -479,53 +552,59 @@ __global__ void __launch_bounds__(256) k_attract_update(const float4* __restrict
     for (int k = 0; k < K; ++k) sums[k] = 0.0;
     const float L = fp.edgeLength;
 
-    for (int vBase = vBegin; vBase < vEnd; vBase += GROUPS_PER_BLOCK) {
-        const int v = vBase + threadIdx.x / G;
+    for (int vBase = vBegin; vBase < vEnd; vBase += 256) {
+        const int v = vBase + threadIdx.x;
         const bool valid = v < vEnd;
         float4 xv[V];
         double acc[4 * V];      // summed in double, see k_repulse_pairs
 #pragma unroll
         for (int k = 0; k < 4 * V; ++k) acc[k] = 0.0;
         double loss = 0.0;
-        float iwv = 1.f;
         int nCoincident = 0;
         if (valid) {
             load_row<V>(x, v, xv);
-            iwv = __ldg(iw + v);
-            const int end = __ldg(rowPtr + v + 1);
-            for (int e = __ldg(rowPtr + v) + lig; e < end; e += G) {
-                const int u = __ldg(col + e);
-                if (u == v) continue;                              // attractionForce: v == u -> 0 (:141)
-                float4 xu[V];
-                load_row<V>(x, u, xu);
-                const float d2 = point_dist2<V>(xu, xv);
-                const float dist = sqrtf(d2);
-                if (dist <= 0.f) { ++nCoincident; continue; }     // :150-155
-                const float ws = iwv * __ldg(iw + u);
-                if (dist * ws > L) {                               // :163-168
-                    axpy_diff_d<V>(acc, fp.attractionScale * ws / dist, xu, xv);
-                    loss += (double)(dist - L / ws);
+            const float iwv = __ldg(iw + v);
+            const int hub = hubSlot ? __ldg(hubSlot + v) : -1;
+            if (hub >= 0) {
+                const double* hf = hubForce + (int64_t)hub * (4 * V + 2);
+#pragma unroll
+                for (int k = 0; k < 4 * V; ++k) acc[k] = hf[k];
+                loss = hf[4 * V];
+                nCoincident = (int)hf[4 * V + 1];
+            } else {
+                int e = __ldg(rowPtr + v);
+                const int end = __ldg(rowPtr + v + 1);
+                for (; e + 1 < end; e += 2) {                      // neighbours in ascending order, two rows in flight
+                    const int u0 = __ldg(col + e), u1 = __ldg(col + e + 1);
+                    float4 a[V], b[V];
+                    load_row<V>(x, u0, a);
+                    load_row<V>(x, u1, b);
+                    const float iw0 = __ldg(iw + u0), iw1 = __ldg(iw + u1);
+                    if (u0 != v) attract_pair<V>(xv, iwv, a, iw0, L, fp.attractionScale, acc, loss, nCoincident);   // v == u -> 0 (:141)
+                    if (u1 != v) attract_pair<V>(xv, iwv, b, iw1, L, fp.attractionScale, acc, loss, nCoincident);
+                }
+                if (e < end) {
+                    const int u0 = __ldg(col + e);
+                    float4 a[V];
+                    load_row<V>(x, u0, a);
+                    if (u0 != v) attract_pair<V>(xv, iwv, a, __ldg(iw + u0), L, fp.attractionScale, acc, loss, nCoincident);
                 }
             }
+            nCoincident += __ldg(coincidentRep + v);
         } else {
 #pragma unroll
             for (int c = 0; c < V; ++c) xv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-#pragma unroll
-        for (int k = 0; k < 4 * V; ++k) acc[k] = group_sum<G>(acc[k]);
-        loss = group_sum<G>(loss);
-        nCoincident = group_sum<G>(nCoincident);
-        if (valid) nCoincident += __ldg(coincidentRep + v);
 
-        // coincident partners: every one of them adds the same unit vector (generator re-created per pair, :150-155, :183-188)
-        if (__any_sync(0xffffffffu, nCoincident > 0)) {
-            for (int gg = 0; gg < GROUPS_PER_WARP; ++gg) {
-                if (gInWarp == gg && lig == 0 && nCoincident > 0)
-                    random_unit_vector(mtState[warp], fp.seed, (uint32_t)v, fp.iteration, fp.dim, unitBuf[warp][gg]);
-                __syncwarp();
-            }
-            if (nCoincident > 0) {
-                const double* uvec = unitBuf[warp][gInWarp];
+        // coincident partners: every one of them adds the same unit vector (generator re-created per pair, :150-155, :183-188).
+        // The generator state (624 words) lives in per-warp shared memory; the rare lanes that need it take turns.
+        uint32_t need = __ballot_sync(0xffffffffu, nCoincident > 0);
+        while (need) {
+            const int l = __ffs(need) - 1;
+            need &= need - 1u;
+            if (lane == l) {
+                double uvec[4 * V];
+                random_unit_vector(mtState[warp], fp.seed, (uint32_t)v, fp.iteration, fp.dim, uvec);
 #pragma unroll
                 for (int k = 0; k < 4 * V; ++k)
                     if (k < fp.dim) acc[k] += nCoincident * uvec[k];
@@ -534,46 +613,45 @@ __global__ void __launch_bounds__(256) k_attract_update(const float4* __restrict
         }
 
         if (valid) {
-            if (lig == 0) { sums[0] += loss; sums[1] += (double)__ldg(lossRep + v); }
+            sums[0] += loss;
+            sums[1] += (double)__ldg(lossRep + v);
 #pragma unroll
             for (int c = 0; c < V; ++c) {
-                if ((c % G) == lig) {
-                    const int64_t at = (int64_t)v * V + c;
-                    const double* fr = forceRep + at * 4;
-                    float4 f = make_float4((float)(acc[4 * c] + fr[0]), (float)(acc[4 * c + 1] + fr[1]), (float)(acc[4 * c + 2] + fr[2]),
-                                           (float)(acc[4 * c + 3] + fr[3]));
-                    if (fp.centreScale != 0.f) {                   // :296-301
-                        f.x = fmaf(-fp.centreScale, xv[c].x, f.x); f.y = fmaf(-fp.centreScale, xv[c].y, f.y);
-                        f.z = fmaf(-fp.centreScale, xv[c].z, f.z); f.w = fmaf(-fp.centreScale, xv[c].w, f.w);
-                    }
-                    if (fp.keepForces) forceOut[at] = f;
-                    float4 xn;
-                    if (fp.optimizer == 1) {
-                        float4 m = mom1[at], s = mom2[at];
-                        const float fe[4] = {f.x, f.y, f.z, f.w};
-                        float me[4] = {m.x, m.y, m.z, m.w}, se[4] = {s.x, s.y, s.z, s.w};
-                        float xe[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w};
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            me[i] = fp.beta1 * me[i] + (1.f - fp.beta1) * fe[i];
-                            se[i] = fp.beta2 * se[i] + (1.f - fp.beta2) * fe[i] * fe[i];
-                            const float mHat = me[i] * fp.invBias1, vHat = se[i] * fp.invBias2;
-                            xe[i] += fp.lr * mHat / (sqrtf(vHat) + fp.eps);
-                        }
-                        mom1[at] = make_float4(me[0], me[1], me[2], me[3]);
-                        mom2[at] = make_float4(se[0], se[1], se[2], se[3]);
-                        xn = make_float4(xe[0], xe[1], xe[2], xe[3]);
-                    } else {
-                        const float cap = fp.maxDisplacement;
-                        xn.x = xv[c].x + fminf(fmaxf(f.x, -cap), cap) * fp.lr;
-                        xn.y = xv[c].y + fminf(fmaxf(f.y, -cap), cap) * fp.lr;
-                        xn.z = xv[c].z + fminf(fmaxf(f.z, -cap), cap) * fp.lr;
-                        xn.w = xv[c].w + fminf(fmaxf(f.w, -cap), cap) * fp.lr;
-                    }
-                    xNew[at] = xn;
-                    sums[2 + 4 * c + 0] += (double)xn.x; sums[2 + 4 * c + 1] += (double)xn.y;
-                    sums[2 + 4 * c + 2] += (double)xn.z; sums[2 + 4 * c + 3] += (double)xn.w;
+                const int64_t at = (int64_t)v * V + c;
+                const double* fr = forceRep + at * 4;
+                float4 f = make_float4((float)(acc[4 * c] + fr[0]), (float)(acc[4 * c + 1] + fr[1]), (float)(acc[4 * c + 2] + fr[2]),
+                                       (float)(acc[4 * c + 3] + fr[3]));
+                if (fp.centreScale != 0.f) {                   // :296-301
+                    f.x = fmaf(-fp.centreScale, xv[c].x, f.x); f.y = fmaf(-fp.centreScale, xv[c].y, f.y);
+                    f.z = fmaf(-fp.centreScale, xv[c].z, f.z); f.w = fmaf(-fp.centreScale, xv[c].w, f.w);
                 }
+                if (fp.keepForces) forceOut[at] = f;
+                float4 xn;
+                if (fp.optimizer == 1) {
+                    float4 m = mom1[at], s = mom2[at];
+                    const float fe[4] = {f.x, f.y, f.z, f.w};
+                    float me[4] = {m.x, m.y, m.z, m.w}, se[4] = {s.x, s.y, s.z, s.w};
+                    float xe[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        me[i] = fp.beta1 * me[i] + (1.f - fp.beta1) * fe[i];
+                        se[i] = fp.beta2 * se[i] + (1.f - fp.beta2) * fe[i] * fe[i];
+                        const float mHat = me[i] * fp.invBias1, vHat = se[i] * fp.invBias2;
+                        xe[i] += fp.lr * mHat / (sqrtf(vHat) + fp.eps);
+                    }
+                    mom1[at] = make_float4(me[0], me[1], me[2], me[3]);
+                    mom2[at] = make_float4(se[0], se[1], se[2], se[3]);
+                    xn = make_float4(xe[0], xe[1], xe[2], xe[3]);
+                } else {
+                    const float cap = fp.maxDisplacement;
+                    xn.x = xv[c].x + fminf(fmaxf(f.x, -cap), cap) * fp.lr;
+                    xn.y = xv[c].y + fminf(fmaxf(f.y, -cap), cap) * fp.lr;
+                    xn.z = xv[c].z + fminf(fmaxf(f.z, -cap), cap) * fp.lr;
+                    xn.w = xv[c].w + fminf(fmaxf(f.w, -cap), cap) * fp.lr;
+                }
+                xNew[at] = xn;
+                sums[2 + 4 * c + 0] += (double)xn.x; sums[2 + 4 * c + 1] += (double)xn.y;
+                sums[2 + 4 * c + 2] += (double)xn.z; sums[2 + 4 * c + 3] += (double)xn.w;
             }
         }
     }

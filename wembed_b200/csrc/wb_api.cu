@@ -63,13 +63,17 @@ struct wb_embedder {
     float *iw = nullptr, *lossRep = nullptr;
     int* coincident = nullptr;
     int* chunkCounter = nullptr;          // work counter of the persistent repulsion kernel
+    int numHubs = 0;                      // rows longer than kHubThreshold, pre-summed by k_attract_hubs
+    int *hubVertex = nullptr, *hubSlot = nullptr;
+    double* hubForce = nullptr;
     std::vector<double> weights;          // state.currentWeights
     std::vector<double> classMax;         // maxWeightOfClass[class(v)] (WeightedIndex.cpp:25-32), for the test hook
     int64_t iteration = 0;                // state.currentIteration
     int adamT = 0;                        // AdamOptimizer::t
 
     // spatial index
-    int mortonBits = 0;
+    int mortonBits = 0, bandBits = 0;     // key = band << (mortonBits * dim) | morton
+    uint8_t* band = nullptr;              // weight band of every vertex (radius doubles from band to band), null if one band
     uint32_t *keysIn = nullptr, *keysOut = nullptr;
     int *valsIn = nullptr, *valsOut = nullptr;
     void* cubTemp = nullptr;
@@ -113,6 +117,7 @@ struct wb_embedder {
 namespace {
 
 using wb::kFan;
+constexpr int kHubThreshold = 96;   // CSR rows longer than this are summed by one block each (k_attract_hubs)
 
 #define WB_DISPATCH_V(V_, ...)                                   \
     switch (V_) {                                                \
@@ -132,7 +137,7 @@ inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 void free_all(wb_embedder* h) {
     auto F = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
     F(h->rowPtr); F(h->col); F(h->x); F(h->xNew); F(h->mom1); F(h->mom2); F(h->forceRep); F(h->force);
-    F(h->iw); F(h->lossRep); F(h->coincident); F(h->chunkCounter); F(h->keysIn); F(h->keysOut); F(h->valsIn); F(h->valsOut);
+    F(h->iw); F(h->lossRep); F(h->coincident); F(h->chunkCounter); F(h->hubVertex); F(h->hubSlot); F(h->hubForce); F(h->band); F(h->keysIn); F(h->keysOut); F(h->valsIn); F(h->valsOut);
     F(h->cubTemp); F(h->momentPartials); F(h->quant); F(h->ids);
     for (int l = 0; l < wb::kMaxLevels; ++l) { F(h->lvlLo[l]); if (l > 0) F(h->lvlHi[l]); F(h->lvlBound[l]); }
     F(h->partialsForce); F(h->partialsRep); F(h->partialsObs); F(h->sumsAll); F(h->ownedList); F(h->ownedCount); F(h->selectTemp); F(h->gathered); F(h->localSums);
@@ -154,6 +159,20 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
     WB_CUDA(cudaMemcpyAsync(h->rowPtr, rowPtr, sizeof(int) * (n + 1), cudaMemcpyHostToDevice, h->stream));
     if (h->numDirected) WB_CUDA(cudaMemcpyAsync(h->col, col, sizeof(int) * h->numDirected, cudaMemcpyHostToDevice, h->stream));
 
+    {   // hub rows
+        std::vector<int> hubs, slot(n, -1);
+        for (int v = 0; v < n; ++v)
+            if (rowPtr[v + 1] - rowPtr[v] > kHubThreshold) { slot[v] = (int)hubs.size(); hubs.push_back(v); }
+        h->numHubs = (int)hubs.size();
+        if (h->numHubs) {
+            h->hubVertex = dalloc<int>(hubs.size());
+            h->hubSlot = dalloc<int>(n);
+            h->hubForce = dalloc<double>(hubs.size() * (4 * V + 2));
+            WB_CUDA(cudaMemcpyAsync(h->hubVertex, hubs.data(), sizeof(int) * hubs.size(), cudaMemcpyHostToDevice, h->stream));
+            WB_CUDA(cudaMemcpyAsync(h->hubSlot, slot.data(), sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
+            WB_CUDA(cudaStreamSynchronize(h->stream));
+        }
+    }
     const size_t rows = (size_t)n * V;
     h->forceRep = dalloc<double>(std::max<size_t>(rows, 1) * 4);
     WB_CUDA(cudaMemsetAsync(h->forceRep, 0, std::max<size_t>(rows, 1) * 4 * sizeof(double), h->stream));
@@ -176,7 +195,7 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
     h->valsIn = dalloc<int>(n); h->valsOut = dalloc<int>(n);
     h->cubBytes = 0;
     WB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, h->cubBytes, h->keysIn, h->keysOut, h->valsIn, h->valsOut, std::max(n, 1), 0,
-                                            h->mortonBits * h->dim, h->stream));
+                                            32, h->stream));
     h->cubTemp = dalloc<char>(h->cubBytes);
     h->momentBlocks = std::max(1, std::min(div_up(n, 256), 592));
     h->momentPartials = dalloc<float>((size_t)h->momentBlocks * 4 * wb::kMaxDim);
@@ -214,7 +233,7 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
     t.ids = h->ids;
 
     // reductions: fixed block -> vertex-range assignment so the sums do not depend on scheduling
-    const int groupsPerBlock = 256 / 8;
+    const int groupsPerBlock = 256;      // one thread per vertex
     h->forceBlocks = std::max(1, std::min(div_up(n, groupsPerBlock), 148 * 16));
     h->forceVertsPerBlock = std::max(groupsPerBlock, div_up(div_up(n, h->forceBlocks), groupsPerBlock) * groupsPerBlock);
     h->forceBlocks = std::max(1, div_up(n, h->forceVertsPerBlock));
@@ -229,9 +248,9 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
     h->obsBlocks = std::max(1, div_up(n, h->obsVertsPerBlock));
     h->ownBegin = 0; h->ownEnd = n; h->rowsPerRank = n;
     const int K = 2 + 4 * V;
-    h->sumsTotal = K + 4;
+    h->sumsTotal = K + 5;      // [ force sums (K) | repulsion counters: pairs, point tests, box tests | observe sums (2) ]
     h->partialsForce = dalloc<double>((size_t)h->forceBlocks * K);
-    h->partialsRep = dalloc<double>((size_t)h->repBlocks * 8 * 2);
+    h->partialsRep = dalloc<double>((size_t)h->repBlocks * 8 * 3);
     h->partialsObs = dalloc<double>((size_t)h->obsBlocks * 2);
     h->sumsAll = dalloc<double>(h->sumsTotal);
     WB_CUDA(cudaMemsetAsync(h->sumsAll, 0, sizeof(double) * h->sumsTotal, h->stream));
@@ -247,9 +266,9 @@ void enqueue_index(wb_embedder* h, const float* pointBound) {
     cudaStream_t s = h->stream;
     WB_DISPATCH_V(V, wb::k_moments<V><<<h->momentBlocks, 256, 0, s>>>(h->x, n, h->momentPartials));
     wb::k_quant_params<<<1, 32, 0, s>>>(h->momentPartials, h->momentBlocks, n, h->dim, h->mortonBits, h->quant);
-    WB_DISPATCH_V(V, wb::k_morton_keys<V><<<div_up(n, 256), 256, 0, s>>>(h->x, n, h->dim, h->mortonBits, h->quant, h->keysIn, h->valsIn));
+    WB_DISPATCH_V(V, wb::k_morton_keys<V><<<div_up(n, 256), 256, 0, s>>>(h->x, n, h->dim, h->mortonBits, h->quant, h->band, h->keysIn, h->valsIn));
     WB_CUDA(cub::DeviceRadixSort::SortPairs(h->cubTemp, h->cubBytes, h->keysIn, h->keysOut, h->valsIn, h->valsOut, n, 0,
-                                            h->mortonBits * h->dim, s));
+                                            h->mortonBits * h->dim + h->bandBits, s));
     const wb::TreeView& t = h->tree;
     WB_DISPATCH_V(V, wb::k_build_leaves<V><<<div_up(t.stride[0], 256), 256, 0, s>>>(
                          h->x, pointBound, h->valsOut, n, h->lvlLo[0], t.stride[0], h->lvlBound[0], h->ids, h->lvlLo[1], h->lvlHi[1],
@@ -322,26 +341,30 @@ void enqueue_step(wb_embedder* h, double learningRate) {
     }
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[1], s));
     WB_CUDA(cudaMemsetAsync(h->chunkCounter, 0, sizeof(int), s));
-    WB_DISPATCH_V(V, wb::k_repulse_pairs<V><<<h->repBlocks, 256, 0, s>>>(h->tree, h->rowPtr, h->col, n, fp, h->forceRep, h->lossRep,
+    WB_DISPATCH_V(V, wb::k_repulse_pairs<V><<<h->repBlocks, 32 * wb::repulse_warps(V), 0, s>>>(h->tree, h->rowPtr, h->col, n, fp, h->forceRep, h->lossRep,
                                                                           h->coincident, h->chunkCounter, queryList, sharded ? ownCount : n,
                                                                           h->partialsRep));
-    wb::k_reduce_partials<<<2, 256, 0, s>>>(h->partialsRep, h->repBlocks * 8, 2, sums + K);
+    wb::k_reduce_partials<<<3, 256, 0, s>>>(h->partialsRep, h->repBlocks * wb::repulse_warps(V), 3, sums + K);
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[2], s));
-    WB_DISPATCH_V(V, wb::k_attract_update<V, 8><<<h->forceBlocks, 256, 0, s>>>(
+    if (h->numHubs) {
+        WB_DISPATCH_V(V, wb::k_attract_hubs<V><<<h->numHubs, 256, 0, s>>>(h->x, h->iw, h->rowPtr, h->col, h->hubVertex, fp, h->hubForce));
+        h->launches += 1;
+    }
+    WB_DISPATCH_V(V, wb::k_attract_update<V><<<h->forceBlocks, 256, 0, s>>>(
                          h->x, h->iw, h->rowPtr, h->col, h->ownBegin, h->ownEnd, h->forceVertsPerBlock, fp, h->forceRep, h->lossRep,
-                         h->coincident, h->xNew, h->mom1, h->mom2, h->force, h->partialsForce));
+                         h->coincident, h->hubSlot, h->hubForce, h->xNew, h->mom1, h->mom2, h->force, h->partialsForce));
     wb::k_reduce_partials<<<K, 256, 0, s>>>(h->partialsForce, h->forceBlocks, K, sums);
     if (sharded) {   // {lossA, lossR, sum xnew[k], pairs, tests}: all-gather, then every rank adds in rank order
-        if (ncclAllGather(sums, h->gathered, K + 2, ncclDouble, h->comm, s) != ncclSuccess) throw std::runtime_error("ncclAllGather (force sums) failed");
-        wb::k_sum_ranks<<<1, 256, 0, s>>>(h->gathered, h->world, K + 2, h->sumsAll);
+        if (ncclAllGather(sums, h->gathered, K + 3, ncclDouble, h->comm, s) != ncclSuccess) throw std::runtime_error("ncclAllGather (force sums) failed");
+        wb::k_sum_ranks<<<1, 256, 0, s>>>(h->gathered, h->world, K + 3, h->sumsAll);
     }
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[3], s));
     WB_DISPATCH_V(V, wb::k_recentre_observe<V><<<h->obsBlocks, 256, 0, s>>>(h->x, h->xNew, n, h->ownBegin, h->ownEnd, h->obsVertsPerBlock, h->dim,
                                                                               h->sumsAll, h->partialsObs));
-    wb::k_reduce_partials<<<2, 256, 0, s>>>(h->partialsObs, h->obsBlocks, 2, sums + K + 2);
+    wb::k_reduce_partials<<<2, 256, 0, s>>>(h->partialsObs, h->obsBlocks, 2, sums + K + 3);
     if (sharded) {
-        if (ncclAllGather(sums + K + 2, h->gathered, 2, ncclDouble, h->comm, s) != ncclSuccess) throw std::runtime_error("ncclAllGather (observe sums) failed");
-        wb::k_sum_ranks<<<1, 256, 0, s>>>(h->gathered, h->world, 2, h->sumsAll + K + 2);
+        if (ncclAllGather(sums + K + 3, h->gathered, 2, ncclDouble, h->comm, s) != ncclSuccess) throw std::runtime_error("ncclAllGather (observe sums) failed");
+        wb::k_sum_ranks<<<1, 256, 0, s>>>(h->gathered, h->world, 2, h->sumsAll + K + 3);
         // publish the owners' updated rows: x is replicated again for the next step's index build and gathers
         const size_t rowFloats = (size_t)h->rowsPerRank * h->rowFloats;
         float* xf = reinterpret_cast<float*>(h->x);
@@ -372,8 +395,9 @@ void collect_step(wb_embedder* h, wb_step_stats* out) {
         for (int k = 0; k < h->dim; ++k) st.centroid[k] = s[2 + k] / (double)h->n;
         st.num_repulsion_pairs = s[K];
         st.num_candidates = s[K + 1];
-        st.sum_displacement = s[K + 2];
-        st.sum_radius_sq = s[K + 3];
+        st.num_box_tests = s[K + 2];
+        st.sum_displacement = s[K + 3];
+        st.sum_radius_sq = s[K + 4];
         const double invN = 1.0 / (double)h->n;                              // observeDisplacement (:341-350)
         const double radius = std::sqrt(st.sum_radius_sq * invN);
         st.rel_displacement = radius > 0.0 ? (st.sum_displacement * invN) / radius : 0.0;
@@ -524,9 +548,30 @@ int wb_set_weights(wb_embedder* h, const double* weights) {
         for (int v = 0; v < n; ++v) iw[v] = (float)(1.0 / std::pow(weights[v], 1.0 / (double)h->dim));
         WB_CUDA(cudaMemcpyAsync(h->iw, iw.data(), sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
         WB_CUDA(cudaStreamSynchronize(h->stream));
-        // weight classes (WeightedIndex::getDoublingWeightBuckets + updateIndices, WeightedIndex.cpp:51-63, 18-32)
         const double minW = *std::min_element(h->weights.begin(), h->weights.end());
         const double maxW = *std::max_element(h->weights.begin(), h->weights.end());
+        {   // weight bands of the device index: band = floor(log2((w / minW)^(1/d))), i.e. the interaction radius doubles
+            // from band to band (the reference's doubling classes double the WEIGHT; in d dimensions that is a factor
+            // 2^(1/d) in radius, too fine a split to pay for the loss of spatial coherence - measured)
+            const double invD = 1.0 / (double)h->dim;
+            const int bands = 1 + (int)std::floor(std::log2(std::pow(maxW / minW, invD)));
+            int bits = 0;
+            while ((1 << bits) < bands) ++bits;
+            bits = std::min(bits, 4);
+            if (!std::getenv("WB_INDEX_BANDS")) bits = 0;   // measured on c4: separate subtrees per band cost more coherence than the tighter bounds save
+            if (h->band) { cudaFree(h->band); h->band = nullptr; }
+            h->bandBits = bits;
+            h->mortonBits = std::max(1, std::min(16, (32 - bits) / h->dim));
+            if (bits > 0) {
+                std::vector<uint8_t> b(n);
+                for (int v = 0; v < n; ++v)
+                    b[v] = (uint8_t)std::min((1 << bits) - 1, (int)std::floor(std::log2(std::pow(weights[v] / minW, invD))));
+                h->band = dalloc<uint8_t>(n);
+                WB_CUDA(cudaMemcpyAsync(h->band, b.data(), n, cudaMemcpyHostToDevice, h->stream));
+                WB_CUDA(cudaStreamSynchronize(h->stream));
+            }
+        }
+        // weight classes (WeightedIndex::getDoublingWeightBuckets + updateIndices, WeightedIndex.cpp:51-63, 18-32)
         std::vector<double> buckets;
         if (h->opt.doubling_factor > 1.0)
             for (double c = minW * h->opt.doubling_factor; c < maxW; c *= h->opt.doubling_factor) buckets.push_back(c);
@@ -637,7 +682,7 @@ int wb_comm_init(wb_embedder* h, const char* id128, int32_t rank, int32_t world)
             *p = q;
         }
         // block -> vertex-range assignment over the owned range
-        const int own = std::max(1, h->ownEnd - h->ownBegin), groupsPerBlock = 256 / 8, K = 2 + 4 * V;
+        const int own = std::max(1, h->ownEnd - h->ownBegin), groupsPerBlock = 256, K = 2 + 4 * V;
         h->forceBlocks = std::max(1, std::min(div_up(own, groupsPerBlock), 148 * 16));
         h->forceVertsPerBlock = std::max(groupsPerBlock, div_up(div_up(own, h->forceBlocks), groupsPerBlock) * groupsPerBlock);
         h->forceBlocks = std::max(1, div_up(own, h->forceVertsPerBlock));

@@ -104,8 +104,13 @@ def _pairs_between(P: np.ndarray, Q: np.ndarray, radius: float, same: bool) -> n
     return np.concatenate(out) if out else np.zeros((0, 2), np.int64)
 
 
-def heavy_tailed_graph(n: int, avg_degree: float = 20.0, beta: float = 2.5, seed: int = 42):
-    """Threshold GIRG-like graph with power-law weights; returns (edges, generator weights)."""
+def heavy_tailed_graph(n: int, avg_degree: float = 20.0, beta: float = 2.5, seed: int = 42, c: float | None = None):
+    """Threshold GIRG-like graph with power-law weights; returns (edges, generator weights).
+
+    The expected degree, pi * c^2 * E[w] up to boundary effects, does not depend on n, so for large n the constant c
+    is calibrated once on a 100k-vertex instance of the same distribution."""
+    if c is None and n > 200_000:
+        c = _calibrate_c(avg_degree, beta, seed)
     rng = np.random.default_rng(seed)
     w = (1.0 - rng.random(n)) ** (-1.0 / (beta - 1.0))
     pts = rng.random((n, 2))
@@ -135,6 +140,8 @@ def heavy_tailed_graph(n: int, avg_degree: float = 20.0, beta: float = 2.5, seed
         e = e[np.lexsort((e[:, 1], e[:, 0]))]
         return e.astype(np.int32)
 
+    if c is not None:
+        return build(c, False), w
     lo, hi = 0.0, 4.0 * np.sqrt(avg_degree)
     target = avg_degree * n / 2.0
     for _ in range(14):
@@ -143,7 +150,13 @@ def heavy_tailed_graph(n: int, avg_degree: float = 20.0, beta: float = 2.5, seed
             lo = mid
         else:
             hi = mid
+    heavy_tailed_graph.last_c = 0.5 * (lo + hi)
     return build(0.5 * (lo + hi), False), w
+
+
+def _calibrate_c(avg_degree, beta, seed):
+    heavy_tailed_graph(100_000, avg_degree, beta, seed)
+    return heavy_tailed_graph.last_c
 
 
 def degree_weights(n: int, edges: np.ndarray, d: int, dimension_hint: float = -1.0) -> np.ndarray:
