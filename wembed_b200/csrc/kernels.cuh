@@ -111,14 +111,14 @@ __global__ void k_quant_params(const float* __restrict__ partial, int numBlocks,
 }
 
 // Index, stage 3: Morton key of every vertex (bit b of dimension k -> key bit b*dim + k), weight band on top.
-template <int V>
+template <int V, typename KeyT>
 __global__ void __launch_bounds__(256) k_morton_keys(const float4* __restrict__ x, int n, int dim, int bits,
                                                      const QuantParams* __restrict__ qp, const uint8_t* __restrict__ band,
-                                                     uint32_t* __restrict__ keys, int* __restrict__ vals) {
+                                                     KeyT* __restrict__ keys, int* __restrict__ vals) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n) return;
     const uint32_t qmax = (1u << bits) - 1u;
-    uint32_t key = 0;
+    KeyT key = 0;
 #pragma unroll
     for (int c = 0; c < V; ++c) {
         const float4 p = __ldg(x + (int64_t)v * V + c);
@@ -129,13 +129,13 @@ __global__ void __launch_bounds__(256) k_morton_keys(const float4* __restrict__ 
             if (k < dim) {
                 const float t = (e[i] - qp->lo[k]) * qp->invCell[k];
                 const uint32_t q = t <= 0.f ? 0u : (t >= (float)qmax ? qmax : (uint32_t)t);
-                for (int b = 0; b < bits; ++b) key |= ((q >> b) & 1u) << (b * dim + k);
+                for (int b = 0; b < bits; ++b) key |= (KeyT)((q >> b) & 1u) << (b * dim + k);
             }
         }
     }
     // weight band in the top bits (bits * dim .. ): points whose interaction radius differs by more than a factor of two
     // live in separate subtrees, so one heavy vertex cannot inflate the pruning bound of a subtree of light ones
-    if (band) key |= (uint32_t)band[v] << (bits * dim);
+    if (band) key |= (KeyT)band[v] << (bits * dim);
     keys[v] = key;
     vals[v] = v;
 }

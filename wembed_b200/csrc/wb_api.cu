@@ -6,6 +6,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
+#include <dlfcn.h>
 #include <nccl.h>
 
 #include <algorithm>
@@ -26,6 +27,32 @@
 namespace {
 
 thread_local std::string g_lastError;
+
+// NCCL is bound lazily (dlopen) and only by the multi-GPU entry points: the single-GPU path has no NCCL dependency, and
+// a host process that already carries an NCCL (e.g. the one bundled with PyTorch, same SONAME) keeps using that copy.
+struct NcclApi {
+    ncclResult_t (*getUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*commInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*allGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*commDestroy)(ncclComm_t) = nullptr;
+    bool ok = false;
+};
+
+NcclApi& nccl() {
+    static NcclApi api = [] {
+        NcclApi a;
+        void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return a;
+        a.getUniqueId = reinterpret_cast<decltype(a.getUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+        a.commInitRank = reinterpret_cast<decltype(a.commInitRank)>(dlsym(lib, "ncclCommInitRank"));
+        a.allGather = reinterpret_cast<decltype(a.allGather)>(dlsym(lib, "ncclAllGather"));
+        a.commDestroy = reinterpret_cast<decltype(a.commDestroy)>(dlsym(lib, "ncclCommDestroy"));
+        a.ok = a.getUniqueId && a.commInitRank && a.allGather && a.commDestroy;
+        return a;
+    }();
+    return api;
+}
 
 int fail(int code, const std::string& msg) {
     g_lastError = msg;
@@ -74,7 +101,8 @@ struct wb_embedder {
     // spatial index
     int mortonBits = 0, bandBits = 0;     // key = band << (mortonBits * dim) | morton
     uint8_t* band = nullptr;              // weight band of every vertex (radius doubles from band to band), null if one band
-    uint32_t *keysIn = nullptr, *keysOut = nullptr;
+    int keyBits = 32;                     // width of the Morton sort key (a 64-bit path exists; it did not pay at d = 16)
+    void *keysIn = nullptr, *keysOut = nullptr;
     int *valsIn = nullptr, *valsOut = nullptr;
     void* cubTemp = nullptr;
     size_t cubBytes = 0;
@@ -141,7 +169,7 @@ void free_all(wb_embedder* h) {
     F(h->cubTemp); F(h->momentPartials); F(h->quant); F(h->ids);
     for (int l = 0; l < wb::kMaxLevels; ++l) { F(h->lvlLo[l]); if (l > 0) F(h->lvlHi[l]); F(h->lvlBound[l]); }
     F(h->partialsForce); F(h->partialsRep); F(h->partialsObs); F(h->sumsAll); F(h->ownedList); F(h->ownedCount); F(h->selectTemp); F(h->gathered); F(h->localSums);
-    if (h->comm) { ncclCommDestroy(h->comm); h->comm = nullptr; }
+    if (h->comm) { nccl().commDestroy(h->comm); h->comm = nullptr; }
     for (auto& p : h->pending) { cudaEventDestroy(p.done); cudaFreeHost(p.hostSums); }
     for (auto& p : h->freeSlots) { cudaEventDestroy(p.done); cudaFreeHost(p.hostSums); }
     h->pending.clear(); h->freeSlots.clear();
@@ -190,12 +218,13 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
     h->classMax.assign(n, 1.0);
 
     // Morton keys: as many bits per dimension as fit a 32-bit key
-    h->mortonBits = std::max(1, std::min(16, 32 / h->dim));
-    h->keysIn = dalloc<uint32_t>(n); h->keysOut = dalloc<uint32_t>(n);
+    h->keyBits = 32;   // measured at d = 16 (2 vs 4 bits per dimension): same test counts, so the cheaper 32-bit sort is kept everywhere
+    h->mortonBits = std::max(1, std::min(16, h->keyBits / h->dim));
+    h->keysIn = dalloc<uint64_t>(n); h->keysOut = dalloc<uint64_t>(n);
     h->valsIn = dalloc<int>(n); h->valsOut = dalloc<int>(n);
     h->cubBytes = 0;
-    WB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, h->cubBytes, h->keysIn, h->keysOut, h->valsIn, h->valsOut, std::max(n, 1), 0,
-                                            32, h->stream));
+    WB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, h->cubBytes, (uint64_t*)h->keysIn, (uint64_t*)h->keysOut, h->valsIn, h->valsOut,
+                                            std::max(n, 1), 0, 64, h->stream));
     h->cubTemp = dalloc<char>(h->cubBytes);
     h->momentBlocks = std::max(1, std::min(div_up(n, 256), 592));
     h->momentPartials = dalloc<float>((size_t)h->momentBlocks * 4 * wb::kMaxDim);
@@ -266,9 +295,18 @@ void enqueue_index(wb_embedder* h, const float* pointBound) {
     cudaStream_t s = h->stream;
     WB_DISPATCH_V(V, wb::k_moments<V><<<h->momentBlocks, 256, 0, s>>>(h->x, n, h->momentPartials));
     wb::k_quant_params<<<1, 32, 0, s>>>(h->momentPartials, h->momentBlocks, n, h->dim, h->mortonBits, h->quant);
-    WB_DISPATCH_V(V, wb::k_morton_keys<V><<<div_up(n, 256), 256, 0, s>>>(h->x, n, h->dim, h->mortonBits, h->quant, h->band, h->keysIn, h->valsIn));
-    WB_CUDA(cub::DeviceRadixSort::SortPairs(h->cubTemp, h->cubBytes, h->keysIn, h->keysOut, h->valsIn, h->valsOut, n, 0,
-                                            h->mortonBits * h->dim + h->bandBits, s));
+    const int sortBits = h->mortonBits * h->dim + h->bandBits;
+    if (h->keyBits == 64) {
+        WB_DISPATCH_V(V, wb::k_morton_keys<V, uint64_t><<<div_up(n, 256), 256, 0, s>>>(h->x, n, h->dim, h->mortonBits, h->quant, h->band,
+                                                                                         (uint64_t*)h->keysIn, h->valsIn));
+        WB_CUDA(cub::DeviceRadixSort::SortPairs(h->cubTemp, h->cubBytes, (uint64_t*)h->keysIn, (uint64_t*)h->keysOut, h->valsIn, h->valsOut, n, 0,
+                                                sortBits, s));
+    } else {
+        WB_DISPATCH_V(V, wb::k_morton_keys<V, uint32_t><<<div_up(n, 256), 256, 0, s>>>(h->x, n, h->dim, h->mortonBits, h->quant, h->band,
+                                                                                         (uint32_t*)h->keysIn, h->valsIn));
+        WB_CUDA(cub::DeviceRadixSort::SortPairs(h->cubTemp, h->cubBytes, (uint32_t*)h->keysIn, (uint32_t*)h->keysOut, h->valsIn, h->valsOut, n, 0,
+                                                sortBits, s));
+    }
     const wb::TreeView& t = h->tree;
     WB_DISPATCH_V(V, wb::k_build_leaves<V><<<div_up(t.stride[0], 256), 256, 0, s>>>(
                          h->x, pointBound, h->valsOut, n, h->lvlLo[0], t.stride[0], h->lvlBound[0], h->ids, h->lvlLo[1], h->lvlHi[1],
@@ -355,7 +393,7 @@ void enqueue_step(wb_embedder* h, double learningRate) {
                          h->coincident, h->hubSlot, h->hubForce, h->xNew, h->mom1, h->mom2, h->force, h->partialsForce));
     wb::k_reduce_partials<<<K, 256, 0, s>>>(h->partialsForce, h->forceBlocks, K, sums);
     if (sharded) {   // {lossA, lossR, sum xnew[k], pairs, tests}: all-gather, then every rank adds in rank order
-        if (ncclAllGather(sums, h->gathered, K + 3, ncclDouble, h->comm, s) != ncclSuccess) throw std::runtime_error("ncclAllGather (force sums) failed");
+        if (nccl().allGather(sums, h->gathered, K + 3, ncclDouble, h->comm, s) != ncclSuccess) throw std::runtime_error("ncclAllGather (force sums) failed");
         wb::k_sum_ranks<<<1, 256, 0, s>>>(h->gathered, h->world, K + 3, h->sumsAll);
     }
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[3], s));
@@ -363,12 +401,12 @@ void enqueue_step(wb_embedder* h, double learningRate) {
                                                                               h->sumsAll, h->partialsObs));
     wb::k_reduce_partials<<<2, 256, 0, s>>>(h->partialsObs, h->obsBlocks, 2, sums + K + 3);
     if (sharded) {
-        if (ncclAllGather(sums + K + 3, h->gathered, 2, ncclDouble, h->comm, s) != ncclSuccess) throw std::runtime_error("ncclAllGather (observe sums) failed");
+        if (nccl().allGather(sums + K + 3, h->gathered, 2, ncclDouble, h->comm, s) != ncclSuccess) throw std::runtime_error("ncclAllGather (observe sums) failed");
         wb::k_sum_ranks<<<1, 256, 0, s>>>(h->gathered, h->world, 2, h->sumsAll + K + 3);
         // publish the owners' updated rows: x is replicated again for the next step's index build and gathers
         const size_t rowFloats = (size_t)h->rowsPerRank * h->rowFloats;
         float* xf = reinterpret_cast<float*>(h->x);
-        if (ncclAllGather(xf + (size_t)h->rank * rowFloats, xf, rowFloats, ncclFloat, h->comm, s) != ncclSuccess)
+        if (nccl().allGather(xf + (size_t)h->rank * rowFloats, xf, rowFloats, ncclFloat, h->comm, s) != ncclSuccess)
             throw std::runtime_error("ncclAllGather (coordinates) failed");
         h->launches += 2;
     }
@@ -561,7 +599,7 @@ int wb_set_weights(wb_embedder* h, const double* weights) {
             if (!std::getenv("WB_INDEX_BANDS")) bits = 0;   // measured on c4: separate subtrees per band cost more coherence than the tighter bounds save
             if (h->band) { cudaFree(h->band); h->band = nullptr; }
             h->bandBits = bits;
-            h->mortonBits = std::max(1, std::min(16, (32 - bits) / h->dim));
+            h->mortonBits = std::max(1, std::min(16, (h->keyBits - bits) / h->dim));
             if (bits > 0) {
                 std::vector<uint8_t> b(n);
                 for (int v = 0; v < n; ++v)
@@ -649,8 +687,9 @@ int wb_get_phase_times(wb_embedder* h, double* ms6) {
 int wb_comm_unique_id(char* id128) {
     if (!id128) return fail(WB_ERR_INVALID, "wb_comm_unique_id: null buffer");
     static_assert(sizeof(ncclUniqueId) <= 128, "ncclUniqueId does not fit the ABI buffer");
+    if (!nccl().ok) return fail(WB_ERR_UNSUPPORTED, "libnccl.so.2 could not be loaded");
     ncclUniqueId id;
-    if (ncclGetUniqueId(&id) != ncclSuccess) return fail(WB_ERR_CUDA, "ncclGetUniqueId failed");
+    if (nccl().getUniqueId(&id) != ncclSuccess) return fail(WB_ERR_CUDA, "ncclGetUniqueId failed");
     std::memset(id128, 0, 128);
     std::memcpy(id128, &id, sizeof(id));
     return WB_OK;
@@ -664,7 +703,8 @@ int wb_comm_init(wb_embedder* h, const char* id128, int32_t rank, int32_t world)
         if (world == 1) return;
         ncclUniqueId id;
         std::memcpy(&id, id128, sizeof(id));
-        if (ncclCommInitRank(&h->comm, world, id, rank) != ncclSuccess) throw std::runtime_error("ncclCommInitRank failed");
+        if (!nccl().ok) throw std::runtime_error("libnccl.so.2 could not be loaded");
+        if (nccl().commInitRank(&h->comm, world, id, rank) != ncclSuccess) throw std::runtime_error("ncclCommInitRank failed");
         const int n = h->n, V = h->V;
         h->world = world;
         h->rank = rank;
