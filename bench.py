@@ -167,14 +167,18 @@ def run_ours(args):
     t0 = time.perf_counter()
     dev.mark(2)
     dev.set_coordinates(x_start)
+    t_set = time.perf_counter() - t0
     for _ in range(args.steps):
         it += 1
         dev.step(lr_schedule(it))
+    t_steps = time.perf_counter() - t0 - t_set
     x_end = dev.coordinates()
     dev.mark(3)
+    de_wall = time.perf_counter() - t0
     de_events = dev.elapsed_ms(2, 3) * 1e-3
     barrier()
-    de = max_over_ranks(max(time.perf_counter() - t0, de_events))   # host-visible time of the blocking calls (>= the device time)
+    de = max_over_ranks(max(de_wall, de_events))   # host-visible time of the blocking calls (>= the device time)
+    e2e_parts = {"set_coordinates_s": t_set, "steps_s": t_steps, "get_coordinates_s": de_wall - t_set - t_steps, "events_s": de_events}
     assert np.isfinite(x_end).all()
     dev.close()
 
@@ -242,7 +246,8 @@ def run_ours(args):
                    "l2": "working set (x, m, v, CSR, index: ~260 MB at c3) exceeds the 126 MB L2; no flush needed"},
         "e2e": {"value": units / de, "unit": "directed-edge force updates/s", "steps_per_s": args.steps / de,
                 "h2d_bytes_per_step": n * d * 8 / args.steps + 8, "d2h_bytes_per_step": n * d * 8 / args.steps + 8 * (8 + 4 * ((d + 3) // 4)),
-                "what": "wb_set_coordinates(host doubles) + K blocking wb_step (observables copied to the host every step) + wb_get_coordinates(host doubles)"},
+                "what": "wb_set_coordinates(host doubles) + K blocking wb_step (observables copied to the host every step) + wb_get_coordinates(host doubles)",
+                "parts": e2e_parts},
         "gpu_launches": None,
         "phases_ms": ph,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -102,3 +102,28 @@ def run_to_convergence(dev, o):
         settled = settled + 1 if st["rel_displacement"] < o.get("stopDisplacementTol", 3e-4) else 0
         mon.observe(st["loss_attract"] + st["loss_repel"])
     return it, st
+
+
+def reconstruction_metrics(x, w, row_ptr, col, nodes=None):
+    """constructDeg (precision at k = deg) and MAP of the reference's evaluationLib on the WeightedGeometric similarity
+    dist / (w_a w_b)^(1/d)  (src/evaluationLib/src/metrics/NodeSampler.cpp:5-111, Reconstruction.cpp:6-23,
+    src/embeddingLib/src/embeddingSpace/WeightedGeometric.cpp:17-21).  Ties are broken by node id like the reference's
+    sort of (similarity, id) pairs.  `nodes` = the sampled vertices (all by default); isolated vertices are skipped."""
+    n, d = x.shape
+    iw = w ** (-1.0 / d)
+    nodes = np.arange(n) if nodes is None else np.asarray(nodes)
+    deg_prec, avg_prec = [], []
+    for v in nodes:
+        nb = col[row_ptr[v]:row_ptr[v + 1]]
+        if len(nb) == 0:
+            continue
+        sim = np.sqrt(((x - x[v]) ** 2).sum(1)) * iw * iw[v]
+        order = np.lexsort((np.arange(n), sim))
+        order = order[order != v]
+        is_nb = np.zeros(n, bool)
+        is_nb[nb] = True
+        hits = is_nb[order]
+        prec = np.cumsum(hits) / np.arange(1, n)
+        deg_prec.append(prec[len(nb) - 1])
+        avg_prec.append(prec[hits].mean())
+    return float(np.mean(deg_prec)), float(np.mean(avg_prec))

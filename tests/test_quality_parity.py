@@ -1,0 +1,48 @@
+"""north_star: "Converged-embedding quality (evaluationLib reconstruction metrics) must match to within 1%"."""
+import numpy as np
+import pytest
+
+import oracle
+from helpers import lr_exponential, make_problem, reconstruction_metrics, run_to_convergence
+
+
+def test_reconstruction_metric_kat():
+    """tests/TestMetrics.cpp:29-62: 3-vertex path, good and bad Euclidean coordinates (unit weights)."""
+    rp, col = np.array([0, 1, 3, 4]), np.array([1, 0, 2, 1])
+    w = np.ones(3)
+    good = np.array([[0.0, 0.0], [1.0, 0.0], [2.0, 0.0]])
+    assert reconstruction_metrics(good, w, rp, col) == (1.0, 1.0)
+    bad = np.array([[0.0, 0.0], [3.0, 0.0], [1.0, 0.0]])
+    cd, mp = reconstruction_metrics(bad, w, rp, col)
+    assert cd == pytest.approx(1.0 / 3.0) and mp == pytest.approx((0.5 + 0.5 + 1.0) / 3.0)
+
+
+@pytest.mark.gpu
+def test_quality_matches_oracle_within_one_percent(device_lib, port_lib):
+    """Fixed iteration budget (the loss stop fires late on perfectly embeddable graphs) and each side's own
+    stop: constructDeg and MAP of the device embedding vs the CPU oracle's, same graph, same initial layout."""
+    n, d = 3000, 4
+    edges, w, x0 = make_problem(n, d)
+    rp, col = device_lib.csr_from_edges(n, edges)
+    nodes = np.random.default_rng(0).choice(n, 500, replace=False)      # cli_evaluator samples <= 1000 nodes
+    budget = 400
+    cpu = oracle.CpuEmbedder("port", edges, n=n, embeddingDimension=d, init_state=False)
+    dev = device_lib.DeviceEmbedder(rp, col, embedding_dimension=d, seed=1234)
+    for e in (cpu, dev):
+        e.set_weights(w)
+        e.set_coordinates(x0)
+    for it in range(1, budget + 1):
+        cpu.step()
+        st = dev.step(lr_exponential(it))
+    q_cpu = reconstruction_metrics(cpu.coordinates(), w, rp, col, nodes)
+    q_dev = reconstruction_metrics(dev.coordinates(), w, rp, col, nodes)
+    assert q_cpu[0] > 0.5 and q_cpu[1] > 0.5
+    for a, b in zip(q_dev, q_cpu):
+        assert abs(a - b) <= 0.01 * b, (q_dev, q_cpu)
+    # losses follow the same curve (chaotic in detail, equal in aggregate)
+    total_cpu = cpu.stats()["loss_attract"] + cpu.stats()["loss_repel"]
+    assert st["loss_attract"] + st["loss_repel"] == pytest.approx(total_cpu, rel=0.15)
+    # to each side's own stop (default loss criterion)
+    it_dev, _ = run_to_convergence(dev, {"maxIterations": 4000})
+    q_final = reconstruction_metrics(dev.coordinates(), w, rp, col, nodes)
+    assert q_final[0] >= q_dev[0] - 0.01 and q_final[1] >= q_dev[1] - 0.01
