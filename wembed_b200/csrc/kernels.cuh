@@ -477,16 +477,46 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
 }
 
 // ---------------------------------------------------------------------------------------------
-// One attractive pair (attractionForce, WembedEmbedder.cpp:140-172): adds the force of u on v to acc, returns the loss.
-template <int V>
-__device__ __forceinline__ void attract_pair(const float4 (&xv)[V], float iwv, const float4 (&xu)[V], float iwu, float L, float scale,
-                                             double (&acc)[4 * V], double& loss, int& nCoincident) {
-    const float d2 = point_dist2<V>(xu, xv);
+// Attraction, centre force and optimizer (WembedEmbedder.cpp:260-272, 140-172, 296-301; AdamOptimizer.cpp:15-30).
+//
+// Layout of the work: G = V (rounded up to a power of two) lanes share one vertex and lane c owns float4 chunk c of every
+// row it touches - its own row, the neighbours' rows, the force, the Adam moments.  For one edge the G lanes read the
+// neighbour's row with ONE coalesced access (16 B per lane), add their partial squared distances with log2(G) shuffles and
+// each accumulates its own four force components in double; nothing has to be reduced at the end and every lane is busy in the
+// optimizer epilogue.  The pair weight ws(v,u) = iw_v * iw_u is read from a per-CSR-entry array (weights are constant during a
+// run, WembedEmbedder.cpp:121-131), so the only gather per edge is the neighbour row.
+
+// ws of every CSR entry (recomputed by wb_set_weights)
+__global__ void k_edge_weights(const int* __restrict__ rowPtr, const int* __restrict__ col, const float* __restrict__ iw, int n,
+                               float* __restrict__ edgeWs) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const float iwv = iw[v];
+    for (int e = rowPtr[v]; e < rowPtr[v + 1]; ++e) edgeWs[e] = iwv * iw[col[e]];
+}
+
+__host__ __device__ constexpr int attract_lanes(int V) { return V <= 1 ? 1 : (V <= 2 ? 2 : (V <= 4 ? 4 : 8)); }
+
+__device__ __forceinline__ float chunk_dist2(float4 a, float4 b) {
+    float e, d2;
+    e = a.x - b.x; d2 = e * e;
+    e = a.y - b.y; d2 = fmaf(e, e, d2);
+    e = a.z - b.z; d2 = fmaf(e, e, d2);
+    e = a.w - b.w; d2 = fmaf(e, e, d2);
+    return d2;
+}
+
+// one attractive pair, chunk view (attractionForce, WembedEmbedder.cpp:140-172): d2 is the full squared distance
+__device__ __forceinline__ void attract_chunk(float4 xv, float4 xu, float d2, float ws, float L, float scale, double (&acc)[4],
+                                              double& loss, int& nCoincident) {
     const float dist = sqrtf(d2);
     if (dist <= 0.f) { ++nCoincident; return; }               // :150-155, resolved by the caller
-    const float ws = iwv * iwu;
     if (dist * ws > L) {                                       // :163-168
-        axpy_diff_d<V>(acc, scale * ws / dist, xu, xv);
+        const float s = scale * ws / dist;
+        acc[0] += (double)(s * (xu.x - xv.x));
+        acc[1] += (double)(s * (xu.y - xv.y));
+        acc[2] += (double)(s * (xu.z - xv.z));
+        acc[3] += (double)(s * (xu.w - xv.w));
         loss += (double)(dist - L / ws);
     }
 }
@@ -494,7 +524,7 @@ __device__ __forceinline__ void attract_pair(const float4 (&xv)[V], float iwv, c
 // Hub rows (degree > hubThreshold; heavy-tailed graphs have rows of 1e4-1e5 entries): one block per hub strides over the row,
 // sums in double and reduces in a fixed order; k_attract_update picks the result up instead of walking the row itself.
 template <int V>
-__global__ void __launch_bounds__(256) k_attract_hubs(const float4* __restrict__ x, const float* __restrict__ iw, const int* __restrict__ rowPtr,
+__global__ void __launch_bounds__(256) k_attract_hubs(const float4* __restrict__ x, const float* __restrict__ edgeWs, const int* __restrict__ rowPtr,
                                                       const int* __restrict__ col, const int* __restrict__ hubVertex, const ForceParams fp,
                                                       double* __restrict__ hubForce /* [hub][4V + 2] */) {
     constexpr int K = 4 * V + 2;
@@ -502,38 +532,36 @@ __global__ void __launch_bounds__(256) k_attract_hubs(const float4* __restrict__
     const int v = hubVertex[blockIdx.x];
     float4 xv[V];
     load_row<V>(x, v, xv);
-    const float iwv = __ldg(iw + v);
     double vals[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) vals[k] = 0.0;
-    double acc[4 * V], loss = 0.0;
-#pragma unroll
-    for (int k = 0; k < 4 * V; ++k) acc[k] = 0.0;
     int nCoincident = 0;
     const int end = __ldg(rowPtr + v + 1);
     for (int e = __ldg(rowPtr + v) + threadIdx.x; e < end; e += 256) {
         const int u = __ldg(col + e);
-        if (u == v) continue;
+        const float ws = __ldg(edgeWs + e);
         float4 xu[V];
         load_row<V>(x, u, xu);
-        attract_pair<V>(xv, iwv, xu, __ldg(iw + u), fp.edgeLength, fp.attractionScale, acc, loss, nCoincident);
-    }
+        const float d2 = point_dist2<V>(xu, xv);
+        int coincidentHere = 0;
 #pragma unroll
-    for (int k = 0; k < 4 * V; ++k) vals[k] = acc[k];
-    vals[4 * V] = loss;
+        for (int c = 0; c < V; ++c) {
+            double acc[4] = {0.0, 0.0, 0.0, 0.0}, loss = 0.0;
+            int nc = 0;
+            attract_chunk(xv[c], xu[c], d2, ws, fp.edgeLength, fp.attractionScale, acc, loss, nc);
+            vals[4 * c] += acc[0]; vals[4 * c + 1] += acc[1]; vals[4 * c + 2] += acc[2]; vals[4 * c + 3] += acc[3];
+            if (c == 0) { vals[4 * V] += loss; coincidentHere = nc; }
+        }
+        nCoincident += coincidentHere;
+    }
     vals[4 * V + 1] = (double)nCoincident;
     block_sum<K, 256>(vals, redBuf, hubForce + (int64_t)blockIdx.x * K);
 }
 
-// ---------------------------------------------------------------------------------------------
-// Attraction + centre force + optimizer, fused (WembedEmbedder.cpp:260-272, 140-172, 296-301; AdamOptimizer.cpp:15-30):
-// the north_star's "fused step kernel".  One thread owns one vertex: it walks the CSR row (two edges in flight), sums in
-// double, adds the repulsive force of k_repulse_pairs, the centre force and the tie-break vectors, and updates x / m / v of
-// its row (a warp reads and writes 32 consecutive rows: coalesced).  No shuffles, no idle lanes; rows longer than the hub
-// threshold are pre-summed by k_attract_hubs.  Each block owns a fixed contiguous vertex range and emits
+// The north_star's "fused step kernel".  Each block owns a fixed contiguous vertex range and emits
 // {lossA, lossR, sum_v xnew[v][k]} for the deterministic reducer.
 template <int V>
-__global__ void __launch_bounds__(256) k_attract_update(const float4* __restrict__ x, const float* __restrict__ iw,
+__global__ void __launch_bounds__(256, 4) k_attract_update(const float4* __restrict__ x, const float* __restrict__ edgeWs,
                                                         const int* __restrict__ rowPtr, const int* __restrict__ col, int rangeBegin,
                                                         int rangeEnd, int vertsPerBlock, const ForceParams fp,
                                                         const double* __restrict__ forceRep, const float* __restrict__ lossRep,
@@ -541,121 +569,160 @@ __global__ void __launch_bounds__(256) k_attract_update(const float4* __restrict
                                                         const double* __restrict__ hubForce, float4* __restrict__ xNew,
                                                         float4* __restrict__ mom1, float4* __restrict__ mom2,
                                                         float4* __restrict__ forceOut, double* __restrict__ partials) {
-    constexpr int K = 2 + 4 * V;
+    constexpr int G = attract_lanes(V), VPW = 32 / G, VPB = 8 * VPW, K = 2 + 4 * V;
     __shared__ uint32_t mtState[8][624];
-    __shared__ double redBuf[8 * K];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ double unitBuf[8][VPW][4 * V];
+    __shared__ double redBuf[8][K];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = lane % G, gi = lane / G;
+    const bool chunkLane = c < V;                                  // lanes G > V (V = 3, 5, 6, 7) only take part in the shuffles
     const int vBegin = rangeBegin + blockIdx.x * vertsPerBlock;     // [rangeBegin, rangeEnd): the vertices this rank owns
     const int vEnd = min(rangeEnd, vBegin + vertsPerBlock);
-    double sums[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) sums[k] = 0.0;
+    double sumLossA = 0.0, sumLossR = 0.0, sumX[4] = {0.0, 0.0, 0.0, 0.0};
     const float L = fp.edgeLength;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    for (int vBase = vBegin; vBase < vEnd; vBase += 256) {
-        const int v = vBase + threadIdx.x;
+    for (int vBase = vBegin; vBase < vEnd; vBase += VPB) {
+        const int v = vBase + warp * VPW + gi;
         const bool valid = v < vEnd;
-        float4 xv[V];
-        double acc[4 * V];      // summed in double, see k_repulse_pairs
-#pragma unroll
-        for (int k = 0; k < 4 * V; ++k) acc[k] = 0.0;
+        const int64_t at = (int64_t)v * V + c;
+        float4 xv = zero4;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};      // summed in double, see k_repulse_pairs
         double loss = 0.0;
         int nCoincident = 0;
+        int e = 0, end = 0, hub = -1;
         if (valid) {
-            load_row<V>(x, v, xv);
-            const float iwv = __ldg(iw + v);
-            const int hub = hubSlot ? __ldg(hubSlot + v) : -1;
-            if (hub >= 0) {
-                const double* hf = hubForce + (int64_t)hub * (4 * V + 2);
+            if (chunkLane) xv = __ldg(x + at);
+            hub = hubSlot ? __ldg(hubSlot + v) : -1;
+            if (hub < 0) { e = __ldg(rowPtr + v); end = __ldg(rowPtr + v + 1); }
+        }
+        // all G lanes of a vertex walk the same edges; groups of one warp have different row lengths, the shuffles below need
+        // every lane, so the warp iterates to the longest row of its groups (rows beyond hubThreshold are pre-summed)
+        int len = end - e;
 #pragma unroll
-                for (int k = 0; k < 4 * V; ++k) acc[k] = hf[k];
-                loss = hf[4 * V];
-                nCoincident = (int)hf[4 * V + 1];
-            } else {
-                int e = __ldg(rowPtr + v);
-                const int end = __ldg(rowPtr + v + 1);
-                for (; e + 1 < end; e += 2) {                      // neighbours in ascending order, two rows in flight
-                    const int u0 = __ldg(col + e), u1 = __ldg(col + e + 1);
-                    float4 a[V], b[V];
-                    load_row<V>(x, u0, a);
-                    load_row<V>(x, u1, b);
-                    const float iw0 = __ldg(iw + u0), iw1 = __ldg(iw + u1);
-                    if (u0 != v) attract_pair<V>(xv, iwv, a, iw0, L, fp.attractionScale, acc, loss, nCoincident);   // v == u -> 0 (:141)
-                    if (u1 != v) attract_pair<V>(xv, iwv, b, iw1, L, fp.attractionScale, acc, loss, nCoincident);
-                }
-                if (e < end) {
-                    const int u0 = __ldg(col + e);
-                    float4 a[V];
-                    load_row<V>(x, u0, a);
-                    if (u0 != v) attract_pair<V>(xv, iwv, a, __ldg(iw + u0), L, fp.attractionScale, acc, loss, nCoincident);
+        for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+        for (int i = 0; i < len; i += 4) {                         // neighbours in ascending order, four rows in flight
+            bool has[4];
+            int u[4];
+            float wsE[4], dd[4];
+            float4 r[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                has[j] = e + i + j < end;
+                u[j] = has[j] ? __ldg(col + e + i + j) : 0;
+                wsE[j] = has[j] ? __ldg(edgeWs + e + i + j) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) r[j] = (has[j] && chunkLane) ? __ldg(x + (int64_t)u[j] * V + c) : xv;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dd[j] = chunkLane ? chunk_dist2(r[j], xv) : 0.f;
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dd[j] += __shfl_xor_sync(0xffffffffu, dd[j], o);
+            }
+            // the four terms of the batch are added in fp32 (their sum carries the same relative error as each term), the batch
+            // sum goes into the double accumulator: one conversion + one DADD per component per four edges
+            float bx = 0.f, by = 0.f, bz = 0.f, bw = 0.f, bl = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (!has[j]) continue;
+                const float dist = sqrtf(dd[j]);
+                if (dist <= 0.f) { ++nCoincident; continue; }           // :150-155, resolved below
+                if (dist * wsE[j] > L) {                                 // :163-168
+                    const float sc = fp.attractionScale * wsE[j] / dist;
+                    bx = fmaf(sc, r[j].x - xv.x, bx); by = fmaf(sc, r[j].y - xv.y, by);
+                    bz = fmaf(sc, r[j].z - xv.z, bz); bw = fmaf(sc, r[j].w - xv.w, bw);
+                    bl += dist - L / wsE[j];
                 }
             }
-            nCoincident += __ldg(coincidentRep + v);
-        } else {
-#pragma unroll
-            for (int c = 0; c < V; ++c) xv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            acc[0] += (double)bx; acc[1] += (double)by; acc[2] += (double)bz; acc[3] += (double)bw;
+            loss += (double)bl;
         }
+        if (valid && hub >= 0) {
+            const double* hf = hubForce + (int64_t)hub * (4 * V + 2);
+            if (chunkLane) { acc[0] = hf[4 * c]; acc[1] = hf[4 * c + 1]; acc[2] = hf[4 * c + 2]; acc[3] = hf[4 * c + 3]; }
+            loss = hf[4 * V];
+            nCoincident = (int)hf[4 * V + 1];
+        }
+        if (valid) nCoincident += __ldg(coincidentRep + v);
 
         // coincident partners: every one of them adds the same unit vector (generator re-created per pair, :150-155, :183-188).
-        // The generator state (624 words) lives in per-warp shared memory; the rare lanes that need it take turns.
-        uint32_t need = __ballot_sync(0xffffffffu, nCoincident > 0);
-        while (need) {
-            const int l = __ffs(need) - 1;
-            need &= need - 1u;
-            if (lane == l) {
-                double uvec[4 * V];
-                random_unit_vector(mtState[warp], fp.seed, (uint32_t)v, fp.iteration, fp.dim, uvec);
+        // The generator state (624 words) lives in per-warp shared memory; the rare vertices that need it take turns.
+        uint32_t need = __ballot_sync(0xffffffffu, nCoincident > 0 && c == 0);
+        if (need) {
+            uint32_t todo = need;
+            while (todo) {
+                const int l = __ffs(todo) - 1;
+                todo &= todo - 1u;
+                if (lane == l) random_unit_vector(mtState[warp], fp.seed, (uint32_t)v, fp.iteration, fp.dim, unitBuf[warp][gi]);
+                __syncwarp();
+            }
+            if (nCoincident > 0 && chunkLane) {
 #pragma unroll
-                for (int k = 0; k < 4 * V; ++k)
-                    if (k < fp.dim) acc[k] += nCoincident * uvec[k];
+                for (int i = 0; i < 4; ++i)
+                    if (4 * c + i < fp.dim) acc[i] += nCoincident * unitBuf[warp][gi][4 * c + i];
             }
             __syncwarp();
         }
 
-        if (valid) {
-            sums[0] += loss;
-            sums[1] += (double)__ldg(lossRep + v);
-#pragma unroll
-            for (int c = 0; c < V; ++c) {
-                const int64_t at = (int64_t)v * V + c;
-                const double* fr = forceRep + at * 4;
-                float4 f = make_float4((float)(acc[4 * c] + fr[0]), (float)(acc[4 * c + 1] + fr[1]), (float)(acc[4 * c + 2] + fr[2]),
-                                       (float)(acc[4 * c + 3] + fr[3]));
-                if (fp.centreScale != 0.f) {                   // :296-301
-                    f.x = fmaf(-fp.centreScale, xv[c].x, f.x); f.y = fmaf(-fp.centreScale, xv[c].y, f.y);
-                    f.z = fmaf(-fp.centreScale, xv[c].z, f.z); f.w = fmaf(-fp.centreScale, xv[c].w, f.w);
-                }
-                if (fp.keepForces) forceOut[at] = f;
-                float4 xn;
-                if (fp.optimizer == 1) {
-                    float4 m = mom1[at], s = mom2[at];
-                    const float fe[4] = {f.x, f.y, f.z, f.w};
-                    float me[4] = {m.x, m.y, m.z, m.w}, se[4] = {s.x, s.y, s.z, s.w};
-                    float xe[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        me[i] = fp.beta1 * me[i] + (1.f - fp.beta1) * fe[i];
-                        se[i] = fp.beta2 * se[i] + (1.f - fp.beta2) * fe[i] * fe[i];
-                        const float mHat = me[i] * fp.invBias1, vHat = se[i] * fp.invBias2;
-                        xe[i] += fp.lr * mHat / (sqrtf(vHat) + fp.eps);
-                    }
-                    mom1[at] = make_float4(me[0], me[1], me[2], me[3]);
-                    mom2[at] = make_float4(se[0], se[1], se[2], se[3]);
-                    xn = make_float4(xe[0], xe[1], xe[2], xe[3]);
-                } else {
-                    const float cap = fp.maxDisplacement;
-                    xn.x = xv[c].x + fminf(fmaxf(f.x, -cap), cap) * fp.lr;
-                    xn.y = xv[c].y + fminf(fmaxf(f.y, -cap), cap) * fp.lr;
-                    xn.z = xv[c].z + fminf(fmaxf(f.z, -cap), cap) * fp.lr;
-                    xn.w = xv[c].w + fminf(fmaxf(f.w, -cap), cap) * fp.lr;
-                }
-                xNew[at] = xn;
-                sums[2 + 4 * c + 0] += (double)xn.x; sums[2 + 4 * c + 1] += (double)xn.y;
-                sums[2 + 4 * c + 2] += (double)xn.z; sums[2 + 4 * c + 3] += (double)xn.w;
+        if (valid && c == 0) {
+            sumLossA += loss;
+            sumLossR += (double)__ldg(lossRep + v);
+        }
+        if (valid && chunkLane) {
+            const double* fr = forceRep + at * 4;
+            float4 f = make_float4((float)(acc[0] + fr[0]), (float)(acc[1] + fr[1]), (float)(acc[2] + fr[2]), (float)(acc[3] + fr[3]));
+            if (fp.centreScale != 0.f) {                   // :296-301
+                f.x = fmaf(-fp.centreScale, xv.x, f.x); f.y = fmaf(-fp.centreScale, xv.y, f.y);
+                f.z = fmaf(-fp.centreScale, xv.z, f.z); f.w = fmaf(-fp.centreScale, xv.w, f.w);
             }
+            if (fp.keepForces) forceOut[at] = f;
+            float4 xn;
+            if (fp.optimizer == 1) {
+                const float4 m = mom1[at], s = mom2[at];
+                const float fe[4] = {f.x, f.y, f.z, f.w};
+                float me[4] = {m.x, m.y, m.z, m.w}, se[4] = {s.x, s.y, s.z, s.w};
+                float xe[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    me[i] = fp.beta1 * me[i] + (1.f - fp.beta1) * fe[i];
+                    se[i] = fp.beta2 * se[i] + (1.f - fp.beta2) * fe[i] * fe[i];
+                    const float mHat = me[i] * fp.invBias1, vHat = se[i] * fp.invBias2;
+                    xe[i] += fp.lr * mHat / (sqrtf(vHat) + fp.eps);
+                }
+                mom1[at] = make_float4(me[0], me[1], me[2], me[3]);
+                mom2[at] = make_float4(se[0], se[1], se[2], se[3]);
+                xn = make_float4(xe[0], xe[1], xe[2], xe[3]);
+            } else {
+                const float cap = fp.maxDisplacement;
+                xn.x = xv.x + fminf(fmaxf(f.x, -cap), cap) * fp.lr;
+                xn.y = xv.y + fminf(fmaxf(f.y, -cap), cap) * fp.lr;
+                xn.z = xv.z + fminf(fmaxf(f.z, -cap), cap) * fp.lr;
+                xn.w = xv.w + fminf(fmaxf(f.w, -cap), cap) * fp.lr;
+            }
+            xNew[at] = xn;
+            sumX[0] += (double)xn.x; sumX[1] += (double)xn.y; sumX[2] += (double)xn.z; sumX[3] += (double)xn.w;
         }
     }
-    block_sum<K, 256>(sums, redBuf, partials + (int64_t)blockIdx.x * K);
+    // fixed-order block reduction: lanes that own the same chunk add up (xor offsets G, 2G, ..), then the 8 warps in order
+#pragma unroll
+    for (int o = G; o < 32; o <<= 1) {
+        sumLossA += __shfl_xor_sync(0xffffffffu, sumLossA, o);
+        sumLossR += __shfl_xor_sync(0xffffffffu, sumLossR, o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sumX[i] += __shfl_xor_sync(0xffffffffu, sumX[i], o);
+    }
+    if (lane == 0) { redBuf[warp][0] = sumLossA; redBuf[warp][1] = sumLossR; }
+    if (lane < G && chunkLane) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) redBuf[warp][2 + 4 * c + i] = sumX[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < K) {
+        double sacc = 0.0;
+        for (int w = 0; w < 8; ++w) sacc += redBuf[w][threadIdx.x];
+        partials[(int64_t)blockIdx.x * K + threadIdx.x] = sacc;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

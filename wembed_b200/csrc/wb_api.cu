@@ -88,6 +88,7 @@ struct wb_embedder {
     float4 *x = nullptr, *xNew = nullptr, *mom1 = nullptr, *mom2 = nullptr, *force = nullptr;
     double* forceRep = nullptr;           // repulsive partial force, n x 4V doubles
     float *iw = nullptr, *lossRep = nullptr;
+    float* edgeWs = nullptr;              // ws(v,u) = iw_v * iw_u of every CSR entry
     int* coincident = nullptr;
     int* chunkCounter = nullptr;          // work counter of the persistent repulsion kernel
     int numHubs = 0;                      // rows longer than kHubThreshold, pre-summed by k_attract_hubs
@@ -165,7 +166,7 @@ inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 void free_all(wb_embedder* h) {
     auto F = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
     F(h->rowPtr); F(h->col); F(h->x); F(h->xNew); F(h->mom1); F(h->mom2); F(h->forceRep); F(h->force);
-    F(h->iw); F(h->lossRep); F(h->coincident); F(h->chunkCounter); F(h->hubVertex); F(h->hubSlot); F(h->hubForce); F(h->band); F(h->keysIn); F(h->keysOut); F(h->valsIn); F(h->valsOut);
+    F(h->iw); F(h->lossRep); F(h->edgeWs); F(h->coincident); F(h->chunkCounter); F(h->hubVertex); F(h->hubSlot); F(h->hubForce); F(h->band); F(h->keysIn); F(h->keysOut); F(h->valsIn); F(h->valsOut);
     F(h->cubTemp); F(h->momentPartials); F(h->quant); F(h->ids);
     for (int l = 0; l < wb::kMaxLevels; ++l) { F(h->lvlLo[l]); if (l > 0) F(h->lvlHi[l]); F(h->lvlBound[l]); }
     F(h->partialsForce); F(h->partialsRep); F(h->partialsObs); F(h->sumsAll); F(h->ownedList); F(h->ownedCount); F(h->selectTemp); F(h->gathered); F(h->localSums);
@@ -209,11 +210,13 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
         WB_CUDA(cudaMemsetAsync(*p, 0, std::max<size_t>(rows, 1) * sizeof(float4), h->stream));
     }
     h->iw = dalloc<float>(n);
+    h->edgeWs = dalloc<float>(h->numDirected);
     h->lossRep = dalloc<float>(n);
     h->coincident = dalloc<int>(n);
     WB_CUDA(cudaMemsetAsync(h->lossRep, 0, std::max(n, 1) * sizeof(float), h->stream));
     WB_CUDA(cudaMemsetAsync(h->coincident, 0, std::max(n, 1) * sizeof(int), h->stream));
     if (n) wb::k_fill<float><<<div_up(n, 256), 256, 0, h->stream>>>(h->iw, n, 1.0f);
+    if (h->numDirected) wb::k_fill<float><<<div_up(h->numDirected, 256), 256, 0, h->stream>>>(h->edgeWs, h->numDirected, 1.0f);
     h->weights.assign(n, 1.0);
     h->classMax.assign(n, 1.0);
 
@@ -262,7 +265,7 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
     t.ids = h->ids;
 
     // reductions: fixed block -> vertex-range assignment so the sums do not depend on scheduling
-    const int groupsPerBlock = 256;      // one thread per vertex
+    const int groupsPerBlock = 256 / wb::attract_lanes(V);      // vertices per block iteration
     h->forceBlocks = std::max(1, std::min(div_up(n, groupsPerBlock), 148 * 16));
     h->forceVertsPerBlock = std::max(groupsPerBlock, div_up(div_up(n, h->forceBlocks), groupsPerBlock) * groupsPerBlock);
     h->forceBlocks = std::max(1, div_up(n, h->forceVertsPerBlock));
@@ -385,11 +388,11 @@ void enqueue_step(wb_embedder* h, double learningRate) {
     wb::k_reduce_partials<<<3, 256, 0, s>>>(h->partialsRep, h->repBlocks * wb::repulse_warps(V), 3, sums + K);
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[2], s));
     if (h->numHubs) {
-        WB_DISPATCH_V(V, wb::k_attract_hubs<V><<<h->numHubs, 256, 0, s>>>(h->x, h->iw, h->rowPtr, h->col, h->hubVertex, fp, h->hubForce));
+        WB_DISPATCH_V(V, wb::k_attract_hubs<V><<<h->numHubs, 256, 0, s>>>(h->x, h->edgeWs, h->rowPtr, h->col, h->hubVertex, fp, h->hubForce));
         h->launches += 1;
     }
     WB_DISPATCH_V(V, wb::k_attract_update<V><<<h->forceBlocks, 256, 0, s>>>(
-                         h->x, h->iw, h->rowPtr, h->col, h->ownBegin, h->ownEnd, h->forceVertsPerBlock, fp, h->forceRep, h->lossRep,
+                         h->x, h->edgeWs, h->rowPtr, h->col, h->ownBegin, h->ownEnd, h->forceVertsPerBlock, fp, h->forceRep, h->lossRep,
                          h->coincident, h->hubSlot, h->hubForce, h->xNew, h->mom1, h->mom2, h->force, h->partialsForce));
     wb::k_reduce_partials<<<K, 256, 0, s>>>(h->partialsForce, h->forceBlocks, K, sums);
     if (sharded) {   // {lossA, lossR, sum xnew[k], pairs, tests}: all-gather, then every rank adds in rank order
@@ -585,6 +588,7 @@ int wb_set_weights(wb_embedder* h, const double* weights) {
         std::vector<float> iw(n);
         for (int v = 0; v < n; ++v) iw[v] = (float)(1.0 / std::pow(weights[v], 1.0 / (double)h->dim));
         WB_CUDA(cudaMemcpyAsync(h->iw, iw.data(), sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+        wb::k_edge_weights<<<div_up(n, 256), 256, 0, h->stream>>>(h->rowPtr, h->col, h->iw, n, h->edgeWs);
         WB_CUDA(cudaStreamSynchronize(h->stream));
         const double minW = *std::min_element(h->weights.begin(), h->weights.end());
         const double maxW = *std::max_element(h->weights.begin(), h->weights.end());
@@ -722,7 +726,7 @@ int wb_comm_init(wb_embedder* h, const char* id128, int32_t rank, int32_t world)
             *p = q;
         }
         // block -> vertex-range assignment over the owned range
-        const int own = std::max(1, h->ownEnd - h->ownBegin), groupsPerBlock = 256, K = 2 + 4 * V;
+        const int own = std::max(1, h->ownEnd - h->ownBegin), groupsPerBlock = 256 / wb::attract_lanes(V), K = 2 + 4 * V;
         h->forceBlocks = std::max(1, std::min(div_up(own, groupsPerBlock), 148 * 16));
         h->forceVertsPerBlock = std::max(groupsPerBlock, div_up(div_up(own, h->forceBlocks), groupsPerBlock) * groupsPerBlock);
         h->forceBlocks = std::max(1, div_up(own, h->forceVertsPerBlock));
