@@ -179,6 +179,16 @@ int wb_get_phase_times(wb_embedder* h, double* ms6);
 int wb_comm_unique_id(char* id128);
 int wb_comm_init(wb_embedder* h, const char* id128, int32_t rank, int32_t world);
 
+/* -- evaluation ("next") ---------------------------------------------------------- */
+
+/*
+ * evaluationLib's Reconstruction metric (src/evaluationLib/src/metrics/Reconstruction.cpp:6-23, NodeSampler.cpp:5-111) of
+ * the CURRENT layout on the WeightedGeometric similarity dist / (w_a w_b)^(1/d) (WeightedGeometric.cpp:17-21), for the given
+ * sample of vertices: out2[0] = "constructDeg" (mean precision at k = degree), out2[1] = "MAP" (mean average precision).
+ * Vertices without neighbours are skipped.  The caller chooses the sample (the reference draws <= 1000 random nodes).
+ */
+int wb_reconstruction(wb_embedder* h, int32_t count, const int32_t* nodes, double* out2);
+
 /* -- measurement ------------------------------------------------------------------------- */
 
 /* Records CUDA event `slot` (0..7) on the handle's stream; wb_elapsed_ms waits for event `to` and returns the

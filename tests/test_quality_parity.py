@@ -46,3 +46,34 @@ def test_quality_matches_oracle_within_one_percent(device_lib, port_lib):
     it_dev, _ = run_to_convergence(dev, {"maxIterations": 4000})
     q_final = reconstruction_metrics(dev.coordinates(), w, rp, col, nodes)
     assert q_final[0] >= q_dev[0] - 0.01 and q_final[1] >= q_dev[1] - 0.01
+
+
+@pytest.mark.gpu
+def test_device_reconstruction_metric(device_lib):
+    """wb_reconstruction against the reference's known answers (tests/TestMetrics.cpp:29-62) and against the numpy
+    restatement of NodeSampler on a geometric graph with hubs and isolated vertices."""
+    rp, col = np.array([0, 1, 3, 4], np.int32), np.array([1, 0, 2, 1], np.int32)
+    dev = device_lib.DeviceEmbedder(rp, col, embedding_dimension=2)
+    dev.set_weights(np.ones(3))
+    dev.set_coordinates(np.array([[0.0, 0.0], [1.0, 0.0], [2.0, 0.0]]))
+    assert dev.reconstruction([0, 1, 2]) == (1.0, 1.0)
+    dev.set_coordinates(np.array([[0.0, 0.0], [3.0, 0.0], [1.0, 0.0]]))
+    cd, mp = dev.reconstruction([0, 1, 2])
+    assert cd == pytest.approx(1.0 / 3.0) and mp == pytest.approx((0.5 + 0.5 + 1.0) / 3.0)
+
+    n, d = 4000, 5
+    edges, w, x0 = make_problem(n, d)
+    edges = np.concatenate([edges[(edges != 17).all(axis=1)], [(3, v) for v in range(100, 2300)]])   # 17 isolated, 3 a hub
+    from wembed_b200.datasets import degree_weights
+    w = degree_weights(n, edges, d)
+    rp, col = device_lib.csr_from_edges(n, edges)
+    dev = device_lib.DeviceEmbedder(rp, col, embedding_dimension=d, seed=1)
+    dev.set_weights(w)
+    dev.set_coordinates(x0)
+    for it in range(1, 60):
+        dev.step(lr_exponential(it))
+    nodes = np.concatenate([[3, 17], np.random.default_rng(1).choice(n, 300, replace=False)])
+    got = dev.reconstruction(nodes)
+    exp = reconstruction_metrics(dev.coordinates(), w, rp, col, nodes)
+    assert got == pytest.approx(exp, rel=1e-9), (got, exp)
+    assert 0.0 < got[0] < 1.0

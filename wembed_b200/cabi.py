@@ -23,7 +23,7 @@ EXPORTS = (
     "wb_abi_version", "wb_build_info", "wb_last_error", "wb_device_count", "wb_options_default", "wb_create", "wb_destroy",
     "wb_set_coordinates", "wb_set_weights", "wb_get_coordinates", "wb_get_weights", "wb_get_forces", "wb_reset_optimizer",
     "wb_set_iteration", "wb_step", "wb_step_async", "wb_step_collect", "wb_synchronize", "wb_query_candidates",
-    "wb_enable_timing", "wb_get_phase_times", "wb_mark", "wb_elapsed_ms", "wb_launch_count", "wb_comm_unique_id", "wb_comm_init",
+    "wb_enable_timing", "wb_get_phase_times", "wb_mark", "wb_elapsed_ms", "wb_launch_count", "wb_comm_unique_id", "wb_comm_init", "wb_reconstruction",
 )
 
 
@@ -79,6 +79,7 @@ def lib():
         "wb_enable_timing": (C.c_int, [H, C.c_int]), "wb_get_phase_times": (C.c_int, [H, dp]),
         "wb_mark": (C.c_int, [H, C.c_int]), "wb_elapsed_ms": (C.c_int, [H, C.c_int, C.c_int, dp]),
         "wb_launch_count": (C.c_int64, [H]),
+        "wb_reconstruction": (C.c_int, [H, i32, ip, dp]),
         "wb_comm_unique_id": (C.c_int, [C.c_char_p]), "wb_comm_init": (C.c_int, [H, C.c_char_p, i32, i32]),
     }
     for name, (res, args) in sig.items():
@@ -202,6 +203,13 @@ class DeviceEmbedder:
 
     def launch_count(self):
         return int(self._l.wb_launch_count(self._h))
+
+    def reconstruction(self, nodes):
+        """(constructDeg, MAP) of the current layout for the sampled vertices (evaluationLib Reconstruction)."""
+        q = np.ascontiguousarray(nodes, dtype=np.int32)
+        out = np.zeros(2, np.float64)
+        self._check(self._l.wb_reconstruction(self._h, len(q), _ip(q), _dp(out)))
+        return float(out[0]), float(out[1])
 
     def comm_init(self, unique_id: bytes, rank: int, world: int):
         """Join the vertex-sharded multi-GPU step (see include/wembed_b200.h)."""

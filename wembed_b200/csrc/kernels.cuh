@@ -397,6 +397,8 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
                         // normalises every component, so a cancellation residue must keep the accuracy of its terms
                         double* fr = forceRep + (int64_t)v * 4 * V;
                         const float sc = fp.repulsionScale * ws / dist;
+                        if (fp.dim == 1) fr[0] += (double)copysignf(fp.repulsionScale * ws, q[0].x - pu[0].x);   // unit vector exactly +-1
+                        else
 #pragma unroll
                         for (int k = 0; k < V; ++k) {
                             fr[4 * k + 0] += (double)(sc * (q[k].x - pu[k].x));
@@ -507,17 +509,18 @@ __device__ __forceinline__ float chunk_dist2(float4 a, float4 b) {
 }
 
 // one attractive pair, chunk view (attractionForce, WembedEmbedder.cpp:140-172): d2 is the full squared distance
-__device__ __forceinline__ void attract_chunk(float4 xv, float4 xu, float d2, float ws, float L, float scale, double (&acc)[4],
+__device__ __forceinline__ void attract_chunk(float4 xv, float4 xu, float d2, float ws, float L, float scale, int dim, double (&acc)[4],
                                               double& loss, int& nCoincident) {
     const float dist = sqrtf(d2);
     if (dist <= 0.f) { ++nCoincident; return; }               // :150-155, resolved by the caller
     if (dist * ws > L) {                                       // :163-168
+        loss += (double)(dist - L / ws);
+        if (dim == 1) { acc[0] += (double)copysignf(scale * ws, xu.x - xv.x); return; }   // unit vector exactly +-1
         const float s = scale * ws / dist;
         acc[0] += (double)(s * (xu.x - xv.x));
         acc[1] += (double)(s * (xu.y - xv.y));
         acc[2] += (double)(s * (xu.z - xv.z));
         acc[3] += (double)(s * (xu.w - xv.w));
-        loss += (double)(dist - L / ws);
     }
 }
 
@@ -548,7 +551,7 @@ __global__ void __launch_bounds__(256) k_attract_hubs(const float4* __restrict__
         for (int c = 0; c < V; ++c) {
             double acc[4] = {0.0, 0.0, 0.0, 0.0}, loss = 0.0;
             int nc = 0;
-            attract_chunk(xv[c], xu[c], d2, ws, fp.edgeLength, fp.attractionScale, acc, loss, nc);
+            attract_chunk(xv[c], xu[c], d2, ws, fp.edgeLength, fp.attractionScale, fp.dim, acc, loss, nc);
             vals[4 * c] += acc[0]; vals[4 * c + 1] += acc[1]; vals[4 * c + 2] += acc[2]; vals[4 * c + 3] += acc[3];
             if (c == 0) { vals[4 * V] += loss; coincidentHere = nc; }
         }
@@ -629,9 +632,15 @@ __global__ void __launch_bounds__(256, 4) k_attract_update(const float4* __restr
                 const float dist = sqrtf(dd[j]);
                 if (dist <= 0.f) { ++nCoincident; continue; }           // :150-155, resolved below
                 if (dist * wsE[j] > L) {                                 // :163-168
-                    const float sc = fp.attractionScale * wsE[j] / dist;
-                    bx = fmaf(sc, r[j].x - xv.x, bx); by = fmaf(sc, r[j].y - xv.y, by);
-                    bz = fmaf(sc, r[j].z - xv.z, bz); bw = fmaf(sc, r[j].w - xv.w, bw);
+                    if (fp.dim == 1) {
+                        // one dimension: the unit vector is exactly +-1 (VectorOperations.hpp:19-24), so symmetric neighbours
+                        // cancel exactly as they do in the reference
+                        bx += copysignf(fp.attractionScale * wsE[j], r[j].x - xv.x);
+                    } else {
+                        const float sc = fp.attractionScale * wsE[j] / dist;
+                        bx = fmaf(sc, r[j].x - xv.x, bx); by = fmaf(sc, r[j].y - xv.y, by);
+                        bz = fmaf(sc, r[j].z - xv.z, bz); bw = fmaf(sc, r[j].w - xv.w, bw);
+                    }
                     bl += dist - L / wsE[j];
                 }
             }
@@ -812,6 +821,105 @@ template <typename T>
 __global__ void k_fill(T* p, int64_t count, T value) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count) p[i] = value;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Reconstruction quality: evaluationLib's NodeSampler / Reconstruction
+// (src/evaluationLib/src/metrics/NodeSampler.cpp:5-111, Reconstruction.cpp:6-23) on the WeightedGeometric similarity
+// dist / (w_a w_b)^(1/d) (src/embeddingLib/src/embeddingSpace/WeightedGeometric.cpp:17-21), without sorting all n nodes:
+// for a sampled vertex v with sorted neighbour keys S_0 < S_1 < .. (key = (similarity, id), the reference's tie order), every
+// other node x bumps the counter of p = upper_bound(S, key_x); rank(S_j) = sum_{p <= j} cnt[p] is the number of nodes ranked
+// before neighbour j, so precision at that neighbour = (j + 1) / (rank + 1).  One block per sampled vertex; all arithmetic
+// in double on the fp32 positions; counters are integers, so the result does not depend on scheduling.
+struct SimKey {
+    double sim;
+    int id;
+};
+__device__ __forceinline__ bool key_less(const SimKey& a, const SimKey& b) { return a.sim < b.sim || (a.sim == b.sim && a.id < b.id); }
+
+template <int V>
+__device__ __forceinline__ double similarity(const float4* __restrict__ x, const double* __restrict__ wroot, int a, const float4 (&xa)[V],
+                                             double wra, int b) {
+    double d2 = 0.0;
+#pragma unroll
+    for (int c = 0; c < V; ++c) {
+        const float4 p = __ldg(x + (int64_t)b * V + c);
+        double e;
+        e = (double)p.x - (double)xa[c].x; d2 += e * e;
+        e = (double)p.y - (double)xa[c].y; d2 += e * e;
+        e = (double)p.z - (double)xa[c].z; d2 += e * e;
+        e = (double)p.w - (double)xa[c].w; d2 += e * e;
+    }
+    (void)a;
+    return sqrt(d2) / (wra * wroot[b]);
+}
+
+template <int V>
+__global__ void __launch_bounds__(256) k_reconstruction(const float4* __restrict__ x, const double* __restrict__ wroot, const int* __restrict__ rowPtr,
+                                                        const int* __restrict__ col, int n, const int* __restrict__ nodes, int first, int count,
+                                                        int capacity, SimKey* __restrict__ keyScratch, int* __restrict__ cntScratch,
+                                                        double* __restrict__ out /* [count][3]: precision@deg, AP, valid */) {
+    const int s = first + blockIdx.x;
+    if (s >= count) return;
+    const int v = nodes[s];
+    const int begin = rowPtr[v], deg = rowPtr[v + 1] - begin;
+    double* o = out + (int64_t)s * 3;
+    if (deg == 0) { if (threadIdx.x == 0) { o[0] = 0.0; o[1] = 0.0; o[2] = 0.0; } return; }
+    SimKey* keys = keyScratch + (int64_t)blockIdx.x * capacity;
+    int* cnt = cntScratch + (int64_t)blockIdx.x * (capacity + 1);
+    float4 xv[V];
+    load_row<V>(x, v, xv);
+    const double wrv = wroot[v];
+    int pow2 = 1;
+    while (pow2 < deg) pow2 <<= 1;
+    for (int i = threadIdx.x; i < pow2; i += 256) {
+        SimKey k;
+        if (i < deg) { k.id = col[begin + i]; k.sim = similarity<V>(x, wroot, v, xv, wrv, k.id); }
+        else { k.id = 0x7fffffff; k.sim = 1.0e300; }
+        keys[i] = k;
+    }
+    for (int i = threadIdx.x; i <= deg; i += 256) cnt[i] = 0;
+    __syncthreads();
+    // bitonic sort of the neighbour keys (deg is ~10 for most vertices, up to 1e5 for hubs; scratch lives in L1/L2)
+    for (int k = 2; k <= pow2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < pow2; i += 256) {
+                const int partner = i ^ j;
+                if (partner > i) {
+                    const SimKey a = keys[i], b = keys[partner];
+                    const bool up = (i & k) == 0;
+                    if (key_less(b, a) == up) { keys[i] = b; keys[partner] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int xnode = threadIdx.x; xnode < n; xnode += 256) {
+        if (xnode == v) continue;
+        SimKey kx;
+        kx.id = xnode;
+        kx.sim = similarity<V>(x, wroot, v, xv, wrv, xnode);
+        int lo = 0, hi = deg;                      // first neighbour key greater than kx
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (key_less(kx, keys[mid])) hi = mid; else lo = mid + 1;
+        }
+        atomicAdd(cnt + lo, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long before = 0;
+        double ap = 0.0;
+        int atDeg = 0;
+        for (int j = 0; j < deg; ++j) {
+            before += cnt[j];                      // nodes ranked before neighbour j (0-based rank)
+            ap += (double)(j + 1) / (double)(before + 1);
+            if (before < deg) ++atDeg;
+        }
+        o[0] = (double)atDeg / (double)deg;        // precisions[deg - 1] (NodeSampler.cpp:46)
+        o[1] = ap / (double)deg;                   // getAveragePrecision (NodeSampler.cpp:95-111)
+        o[2] = 1.0;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -95,6 +95,7 @@ struct wb_embedder {
     int *hubVertex = nullptr, *hubSlot = nullptr;
     double* hubForce = nullptr;
     std::vector<double> weights;          // state.currentWeights
+    std::vector<int> hostDegree;          // CSR row lengths (host copy)
     std::vector<double> classMax;         // maxWeightOfClass[class(v)] (WeightedIndex.cpp:25-32), for the test hook
     int64_t iteration = 0;                // state.currentIteration
     int adamT = 0;                        // AdamOptimizer::t
@@ -188,6 +189,8 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
     WB_CUDA(cudaMemcpyAsync(h->rowPtr, rowPtr, sizeof(int) * (n + 1), cudaMemcpyHostToDevice, h->stream));
     if (h->numDirected) WB_CUDA(cudaMemcpyAsync(h->col, col, sizeof(int) * h->numDirected, cudaMemcpyHostToDevice, h->stream));
 
+    h->hostDegree.resize(n);
+    for (int v = 0; v < n; ++v) h->hostDegree[v] = rowPtr[v + 1] - rowPtr[v];
     {   // hub rows
         std::vector<int> hubs, slot(n, -1);
         for (int v = 0; v < n; ++v)
@@ -744,6 +747,52 @@ int wb_comm_init(wb_embedder* h, const char* id128, int32_t rank, int32_t world)
         WB_CUDA(cudaMemsetAsync(h->localSums, 0, sizeof(double) * h->sumsTotal, h->stream));
         WB_CUDA(cudaStreamSynchronize(h->stream));
         (void)K;
+    });
+}
+
+int wb_reconstruction(wb_embedder* h, int32_t count, const int32_t* nodes, double* out2) {
+    if (h && (count < 0 || (count > 0 && !nodes) || !out2)) return fail(WB_ERR_INVALID, "wb_reconstruction: bad arguments");
+    if (h && !h->pending.empty()) return fail(WB_ERR_INVALID, "wb_reconstruction: steps in flight");
+    return guarded(h, [&] {
+        out2[0] = out2[1] = 0.0;
+        const int n = h->n, d = h->dim;
+        if (count == 0 || n == 0) return;
+        std::vector<int> deg(count);
+        int maxDeg = 1;
+        for (int i = 0; i < count; ++i) {
+            if (nodes[i] < 0 || nodes[i] >= n) throw std::runtime_error("wb_reconstruction: node id out of range");
+            deg[i] = h->hostDegree[nodes[i]];
+            maxDeg = std::max(maxDeg, deg[i]);
+        }
+        int capacity = 1;
+        while (capacity < maxDeg) capacity <<= 1;
+        const int batch = (int)std::max<int64_t>(1, std::min<int64_t>(count, (int64_t)(64 << 20) / capacity));   // <= 1 Gi scratch bytes
+        std::vector<double> wroot(n);
+        for (int v = 0; v < n; ++v) wroot[v] = std::pow(h->weights[v], 1.0 / (double)d);
+        double* dW = dalloc<double>(n);
+        int* dNodes = dalloc<int>(count);
+        double* dOut = dalloc<double>((size_t)count * 3);
+        wb::SimKey* dKeys = dalloc<wb::SimKey>((size_t)batch * capacity);
+        int* dCnt = dalloc<int>((size_t)batch * (capacity + 1));
+        auto cleanup = [&] { cudaFree(dW); cudaFree(dNodes); cudaFree(dOut); cudaFree(dKeys); cudaFree(dCnt); };
+        try {
+            cudaStream_t s = h->stream;
+            WB_CUDA(cudaMemcpyAsync(dW, wroot.data(), sizeof(double) * n, cudaMemcpyHostToDevice, s));
+            WB_CUDA(cudaMemcpyAsync(dNodes, nodes, sizeof(int) * count, cudaMemcpyHostToDevice, s));
+            for (int first = 0; first < count; first += batch) {
+                WB_DISPATCH_V(h->V, wb::k_reconstruction<V><<<std::min(batch, count - first), 256, 0, s>>>(h->x, dW, h->rowPtr, h->col, n, dNodes, first,
+                                                                                                          count, capacity, dKeys, dCnt, dOut));
+                h->launches += 1;
+            }
+            std::vector<double> res((size_t)count * 3);
+            WB_CUDA(cudaMemcpyAsync(res.data(), dOut, sizeof(double) * res.size(), cudaMemcpyDeviceToHost, s));
+            WB_CUDA(cudaStreamSynchronize(s));
+            double a = 0.0, b = 0.0, k = 0.0;      // Toolkit::averageFromVector over the sampled nodes, in sample order
+            for (int i = 0; i < count; ++i)
+                if (res[3 * i + 2] != 0.0) { a += res[3 * i]; b += res[3 * i + 1]; k += 1.0; }
+            if (k > 0.0) { out2[0] = a / k; out2[1] = b / k; }
+        } catch (...) { cleanup(); throw; }
+        cleanup();
     });
 }
 
