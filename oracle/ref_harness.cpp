@@ -12,6 +12,9 @@
 #include <vector>
 
 #include "Graph.hpp"
+#include "GraphHierarchy.hpp"
+#include "LabelPropagation.hpp"
+#include "LayeredEmbedder.hpp"
 #include "Rand.hpp"
 #include "WembedEmbedder.hpp"
 #include "oracle_api.h"
@@ -173,6 +176,52 @@ int64_t ref_candidates(void* p, int32_t v, int32_t* out, int64_t cap) {
     const std::vector<NodeId> c = e->getRepellingCandidatesForNode(v, buf);
     for (std::size_t i = 0; i < c.size() && static_cast<int64_t>(i) < cap; ++i) out[i] = c[i];
     return static_cast<int64_t>(c.size());
+}
+
+
+// ---- multilevel driver: reference-only helpers used to generate golden fixtures ------------------------
+
+// LabelPropagation::coarsenAllLayers with the defaults of wembed::createEmbedder (src/wembed.cpp:229-233): returns the number
+// of layers; layer_sizes[l] = vertices of layer l, parents = the parent pointers of all layers concatenated.
+int32_t ref_coarsen(int64_t m, const int32_t* src, const int32_t* dst, int32_t* layer_sizes, int32_t max_layers, int32_t* parents,
+                    int64_t cap) {
+    std::vector<std::pair<int, int>> edges;
+    for (int64_t i = 0; i < m; ++i) edges.emplace_back(src[i], dst[i]);
+    Graph g(edges);
+    std::vector<double> edgeWeights(g.getNumEdges() * 2, 1.0);
+    LabelPropagation coarsener(PartitionerOptions{}, g, edgeWeights);
+    const ParentPointerTree tree = coarsener.coarsenAllLayers();
+    int64_t at = 0;
+    for (std::size_t l = 0; l < tree.size() && static_cast<int32_t>(l) < max_layers; ++l) {
+        layer_sizes[l] = static_cast<int32_t>(tree[l].size());
+        for (NodeId p : tree[l])
+            if (at < cap) parents[at++] = p;
+    }
+    return static_cast<int32_t>(tree.size());
+}
+
+// The whole layered embedding (LayeredEmbedder::calculateEmbedding): final coordinates / weights of layer 0; returns iterations.
+int64_t ref_layered_run(int64_t m, const int32_t* src, const int32_t* dst, const orc_options* o, int32_t seed, double* coords,
+                        double* weights, double* stats8) {
+    if (o->numThreads > 0) omp_set_num_threads(o->numThreads);
+    Rand::setSeed(seed);
+    std::vector<std::pair<int, int>> edges;
+    for (int64_t i = 0; i < m; ++i) edges.emplace_back(src[i], dst[i]);
+    Graph g(edges);
+    std::vector<double> edgeWeights(g.getNumEdges() * 2, 1.0);
+    LabelPropagation coarsener(PartitionerOptions{}, g, edgeWeights);
+    LayeredEmbedder emb(g, coarsener, translate(*o));
+    emb.calculateEmbedding();
+    emb.copyCoordinatesTo(coords);
+    const auto w = emb.getWeights();
+    std::copy(w.begin(), w.end(), weights);
+    const EmbeddingLoss l = emb.getLoss();
+    stats8[ORC_LOSS_ATTRACT] = l.attractive;
+    stats8[ORC_LOSS_REPEL] = l.repulsive;
+    stats8[ORC_LR] = emb.getCurrentLearningRate();
+    stats8[ORC_REL_DISP] = emb.getLastRelDisplacement();
+    stats8[ORC_ITERATION] = static_cast<double>(emb.currentIteration);
+    return emb.currentIteration;
 }
 
 }  // extern "C"

@@ -91,6 +91,36 @@ def main():
         for k, v in g.items():
             out[f"{name}_{k}"] = v
     np.savez_compressed(os.path.join(HERE, "geo300_options.npz"), edges=edges, **out)
+    # (e) multilevel driver: parent pointers of LabelPropagation::coarsenAllLayers and the outcome of a whole
+    #     LayeredEmbedder run, straight from the reference through oracle/ref_harness.cpp
+    import ctypes as C
+    from oracle.oracle import OrcOptions, _PATHS
+    from helpers import reconstruction_metrics
+    from wembed_b200 import cabi
+    from wembed_b200.datasets import heavy_tailed_graph
+    ref = C.CDLL(_PATHS["ref"])
+    ip, dp = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+    out = {}
+    for name, e in (("ring64", ring), ("geo3000", geometric_graph(3000, 10, seed=5)[0]), ("heavy4000", heavy_tailed_graph(4000, 20, seed=1)[0])):
+        src, dst = np.ascontiguousarray(e[:, 0], dtype=np.int32), np.ascontiguousarray(e[:, 1], dtype=np.int32)
+        sizes, parents = np.zeros(64, np.int32), np.zeros(4 * len(e) + 64, np.int32)
+        ref.ref_coarsen.restype = C.c_int32
+        nl = ref.ref_coarsen(C.c_int64(len(src)), src.ctypes.data_as(ip), dst.ctypes.data_as(ip), sizes.ctypes.data_as(ip), 64,
+                             parents.ctypes.data_as(ip), C.c_int64(len(parents)))
+        out[f"{name}_edges"], out[f"{name}_sizes"], out[f"{name}_parents"] = e, sizes[:nl].copy(), parents[: sizes[:nl].sum()].copy()
+        if name == "geo3000":
+            n = int(e.max()) + 1
+            o = OrcOptions()
+            ref.ref_options_default(C.byref(o))
+            o.embeddingDimension = 4
+            x, w, st = np.zeros((n, 4)), np.zeros(n), np.zeros(8)
+            ref.ref_layered_run.restype = C.c_int64
+            iters = ref.ref_layered_run(C.c_int64(len(src)), src.ctypes.data_as(ip), dst.ctypes.data_as(ip), C.byref(o), 7, x.ctypes.data_as(dp),
+                                        w.ctypes.data_as(dp), st.ctypes.data_as(dp))
+            rp, col = cabi.csr_from_edges(n, e)
+            q = reconstruction_metrics(x, w, rp, col, np.arange(0, n, 6))
+            out["geo3000_layered"] = np.array([iters, st[0] + st[1], q[0], q[1]])
+    np.savez_compressed(os.path.join(HERE, "hierarchy.npz"), **out)
     print("golden fixtures written to", HERE)
 
 

@@ -17,8 +17,8 @@ _ROOT = os.path.dirname(os.path.dirname(_HERE))
 _LIBDIR = os.path.join(os.path.dirname(_HERE), "lib")
 HOST_LIB = os.path.join(_LIBDIR, "libwembed_host.so")
 PYMOD = os.path.join(_LIBDIR, "wembed" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
-_SRCS = [os.path.join(_HERE, f) for f in ("graph.cpp", "embedder.cpp", "wembed.cpp")]
-_DEPS = _SRCS + [os.path.join(_HERE, f) for f in ("graph.hpp", "embedder.hpp", "bindings.cpp")] + [
+_SRCS = [os.path.join(_HERE, f) for f in ("graph.cpp", "embedder.cpp", "hierarchy.cpp", "wembed.cpp")]
+_DEPS = _SRCS + [os.path.join(_HERE, f) for f in ("graph.hpp", "embedder.hpp", "hierarchy.hpp", "bindings.cpp")] + [
     os.path.join(_ROOT, "include", "wembed.h"), os.path.join(_ROOT, "include", "wembed_b200.h")]
 CXX = "/usr/bin/g++"
 

@@ -5,7 +5,10 @@
 namespace wembed {
 namespace impl {
 
-EmbeddingGraph::EmbeddingGraph(const std::vector<std::pair<int, int>>& edges) {
+EmbeddingGraph::EmbeddingGraph(const std::vector<std::pair<int, int>>& edges) { build(0, edges); }
+EmbeddingGraph::EmbeddingGraph(int numVertices, const std::vector<std::pair<int, int>>& edges) { build(numVertices, edges); }
+
+void EmbeddingGraph::build(int numVertices, const std::vector<std::pair<int, int>>& edges) {
     // symmetrise + dedupe + order rows by sorting 64-bit (src, dst) keys; all self loops are dropped
     // (the reference skips only the first one it meets and then overruns its edge array, Graph.cpp:124-128)
     std::vector<std::uint64_t> keys;
@@ -19,7 +22,7 @@ EmbeddingGraph::EmbeddingGraph(const std::vector<std::pair<int, int>>& edges) {
     }
     std::sort(keys.begin(), keys.end());
     keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
-    const int n = maxId + 1;   // Graph.cpp:101: number of nodes = largest id + 1
+    const int n = std::max(numVertices, maxId + 1);   // Graph.cpp:101: number of nodes = largest id + 1
     rowPtr_.assign(static_cast<std::size_t>(n) + 1, 0);
     col_.resize(keys.size());
     for (std::size_t i = 0; i < keys.size(); ++i) {

@@ -14,6 +14,7 @@ class EmbeddingGraph {
    public:
     EmbeddingGraph() : rowPtr_(1, 0) {}
     explicit EmbeddingGraph(const std::vector<std::pair<int, int>>& edges);   // Graph::constructFromEdges (Graph.cpp:139-150)
+    EmbeddingGraph(int numVertices, const std::vector<std::pair<int, int>>& edges);   // Graph(map): vertices without edges kept (Graph.cpp:87-137)
 
     int32_t getNumVertices() const { return static_cast<int32_t>(rowPtr_.size()) - 1; }
     int32_t getNumEdges() const { return static_cast<int32_t>(col_.size() / 2); }
@@ -28,6 +29,7 @@ class EmbeddingGraph {
     const std::vector<int32_t>& col() const { return col_; }
 
    private:
+    void build(int numVertices, const std::vector<std::pair<int, int>>& edges);
     std::vector<int32_t> rowPtr_, col_;
 };
 

@@ -10,6 +10,7 @@
 
 #include "embedder.hpp"
 #include "graph.hpp"
+#include "hierarchy.hpp"
 #include "wembed.h"
 
 namespace wembed {
@@ -103,10 +104,8 @@ void Embedder::writeCoordinates(const std::string& filePath, bool writeWeights) 
 
 // ---- free functions ------------------------------------------------------------------------------------------------
 Embedder createEmbedder(const Graph& g, const Options& options) {
-    if (options.layeredEmbedding)
-        // The multilevel driver (LayeredEmbedder + LabelPropagation, wembed.cpp:229-233 of the reference) is a caller of
-        // the step, outside the device hot path ("next #1"); the single-level embedder is used.
-        std::cout << "[WARNING] layeredEmbedding is not implemented by the B200 build; running the single-level embedder" << std::endl;
+    if (options.layeredEmbedding)   // multilevel driver: coarsen with label propagation, embed layer by layer (wembed.cpp:229-233)
+        return Embedder(std::make_unique<impl::LayeredDeviceEmbedder>(*g._graph, options));
     return Embedder(std::make_unique<impl::DeviceEmbedder>(*g._graph, options));
 }
 
