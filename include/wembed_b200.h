@@ -159,7 +159,8 @@ int wb_query_candidates(wb_embedder* h, int32_t nq, const int32_t* queries, int6
                         int32_t* out_ids, int64_t cap);
 
 /* Device time (ms, CUDA events) of each phase of the most recent wb_step:
- * [0] index  [1] attract  [2] repel  [3] optimizer  [4] recentre+observe  [5] total.
+ * [0] index  [1] attract + optimizer (fused)  [2] repel (kernel + row all-gather)  [3] row all-gather of a sharded run
+ * [4] recentre+observe  [5] total.
  * Mirrors the util::Timer keys of WembedEmbedder.cpp:28-58. Requires wb_enable_timing(h,1). */
 int wb_enable_timing(wb_embedder* h, int enable);
 int wb_get_phase_times(wb_embedder* h, double* ms6);

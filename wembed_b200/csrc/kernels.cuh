@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256) k_morton_keys(const float4* __restrict__ 
 template <int V>
 __global__ void __launch_bounds__(256) k_build_leaves(const float4* __restrict__ x, const float* __restrict__ pointBound,
                                                       const int* __restrict__ order, int n, float4* __restrict__ pts,
-                                                      int stride0, float* __restrict__ bound0, int* __restrict__ ids,
+                                                      int stride0, float* __restrict__ bound0, int* __restrict__ ids, int* __restrict__ invOrder,
                                                       float4* __restrict__ lo1, float4* __restrict__ hi1,
                                                       float* __restrict__ bound1, int stride1) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;   // sorted position
@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(256) k_build_leaves(const float4* __restrict__
         }
         bound0[i] = b;
         ids[i] = src;
+        invOrder[src] = i;
     } else {
 #pragma unroll
         for (int c = 0; c < V; ++c) { lo[c] = make_float4(3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f); hi[c] = make_float4(-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f); }
@@ -307,18 +308,38 @@ __device__ __forceinline__ bool is_neighbor(const int* __restrict__ col, int beg
 // left, so warps whose queries need long walks do not hold finished warps of the same block hostage (measured: 28 %
 // of all stall samples sat on the final block barrier before).  Which warp handles which chunk does not influence
 // any result: a query's force depends only on its own walk, and the two statistics counters are integers.
+// Layout of the repulsion results.  One row of 4V + 2 doubles per SORTED position p: [force (4V) | loss | coincident partners].
+// The sorted order is cut into blocks of kRepBlockChunks chunks (a chunk = 32 consecutive positions = one warp's queries) and the
+// blocks are dealt round-robin to the ranks of a sharded run: whole blocks, because warps that run at the same time should work
+// on neighbouring chunks (they share tree nodes in L1 / L2; dealing single chunks cost 1.6x in walk time), round-robin because
+// the walk cost varies across space.  The rows a rank produces are contiguous, so one in-place all-gather publishes them:
+// row(p) = owner * segRows + local row.  With world = 1 this is the identity.
+constexpr int kRepBlockChunks = 32;
+struct RepLayout {
+    int world, rank, segRows;
+    __host__ __device__ __forceinline__ int64_t row(int p) const {
+        const int c = p >> 5, blk = c / kRepBlockChunks;
+        return (int64_t)(blk % world) * segRows + ((int64_t)(blk / world) * kRepBlockChunks + c % kRepBlockChunks) * 32 + (p & 31);
+    }
+    // l-th row this rank produces (l < segRows) -> sorted position
+    __host__ __device__ __forceinline__ int position(int l) const {
+        constexpr int blockRows = kRepBlockChunks * 32;
+        return ((l / blockRows) * world + rank) * blockRows + l % blockRows;
+    }
+};
+
 // warps per block of k_repulse_pairs: the per-warp shared memory (queries + stack) grows with V
 __host__ __device__ constexpr int repulse_warps(int V) { return V <= 4 ? 8 : 4; }
 
 template <int V>
 __global__ void __launch_bounds__(256, (V <= 2 ? 4 : (V <= 4 ? 2 : 1)))
 k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __restrict__ col, int n, const ForceParams fp,
-                double* __restrict__ forceRep, float* __restrict__ lossRep, int* __restrict__ coincident, int* __restrict__ chunkCounter,
-                const int* __restrict__ queryList, int numQueries, double* __restrict__ partials) {
+                double* __restrict__ forceRep, const RepLayout lay, int queriesPerUnit, int* __restrict__ chunkCounter,
+                double* __restrict__ partials) {
+    constexpr int RS = 4 * V + 2;                // doubles per result row
     constexpr int WARPS = repulse_warps(V), STACK = 56 * kMaxLevels + 72;   // LIFO bound: <= 56 leftovers per level + one push of 64
     __shared__ float4 sQ[WARPS][32][V];
     __shared__ float sIw[WARPS][32];
-    __shared__ int sPos[WARPS][32];              // sorted position of each query (differs from chunk * 32 + lane when sharded)
     __shared__ int sVert[WARPS][32];             // vertex id of each query
     __shared__ uint32_t sStack[WARPS][STACK];    // (level << 28) | (query lane << 23) | node   (node < 2^23: n <= 6.7e7)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = lane & (kFan - 1), g = lane >> kFanLog2;
@@ -331,15 +352,14 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
     }
     float4* myQ = &sQ[warp][0][0];
     float* myIw = &sIw[warp][0];
-    int* myPos = &sPos[warp][0];
     int* myVert = &sVert[warp][0];
     uint32_t* myStack = &sStack[warp][0];
     const float L = fp.edgeLength;
     const uint32_t ltMask = (1u << lane) - 1u;
-    // queryList == nullptr: the queries are all sorted positions 0..n-1; otherwise (vertex-sharded multi-GPU step) the
-    // sorted positions of the vertices this rank owns, in sorted order
-    const int numChunks = (numQueries + 31) >> 5;
-    int nPairs = 0, nTests = 0, nBoxTests = 0;
+    // Work unit of a warp = queriesPerUnit (8, 16 or 32) consecutive rows of this rank's share of the sorted order.  Small units
+    // keep the dynamic schedule balanced when a rank (or a small graph) has few queries per resident warp.
+    const int numChunks = lay.segRows / queriesPerUnit;
+    int nPairs = 0, nTests = 0, nBoxTests = 0, qBase = 0;
 
     // One (node, query) pair of the round: lane c tests child c.  Returns pass; lv / idx / qq / d2 / s describe the test.
     struct Slot { int lv, idx, qq; float d2, s; bool active, pass; };
@@ -369,7 +389,7 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
     // and accumulates into its row of forceRep (read-modify-write in global memory: hits are rare - a handful per query -
     // and keeping the accumulators out of registers buys occupancy for the walk).
     auto resolveHits = [&](const Slot& r) {
-        bool hit = r.pass && r.lv == 0 && (r.idx != myPos[r.qq]);
+        bool hit = r.pass && r.lv == 0 && (r.idx != qBase + r.qq);
         if (hit) {
             const float dist = sqrtf(r.d2);
             if (dist > 0.f) hit = dist * r.s <= L;           // exact predicate; dist <= 0 is the coincident case
@@ -389,13 +409,13 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
                 const int v = myVert[lane];
                 const float dist = sqrtf(box_dist2<V>(q, pu, pu));
                 const float ws = myIw[lane] * iwu;
+                double* fr = forceRep + lay.row(qBase + lane) * RS;
                 if (dist <= 0.f) {
-                    if (!is_neighbor(col, __ldg(rowPtr + v), __ldg(rowPtr + v + 1), u)) coincident[v] += 1;
+                    if (!is_neighbor(col, __ldg(rowPtr + v), __ldg(rowPtr + v + 1), u)) fr[4 * V + 1] += 1.0;
                 } else if (dist * ws <= L) {
                     if (!is_neighbor(col, __ldg(rowPtr + v), __ldg(rowPtr + v + 1), u)) {
                         // summed in double: a vertex can own hundreds of repulsive terms in a collapsed layout and the optimizer
                         // normalises every component, so a cancellation residue must keep the accuracy of its terms
-                        double* fr = forceRep + (int64_t)v * 4 * V;
                         const float sc = fp.repulsionScale * ws / dist;
                         if (fp.dim == 1) fr[0] += (double)copysignf(fp.repulsionScale * ws, q[0].x - pu[0].x);   // unit vector exactly +-1
                         else
@@ -406,7 +426,7 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
                             fr[4 * k + 2] += (double)(sc * (q[k].z - pu[k].z));
                             fr[4 * k + 3] += (double)(sc * (q[k].w - pu[k].w));
                         }
-                        lossRep[v] += L / ws - dist;
+                        fr[4 * V] += (double)(L / ws - dist);
                         ++nPairs;
                     }
                 }
@@ -419,22 +439,19 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
         if (lane == 0) chunk = atomicAdd(chunkCounter, 1);
         chunk = __shfl_sync(0xffffffffu, chunk, 0);
         if (chunk >= numChunks) break;
-        const int slot = chunk * 32 + lane;
-        const bool valid = slot < numQueries;
-        const int qi = valid ? (queryList ? __ldg(queryList + slot) : slot) : -1;
+        qBase = lay.position(chunk * queriesPerUnit);         // sorted position of lane 0's query (a unit never straddles a block)
+        if (qBase >= n) continue;                             // padding of the last block
+        const int qi = qBase + lane;
+        const bool valid = lane < queriesPerUnit && qi < n;
         if (valid) {
 #pragma unroll
             for (int k = 0; k < V; ++k) myQ[lane * V + k] = __ldg(t.lo[0] + (int64_t)k * t.stride[0] + qi);
             myIw[lane] = __ldg(t.bound[0] + qi);
-            const int v = __ldg(t.ids + qi);
-            myVert[lane] = v;
-            double* fr = forceRep + (int64_t)v * 4 * V;
+            myVert[lane] = __ldg(t.ids + qi);
+            double* fr = forceRep + lay.row(qi) * RS;
 #pragma unroll
-            for (int k = 0; k < 4 * V; ++k) fr[k] = 0.0;
-            lossRep[v] = 0.f;
-            coincident[v] = 0;
+            for (int k = 0; k < RS; ++k) fr[k] = 0.0;
         }
-        myPos[lane] = qi;
         const uint32_t validMask = __ballot_sync(0xffffffffu, valid);
         if (valid) myStack[__popc(validMask & ltMask)] = ((uint32_t)(t.numLevels + 1) << 28) | ((uint32_t)lane << 23);
         int sp = __popc(validMask);
@@ -567,12 +584,12 @@ template <int V>
 __global__ void __launch_bounds__(256, 4) k_attract_update(const float4* __restrict__ x, const float* __restrict__ edgeWs,
                                                         const int* __restrict__ rowPtr, const int* __restrict__ col, int rangeBegin,
                                                         int rangeEnd, int vertsPerBlock, const ForceParams fp,
-                                                        const double* __restrict__ forceRep, const float* __restrict__ lossRep,
-                                                        const int* __restrict__ coincidentRep, const int* __restrict__ hubSlot,
+                                                        const double* __restrict__ forceRep, const RepLayout lay,
+                                                        const int* __restrict__ invOrder, const int* __restrict__ hubSlot,
                                                         const double* __restrict__ hubForce, float4* __restrict__ xNew,
                                                         float4* __restrict__ mom1, float4* __restrict__ mom2,
                                                         float4* __restrict__ forceOut, double* __restrict__ partials) {
-    constexpr int G = attract_lanes(V), VPW = 32 / G, VPB = 8 * VPW, K = 2 + 4 * V;
+    constexpr int G = attract_lanes(V), VPW = 32 / G, VPB = 8 * VPW, K = 2 + 4 * V, RS = 4 * V + 2;
     __shared__ uint32_t mtState[8][624];
     __shared__ double unitBuf[8][VPW][4 * V];
     __shared__ double redBuf[8][K];
@@ -593,7 +610,9 @@ __global__ void __launch_bounds__(256, 4) k_attract_update(const float4* __restr
         double loss = 0.0;
         int nCoincident = 0;
         int e = 0, end = 0, hub = -1;
+        const double* rep = forceRep;                              // this vertex' row of repulsion results
         if (valid) {
+            rep = forceRep + lay.row(__ldg(invOrder + v)) * RS;
             if (chunkLane) xv = __ldg(x + at);
             hub = hubSlot ? __ldg(hubSlot + v) : -1;
             if (hub < 0) { e = __ldg(rowPtr + v); end = __ldg(rowPtr + v + 1); }
@@ -653,7 +672,7 @@ __global__ void __launch_bounds__(256, 4) k_attract_update(const float4* __restr
             loss = hf[4 * V];
             nCoincident = (int)hf[4 * V + 1];
         }
-        if (valid) nCoincident += __ldg(coincidentRep + v);
+        if (valid) nCoincident += (int)rep[4 * V + 1];
 
         // coincident partners: every one of them adds the same unit vector (generator re-created per pair, :150-155, :183-188).
         // The generator state (624 words) lives in per-warp shared memory; the rare vertices that need it take turns.
@@ -676,10 +695,10 @@ __global__ void __launch_bounds__(256, 4) k_attract_update(const float4* __restr
 
         if (valid && c == 0) {
             sumLossA += loss;
-            sumLossR += (double)__ldg(lossRep + v);
+            sumLossR += rep[4 * V];
         }
         if (valid && chunkLane) {
-            const double* fr = forceRep + at * 4;
+            const double* fr = rep + 4 * c;
             float4 f = make_float4((float)(acc[0] + fr[0]), (float)(acc[1] + fr[1]), (float)(acc[2] + fr[2]), (float)(acc[3] + fr[3]));
             if (fp.centreScale != 0.f) {                   // :296-301
                 f.x = fmaf(-fp.centreScale, xv.x, f.x); f.y = fmaf(-fp.centreScale, xv.y, f.y);
@@ -793,15 +812,6 @@ __global__ void k_sum_ranks(const double* __restrict__ gathered, int world, int 
     for (int r = 0; r < world; ++r) s += gathered[r * cols + k];
     out[k] = s;
 }
-
-struct OwnedPosition {        // predicate of the owned-query compaction: sorted position -> is its vertex in [lo, hi)?
-    const int* ids;
-    int lo, hi;
-    __device__ __forceinline__ bool operator()(int pos) const {
-        const int v = ids[pos];
-        return v >= lo && v < hi;
-    }
-};
 
 // ---------------------------------------------------------------------------------------------
 // Boundary conversions (coordinates cross the C ABI as row-major n x d doubles).

@@ -4,8 +4,6 @@
 // kernel launches on that stream (see enqueue_step); the only host<->device traffic per step is one
 // small D2H copy of the reduced sums.  There is no CPU fallback anywhere in this file.
 #include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_select.cuh>
-#include <cub/iterator/counting_input_iterator.cuh>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -86,10 +84,11 @@ struct wb_embedder {
 
     // layout state
     float4 *x = nullptr, *xNew = nullptr, *mom1 = nullptr, *mom2 = nullptr, *force = nullptr;
-    double* forceRep = nullptr;           // repulsive partial force, n x 4V doubles
-    float *iw = nullptr, *lossRep = nullptr;
+    double* forceRep = nullptr;           // repulsion results, one row of 4V + 2 doubles per sorted position (wb::RepLayout)
+    wb::RepLayout repLayout{1, 0, 0};
+    int* invOrder = nullptr;              // vertex -> sorted position
+    float* iw = nullptr;
     float* edgeWs = nullptr;              // ws(v,u) = iw_v * iw_u of every CSR entry
-    int* coincident = nullptr;
     int* chunkCounter = nullptr;          // work counter of the persistent repulsion kernel
     int numHubs = 0;                      // rows longer than kHubThreshold, pre-summed by k_attract_hubs
     int *hubVertex = nullptr, *hubSlot = nullptr;
@@ -126,10 +125,6 @@ struct wb_embedder {
     // re-assembled by an all-gather of the owners' rows at the end of every step
     ncclComm_t comm = nullptr;
     int world = 1, rank = 0, ownBegin = 0, ownEnd = 0, rowsPerRank = 0;
-    int* ownedList = nullptr;             // sorted positions of the owned vertices, rebuilt every step
-    int* ownedCount = nullptr;
-    void* selectTemp = nullptr;
-    size_t selectBytes = 0;
     double* gathered = nullptr;           // world x sumsTotal doubles
     double* localSums = nullptr;          // this rank's share of sumsAll
 
@@ -167,10 +162,10 @@ inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 void free_all(wb_embedder* h) {
     auto F = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
     F(h->rowPtr); F(h->col); F(h->x); F(h->xNew); F(h->mom1); F(h->mom2); F(h->forceRep); F(h->force);
-    F(h->iw); F(h->lossRep); F(h->edgeWs); F(h->coincident); F(h->chunkCounter); F(h->hubVertex); F(h->hubSlot); F(h->hubForce); F(h->band); F(h->keysIn); F(h->keysOut); F(h->valsIn); F(h->valsOut);
+    F(h->iw); F(h->invOrder); F(h->edgeWs); F(h->chunkCounter); F(h->hubVertex); F(h->hubSlot); F(h->hubForce); F(h->band); F(h->keysIn); F(h->keysOut); F(h->valsIn); F(h->valsOut);
     F(h->cubTemp); F(h->momentPartials); F(h->quant); F(h->ids);
     for (int l = 0; l < wb::kMaxLevels; ++l) { F(h->lvlLo[l]); if (l > 0) F(h->lvlHi[l]); F(h->lvlBound[l]); }
-    F(h->partialsForce); F(h->partialsRep); F(h->partialsObs); F(h->sumsAll); F(h->ownedList); F(h->ownedCount); F(h->selectTemp); F(h->gathered); F(h->localSums);
+    F(h->partialsForce); F(h->partialsRep); F(h->partialsObs); F(h->sumsAll); F(h->gathered); F(h->localSums);
     if (h->comm) { nccl().commDestroy(h->comm); h->comm = nullptr; }
     for (auto& p : h->pending) { cudaEventDestroy(p.done); cudaFreeHost(p.hostSums); }
     for (auto& p : h->freeSlots) { cudaEventDestroy(p.done); cudaFreeHost(p.hostSums); }
@@ -206,18 +201,17 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
         }
     }
     const size_t rows = (size_t)n * V;
-    h->forceRep = dalloc<double>(std::max<size_t>(rows, 1) * 4);
-    WB_CUDA(cudaMemsetAsync(h->forceRep, 0, std::max<size_t>(rows, 1) * 4 * sizeof(double), h->stream));
+    h->repLayout = wb::RepLayout{1, 0, div_up(std::max(n, 1), 32) * 32};
+    h->forceRep = dalloc<double>((size_t)h->repLayout.segRows * (4 * V + 2));
+    WB_CUDA(cudaMemsetAsync(h->forceRep, 0, (size_t)h->repLayout.segRows * (4 * V + 2) * sizeof(double), h->stream));
+    h->invOrder = dalloc<int>(n);
+    WB_CUDA(cudaMemsetAsync(h->invOrder, 0, std::max(n, 1) * sizeof(int), h->stream));
     for (float4** p : {&h->x, &h->xNew, &h->mom1, &h->mom2, &h->force}) {
         *p = dalloc<float4>(rows);
         WB_CUDA(cudaMemsetAsync(*p, 0, std::max<size_t>(rows, 1) * sizeof(float4), h->stream));
     }
     h->iw = dalloc<float>(n);
     h->edgeWs = dalloc<float>(h->numDirected);
-    h->lossRep = dalloc<float>(n);
-    h->coincident = dalloc<int>(n);
-    WB_CUDA(cudaMemsetAsync(h->lossRep, 0, std::max(n, 1) * sizeof(float), h->stream));
-    WB_CUDA(cudaMemsetAsync(h->coincident, 0, std::max(n, 1) * sizeof(int), h->stream));
     if (n) wb::k_fill<float><<<div_up(n, 256), 256, 0, h->stream>>>(h->iw, n, 1.0f);
     if (h->numDirected) wb::k_fill<float><<<div_up(h->numDirected, 256), 256, 0, h->stream>>>(h->edgeWs, h->numDirected, 1.0f);
     h->weights.assign(n, 1.0);
@@ -275,7 +269,7 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
     {   // persistent repulsion grid: enough resident blocks to fill every SM, never more than there are chunks
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->opt.device);
-        h->repBlocks = std::max(1, std::min(div_up(div_up(n, 32), 8), sms * 4));
+        h->repBlocks = std::max(1, std::min(div_up(div_up(n, 8), 8), sms * 4));
     }
     h->chunkCounter = dalloc<int>(1);
     h->obsBlocks = std::max(1, std::min(div_up(n, 256), 148 * 8));
@@ -315,7 +309,7 @@ void enqueue_index(wb_embedder* h, const float* pointBound) {
     }
     const wb::TreeView& t = h->tree;
     WB_DISPATCH_V(V, wb::k_build_leaves<V><<<div_up(t.stride[0], 256), 256, 0, s>>>(
-                         h->x, pointBound, h->valsOut, n, h->lvlLo[0], t.stride[0], h->lvlBound[0], h->ids, h->lvlLo[1], h->lvlHi[1],
+                         h->x, pointBound, h->valsOut, n, h->lvlLo[0], t.stride[0], h->lvlBound[0], h->ids, h->invOrder, h->lvlLo[1], h->lvlHi[1],
                          h->lvlBound[1], t.stride[1]));
     for (int l = 2; l <= t.numLevels; ++l) {
         WB_DISPATCH_V(V, wb::k_build_level<V><<<div_up((int64_t)t.count[l] * kFan, 256), 256, 0, s>>>(
@@ -372,22 +366,23 @@ void enqueue_step(wb_embedder* h, double learningRate) {
 
     const bool sharded = h->world > 1;
     double* sums = sharded ? h->localSums : h->sumsAll;      // a sharded step reduces locally first, then across ranks
-    const int ownCount = std::max(0, h->ownEnd - h->ownBegin);
 
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[0], s));
     enqueue_index(h, h->iw);
-    const int* queryList = nullptr;
-    if (sharded) {   // the queries of this rank: sorted positions whose vertex it owns, in sorted order
-        wb::OwnedPosition pred{h->ids, h->ownBegin, h->ownEnd};
-        WB_CUDA(cub::DeviceSelect::If(h->selectTemp, h->selectBytes, cub::CountingInputIterator<int>(0), h->ownedList, h->ownedCount, n, pred, s));
-        queryList = h->ownedList;
+    if (h->timing) WB_CUDA(cudaEventRecord(h->ev[1], s));
+    // at least ~8 work units per resident warp, else the tail of the dynamic schedule dominates
+    const int64_t residentWarps = (int64_t)h->repBlocks * wb::repulse_warps(V);
+    const int queriesPerUnit = h->repLayout.segRows / 32 >= 8 * residentWarps ? 32 : (h->repLayout.segRows / 16 >= 8 * residentWarps ? 16 : 8);
+    WB_CUDA(cudaMemsetAsync(h->chunkCounter, 0, sizeof(int), s));
+    WB_DISPATCH_V(V, wb::k_repulse_pairs<V><<<h->repBlocks, 32 * wb::repulse_warps(V), 0, s>>>(h->tree, h->rowPtr, h->col, n, fp, h->forceRep,
+                                                                                                  h->repLayout, queriesPerUnit, h->chunkCounter, h->partialsRep));
+    if (h->timing) WB_CUDA(cudaEventRecord(h->ev[5], s));
+    if (sharded) {   // publish the rows this rank produced (its blocks of the sorted order)
+        const size_t segDoubles = (size_t)h->repLayout.segRows * (4 * V + 2);
+        if (nccl().allGather(h->forceRep + (size_t)h->rank * segDoubles, h->forceRep, segDoubles, ncclDouble, h->comm, s) != ncclSuccess)
+            throw std::runtime_error("ncclAllGather (repulsion rows) failed");
         h->launches += 1;
     }
-    if (h->timing) WB_CUDA(cudaEventRecord(h->ev[1], s));
-    WB_CUDA(cudaMemsetAsync(h->chunkCounter, 0, sizeof(int), s));
-    WB_DISPATCH_V(V, wb::k_repulse_pairs<V><<<h->repBlocks, 32 * wb::repulse_warps(V), 0, s>>>(h->tree, h->rowPtr, h->col, n, fp, h->forceRep, h->lossRep,
-                                                                          h->coincident, h->chunkCounter, queryList, sharded ? ownCount : n,
-                                                                          h->partialsRep));
     wb::k_reduce_partials<<<3, 256, 0, s>>>(h->partialsRep, h->repBlocks * wb::repulse_warps(V), 3, sums + K);
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[2], s));
     if (h->numHubs) {
@@ -395,8 +390,8 @@ void enqueue_step(wb_embedder* h, double learningRate) {
         h->launches += 1;
     }
     WB_DISPATCH_V(V, wb::k_attract_update<V><<<h->forceBlocks, 256, 0, s>>>(
-                         h->x, h->edgeWs, h->rowPtr, h->col, h->ownBegin, h->ownEnd, h->forceVertsPerBlock, fp, h->forceRep, h->lossRep,
-                         h->coincident, h->hubSlot, h->hubForce, h->xNew, h->mom1, h->mom2, h->force, h->partialsForce));
+                         h->x, h->edgeWs, h->rowPtr, h->col, h->ownBegin, h->ownEnd, h->forceVertsPerBlock, fp, h->forceRep, h->repLayout,
+                         h->invOrder, h->hubSlot, h->hubForce, h->xNew, h->mom1, h->mom2, h->force, h->partialsForce));
     wb::k_reduce_partials<<<K, 256, 0, s>>>(h->partialsForce, h->forceBlocks, K, sums);
     if (sharded) {   // {lossA, lossR, sum xnew[k], pairs, tests}: all-gather, then every rank adds in rank order
         if (nccl().allGather(sums, h->gathered, K + 3, ncclDouble, h->comm, s) != ncclSuccess) throw std::runtime_error("ncclAllGather (force sums) failed");
@@ -451,7 +446,7 @@ void collect_step(wb_embedder* h, wb_step_stats* out) {
             WB_CUDA(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1])); h->phaseMs[0] = ms;
             WB_CUDA(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3])); h->phaseMs[1] = ms;
             WB_CUDA(cudaEventElapsedTime(&ms, h->ev[1], h->ev[2])); h->phaseMs[2] = ms;
-            h->phaseMs[3] = 0.0;  // the optimizer is fused into the attraction kernel
+            WB_CUDA(cudaEventElapsedTime(&ms, h->ev[5], h->ev[2])); h->phaseMs[3] = ms;   // slot 3: all-gather of the repulsion rows (0 on one GPU); the optimizer itself is fused into slot 1
             WB_CUDA(cudaEventElapsedTime(&ms, h->ev[3], h->ev[4])); h->phaseMs[4] = ms;
             WB_CUDA(cudaEventElapsedTime(&ms, h->ev[0], h->ev[4])); h->phaseMs[5] = ms;
             h->havePhase = true;
@@ -736,12 +731,12 @@ int wb_comm_init(wb_embedder* h, const char* id128, int32_t rank, int32_t world)
         h->obsBlocks = std::max(1, std::min(div_up(own, 256), 148 * 8));
         h->obsVertsPerBlock = std::max(256, div_up(div_up(own, h->obsBlocks), 256) * 256);
         h->obsBlocks = std::max(1, div_up(own, h->obsVertsPerBlock));
-        h->ownedList = dalloc<int>(n);
-        h->ownedCount = dalloc<int>(1);
-        h->selectBytes = 0;
-        wb::OwnedPosition pred{h->ids, h->ownBegin, h->ownEnd};
-        WB_CUDA(cub::DeviceSelect::If(nullptr, h->selectBytes, cub::CountingInputIterator<int>(0), h->ownedList, h->ownedCount, std::max(n, 1), pred, h->stream));
-        h->selectTemp = dalloc<char>(h->selectBytes);
+        // repulsion rows: blocks of kRepBlockChunks chunks of the sorted order dealt round-robin to the ranks, each rank's rows contiguous
+        const int blocksPerRank = div_up(div_up(div_up(std::max(n, 1), 32), wb::kRepBlockChunks), world);
+        h->repLayout = wb::RepLayout{world, rank, blocksPerRank * wb::kRepBlockChunks * 32};
+        cudaFree(h->forceRep);
+        h->forceRep = dalloc<double>((size_t)h->repLayout.segRows * world * (4 * V + 2));
+        WB_CUDA(cudaMemsetAsync(h->forceRep, 0, (size_t)h->repLayout.segRows * world * (4 * V + 2) * sizeof(double), h->stream));
         h->gathered = dalloc<double>((size_t)world * h->sumsTotal);
         h->localSums = dalloc<double>(h->sumsTotal);
         WB_CUDA(cudaMemsetAsync(h->localSums, 0, sizeof(double) * h->sumsTotal, h->stream));
