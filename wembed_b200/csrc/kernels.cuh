@@ -93,14 +93,23 @@ __global__ void __launch_bounds__(256) k_moments(const float4* __restrict__ x, i
 
 // Index, stage 2: quantisation frame = [mean - 4 sd, mean + 4 sd] clipped to [min, max] per dimension, so a few
 // far outliers do not eat the key resolution of the bulk.  Only locality depends on this frame, never results.
-__global__ void k_quant_params(const float* __restrict__ partial, int numBlocks, int n, int dim, int bits, QuantParams* __restrict__ qp) {
-    const int k = threadIdx.x;
-    if (k >= dim) return;
+__global__ void __launch_bounds__(256) k_quant_params(const float* __restrict__ partial, int numBlocks, int n, int dim, int bits,
+                                                      QuantParams* __restrict__ qp) {
+    // thread (k, j) = (dimension, slice): slice j folds blocks j, j+8, .. in order; the 8 slices are combined in slice order
+    __shared__ float sMin[8][kMaxDim], sMax[8][kMaxDim];
+    __shared__ double sS1[8][kMaxDim], sS2[8][kMaxDim];
+    const int k = threadIdx.x & 31, j = threadIdx.x >> 5;
     float mn = 3.0e38f, mx = -3.0e38f; double s1 = 0.0, s2 = 0.0;
-    for (int b = 0; b < numBlocks; ++b) {
-        const float* p = partial + (int64_t)b * 4 * kMaxDim;
-        mn = fminf(mn, p[k]); mx = fmaxf(mx, p[kMaxDim + k]); s1 += p[2 * kMaxDim + k]; s2 += p[3 * kMaxDim + k];
+    if (k < dim) {
+        for (int b = j; b < numBlocks; b += 8) {
+            const float* p = partial + (int64_t)b * 4 * kMaxDim;
+            mn = fminf(mn, p[k]); mx = fmaxf(mx, p[kMaxDim + k]); s1 += p[2 * kMaxDim + k]; s2 += p[3 * kMaxDim + k];
+        }
     }
+    sMin[j][k] = mn; sMax[j][k] = mx; sS1[j][k] = s1; sS2[j][k] = s2;
+    __syncthreads();
+    if (j != 0 || k >= dim) return;
+    for (int t = 1; t < 8; ++t) { mn = fminf(mn, sMin[t][k]); mx = fmaxf(mx, sMax[t][k]); s1 += sS1[t][k]; s2 += sS2[t][k]; }
     const double mean = s1 / n;
     const double var = fmax(0.0, s2 / n - mean * mean);
     const float sd = (float)sqrt(var);

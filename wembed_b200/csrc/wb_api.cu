@@ -294,7 +294,7 @@ void enqueue_index(wb_embedder* h, const float* pointBound) {
     const int n = h->n, V = h->V;
     cudaStream_t s = h->stream;
     WB_DISPATCH_V(V, wb::k_moments<V><<<h->momentBlocks, 256, 0, s>>>(h->x, n, h->momentPartials));
-    wb::k_quant_params<<<1, 32, 0, s>>>(h->momentPartials, h->momentBlocks, n, h->dim, h->mortonBits, h->quant);
+    wb::k_quant_params<<<1, 256, 0, s>>>(h->momentPartials, h->momentBlocks, n, h->dim, h->mortonBits, h->quant);
     const int sortBits = h->mortonBits * h->dim + h->bandBits;
     if (h->keyBits == 64) {
         WB_DISPATCH_V(V, wb::k_morton_keys<V, uint64_t><<<div_up(n, 256), 256, 0, s>>>(h->x, n, h->dim, h->mortonBits, h->quant, h->band,
