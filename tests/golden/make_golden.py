@@ -121,6 +121,30 @@ def main():
             q = reconstruction_metrics(x, w, rp, col, np.arange(0, n, 6))
             out["geo3000_layered"] = np.array([iters, st[0] + st[1], q[0], q[1]])
     np.savez_compressed(os.path.join(HERE, "hierarchy.npz"), **out)
+    # (f) host scalar logic: the reference's own learning rates, loss rates and stop iterations on ring-64 (tests/TestDeterminism.cpp
+    #     option sets) together with the loss / displacement sequences that produced them
+    sched = {}
+    cases = {
+        "loss_stop": dict(maxIterations=2000, stopCriterion=1, lossRateWindow=10, stopLossTol=1e-2, stopLossPatience=10),
+        "disp_stop": dict(maxIterations=5000, stopCriterion=0, stopDisplacementTol=1e-3, stopDisplacementPatience=5),
+        "adaptive": dict(maxIterations=400, lrScheduleType=1, lossRateWindow=10, lrDecayThreshold=1e-2, lrDecayFactor=0.5,
+                         lrGrowthThreshold=1e-1, lrGrowthFactor=1.0, lrAdaptPatience=5),
+        "default": dict(maxIterations=300),
+    }
+    for name, o in cases.items():
+        cpu = oracle.CpuEmbedder("ref", ring, seed=1234, embeddingDimension=2, **o)
+        rows = []
+        while not cpu.is_finished():
+            cpu.step()
+            s_ = cpu.stats()
+            rows.append([s_["loss_attract"] + s_["loss_repel"], s_["rel_displacement"], s_["lr"], s_["rel_loss_improvement"]])
+        op = cpu.opts
+        sched[name + "_trace"] = np.asarray(rows)
+        sched[name + "_opts"] = np.array([op.lrScheduleType, op.learningRate, op.warmupSteps, op.lrCoolingFactor, op.lrDecayFactor, op.lrDecayThreshold,
+                                          op.lrAdaptPatience, op.lrGrowthFactor, op.lrGrowthThreshold, op.stopCriterion, op.stopDisplacementTol,
+                                          op.stopDisplacementPatience, op.lossSmoothingFactor, op.lossRateWindow, op.stopLossTol, op.stopLossPatience,
+                                          op.maxIterations], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "host_logic.npz"), **sched)
     print("golden fixtures written to", HERE)
 
 

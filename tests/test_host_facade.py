@@ -166,3 +166,30 @@ def test_ring64_stop_criteria_through_public_api(wembed):
     assert rates[0] == pytest.approx(10.0 / 20.0) and max(rates) == 10.0      # warm-up ramp, then the initial rate
     assert min(rates[30:]) <= 5.0                                              # a plateau decay fired (TestDeterminism.cpp:131-147)
     assert all(b <= a for a, b in zip(rates[20:], rates[21:]))                 # growth is off: the rate never increases
+
+
+@pytest.mark.parametrize("case", ["loss_stop", "disp_stop", "adaptive", "default"])
+def test_host_scalar_logic_matches_reference(case):
+    """LRScheduler (both schedules + warm-up), ConvergenceMonitor, DisplacementMonitor and isFinished of the C++ facade, replayed
+    over the reference's own loss / displacement sequences (tests/TestDeterminism.cpp option sets on ring-64; golden from the
+    reference build): learning rates, loss rates and the stop iteration must be bit-identical - it is pure double arithmetic."""
+    import ctypes as C
+    from wembed_b200 import cabi, host
+    host.build()
+    cabi.lib()
+    C.CDLL(cabi.LIB_PATH, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(host.HOST_LIB)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "host_logic.npz"))
+    trace, opts = g[f"{case}_trace"], np.ascontiguousarray(g[f"{case}_opts"])
+    steps = len(trace)
+    loss, disp = np.ascontiguousarray(trace[:, 0]), np.ascontiguousarray(trace[:, 1])
+    lr, rate = np.zeros(steps), np.zeros(steps)
+    dp = C.POINTER(C.c_double)
+    lib.wbh_host_logic_trace.restype = C.c_int
+    stop = lib.wbh_host_logic_trace(opts.ctypes.data_as(dp), steps, loss.ctypes.data_as(dp), disp.ctypes.data_as(dp), lr.ctypes.data_as(dp),
+                                    rate.ctypes.data_as(dp))
+    np.testing.assert_array_equal(lr, trace[:, 2])
+    np.testing.assert_array_equal(rate, trace[:, 3])          # inf during the window warm-up, then the windowed relative decrease
+    assert stop == steps                                      # the reference stopped exactly after its last recorded step
+    if case == "adaptive":
+        assert lr.min() < 10.0 and (np.diff(lr[20:]) <= 0).all()

@@ -241,3 +241,33 @@ void DeviceEmbedder::setWeights(const std::vector<double>& weights) {
 
 }  // namespace impl
 }  // namespace wembed
+
+// Test hook (CPU only): the host scalar logic of one embedding run - learning-rate schedule, loss monitor, displacement monitor,
+// stop decision - replayed over a given sequence of per-step losses and relative displacements, exactly in the order
+// DeviceEmbedder::calculateStep uses them.  o = {lrSchedule, learningRate, warmupSteps, lrCoolingFactor, lrDecayFactor,
+// lrDecayThreshold, lrAdaptPatience, lrGrowthFactor, lrGrowthThreshold, stopCriterion, stopDisplacementTol,
+// stopDisplacementPatience, lossSmoothingFactor, lossRateWindow, stopLossTol, stopLossPatience, maxIterations}.
+// Returns the first iteration after which isFinished() holds (0 if never within `steps`).
+extern "C" int wbh_host_logic_trace(const double* o, int steps, const double* loss, const double* relDisp, double* outLr, double* outRate) {
+    using namespace wembed;
+    Options opt;
+    opt.lrSchedule = o[0] == 0.0 ? LRExponentialCooling : LRLossAdaptive;
+    opt.learningRate = o[1]; opt.warmupSteps = (int)o[2]; opt.lrCoolingFactor = o[3]; opt.lrDecayFactor = o[4];
+    opt.lrDecayThreshold = o[5]; opt.lrAdaptPatience = (int)o[6]; opt.lrGrowthFactor = o[7]; opt.lrGrowthThreshold = o[8];
+    opt.stopCriterion = o[9] == 0.0 ? StopDisplacement : StopLoss;
+    opt.stopDisplacementTol = o[10]; opt.stopDisplacementPatience = (int)o[11]; opt.lossSmoothingFactor = o[12];
+    opt.lossRateWindow = (int)o[13]; opt.stopLossTol = o[14]; opt.stopLossPatience = (int)o[15]; opt.maxIterations = (int)o[16];
+    impl::LossMonitor lossMon(opt.stopLossTol, opt.stopLossPatience, opt.lossSmoothingFactor, opt.lossRateWindow);
+    impl::MoveMonitor moveMon(opt.stopDisplacementTol, opt.stopDisplacementPatience);
+    impl::LearningRate schedule(opt);
+    int finishedAt = 0;
+    for (int it = 1; it <= steps; ++it) {
+        outLr[it - 1] = schedule.next(it, lossMon);
+        moveMon.observe(relDisp[it - 1]);
+        lossMon.observe(loss[it - 1]);
+        outRate[it - 1] = lossMon.rate();
+        const bool finished = it >= opt.maxIterations || (opt.stopCriterion == StopDisplacement ? moveMon.converged() : lossMon.converged());
+        if (finished && finishedAt == 0) finishedAt = it;
+    }
+    return finishedAt;
+}
