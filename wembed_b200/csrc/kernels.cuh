@@ -119,15 +119,14 @@ __global__ void __launch_bounds__(256) k_quant_params(const float* __restrict__ 
     qp->invCell[k] = (float)(1u << bits) / (hi - lo);
 }
 
-// Index, stage 3: Morton key of every vertex (bit b of dimension k -> key bit b*dim + k), weight band on top.
-template <int V, typename KeyT>
+// Index, stage 3: Morton key of every vertex (bit b of dimension k -> key bit b*dim + k).
+template <int V>
 __global__ void __launch_bounds__(256) k_morton_keys(const float4* __restrict__ x, int n, int dim, int bits,
-                                                     const QuantParams* __restrict__ qp, const uint8_t* __restrict__ band,
-                                                     KeyT* __restrict__ keys, int* __restrict__ vals) {
+                                                     const QuantParams* __restrict__ qp, uint32_t* __restrict__ keys, int* __restrict__ vals) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n) return;
     const uint32_t qmax = (1u << bits) - 1u;
-    KeyT key = 0;
+    uint32_t key = 0;
 #pragma unroll
     for (int c = 0; c < V; ++c) {
         const float4 p = __ldg(x + (int64_t)v * V + c);
@@ -138,13 +137,10 @@ __global__ void __launch_bounds__(256) k_morton_keys(const float4* __restrict__ 
             if (k < dim) {
                 const float t = (e[i] - qp->lo[k]) * qp->invCell[k];
                 const uint32_t q = t <= 0.f ? 0u : (t >= (float)qmax ? qmax : (uint32_t)t);
-                for (int b = 0; b < bits; ++b) key |= (KeyT)((q >> b) & 1u) << (b * dim + k);
+                for (int b = 0; b < bits; ++b) key |= ((q >> b) & 1u) << (b * dim + k);
             }
         }
     }
-    // weight band in the top bits (bits * dim .. ): points whose interaction radius differs by more than a factor of two
-    // live in separate subtrees, so one heavy vertex cannot inflate the pruning bound of a subtree of light ones
-    if (band) key |= (KeyT)band[v] << (bits * dim);
     keys[v] = key;
     vals[v] = v;
 }
@@ -343,8 +339,8 @@ __host__ __device__ constexpr int repulse_warps(int V) { return V <= 4 ? 8 : 4; 
 template <int V>
 __global__ void __launch_bounds__(256, (V <= 2 ? 4 : (V <= 4 ? 2 : 1)))
 k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __restrict__ col, int n, const ForceParams fp,
-                double* __restrict__ forceRep, const RepLayout lay, int queriesPerUnit, int* __restrict__ chunkCounter,
-                double* __restrict__ partials) {
+                double* __restrict__ forceRep, const RepLayout lay, int queriesPerUnit, const int* __restrict__ heavySlot,
+                int* __restrict__ chunkCounter, double* __restrict__ partials) {
     constexpr int RS = 4 * V + 2;                // doubles per result row
     constexpr int WARPS = repulse_warps(V), STACK = 56 * kMaxLevels + 72;   // LIFO bound: <= 56 leftovers per level + one push of 64
     __shared__ float4 sQ[WARPS][32][V];
@@ -451,7 +447,10 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
         qBase = lay.position(chunk * queriesPerUnit);         // sorted position of lane 0's query (a unit never straddles a block)
         if (qBase >= n) continue;                             // padding of the last block
         const int qi = qBase + lane;
-        const bool valid = lane < queriesPerUnit && qi < n;
+        bool valid = lane < queriesPerUnit && qi < n;
+        // heavy vertices (thousands of partners each) are walked by k_repulse_heavy, one block per vertex: here their hits
+        // would be applied one by one by a single owner lane and the whole grid would wait for that lane
+        if (valid && heavySlot && __ldg(heavySlot + __ldg(t.ids + qi)) >= 0) valid = false;
         if (valid) {
 #pragma unroll
             for (int k = 0; k < V; ++k) myQ[lane * V + k] = __ldg(t.lo[0] + (int64_t)k * t.stride[0] + qi);
@@ -502,6 +501,95 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
         partials[3 * w + 1] = totalTests;
         partials[3 * w + 2] = totalBoxTests;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Repulsion for heavy vertices (weight >= kHeavyWeight x the mean: hubs of heavy-tailed graphs).  The interaction radius grows
+// like w^(1/d) and the number of partners like w, so a hub of weight 6000 (c4) has tens of thousands of in-radius partners and
+// its ball covers most of the layout.  One block per heavy vertex scans the level-2 boxes with a fixed thread <-> box
+// assignment, descends into passing leaves and points, and every thread applies its own hits to private accumulators; a
+// fixed-order block reduction produces the vertex' result row.  Same predicates as the pair-stack walk, so the same pair set.
+constexpr float kHeavyWeight = 32.0f;
+
+template <int V>
+__global__ void __launch_bounds__(256) k_repulse_heavy(const TreeView t, const int* __restrict__ rowPtr, const int* __restrict__ col, int n,
+                                                       const ForceParams fp, double* __restrict__ forceRep, const RepLayout lay,
+                                                       const int* __restrict__ heavyVertex, const int* __restrict__ invOrder,
+                                                       double* __restrict__ partials /* [block][3] */) {
+    constexpr int RS = 4 * V + 2, K = RS + 3;
+    __shared__ double redBuf[8 * K];
+    const int v = heavyVertex[blockIdx.x];
+    const int p = invOrder[v];
+    double vals[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) vals[k] = 0.0;
+    // in a sharded run every rank launches all heavy vertices and keeps those whose sorted position falls in its blocks
+    const bool mine = ((p >> 5) / kRepBlockChunks) % lay.world == lay.rank;
+    if (mine) {
+        float4 q[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) q[k] = __ldg(t.lo[0] + (int64_t)k * t.stride[0] + p);
+        const float iwq = __ldg(t.bound[0] + p);
+        const int rowBegin = __ldg(rowPtr + v), rowEnd = __ldg(rowPtr + v + 1);
+        const float L = fp.edgeLength;
+        const int top = t.numLevels >= 2 ? 2 : 1;            // level the flat scan starts from
+        auto box = [&](int lv, int idx, float& bnd) {
+            float4 lo[V], hi[V];
+            const int64_t st = t.stride[lv];
+#pragma unroll
+            for (int k = 0; k < V; ++k) { lo[k] = __ldg(t.lo[lv] + k * st + idx); hi[k] = __ldg(t.hi[lv] + k * st + idx); }
+            bnd = __ldg(t.bound[lv] + idx);
+            return box_dist2<V>(q, lo, hi);
+        };
+        auto passes = [&](float d2, float bnd) { const float s = iwq * bnd; return d2 * s * s <= fp.pruneL2; };
+        auto leaf = [&](int leafIdx) {
+            for (int j = 0; j < kFan; ++j) {
+                const int idx = leafIdx * kFan + j;
+                if (idx >= n) break;
+                vals[RS + 1] += 1.0;
+                float4 pu[V];
+#pragma unroll
+                for (int k = 0; k < V; ++k) pu[k] = __ldg(t.lo[0] + (int64_t)k * t.stride[0] + idx);
+                const float iwu = __ldg(t.bound[0] + idx);
+                const float d2 = box_dist2<V>(q, pu, pu);
+                if (!passes(d2, iwu) || idx == p) continue;
+                const float dist = sqrtf(d2);
+                const float ws = iwq * iwu;
+                if (dist > 0.f && !(dist * ws <= L)) continue;
+                const int u = __ldg(t.ids + idx);
+                if (is_neighbor(col, rowBegin, rowEnd, u)) continue;
+                if (dist <= 0.f) { vals[4 * V + 1] += 1.0; continue; }
+                const float sc = fp.repulsionScale * ws / dist;
+                if (fp.dim == 1) vals[0] += (double)copysignf(fp.repulsionScale * ws, q[0].x - pu[0].x);
+                else
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    vals[4 * k + 0] += (double)(sc * (q[k].x - pu[k].x));
+                    vals[4 * k + 1] += (double)(sc * (q[k].y - pu[k].y));
+                    vals[4 * k + 2] += (double)(sc * (q[k].z - pu[k].z));
+                    vals[4 * k + 3] += (double)(sc * (q[k].w - pu[k].w));
+                }
+                vals[4 * V] += (double)(L / ws - dist);
+                vals[RS] += 1.0;
+            }
+        };
+        for (int node = threadIdx.x; node < t.count[top]; node += 256) {
+            float bnd;
+            vals[RS + 2] += 1.0;
+            if (!passes(box(top, node, bnd), bnd)) continue;
+            if (top == 1) { leaf(node); continue; }
+            for (int c = 0; c < kFan; ++c) {
+                const int lf = node * kFan + c;
+                if (lf >= t.count[1]) break;
+                vals[RS + 2] += 1.0;
+                if (passes(box(1, lf, bnd), bnd)) leaf(lf);
+            }
+        }
+    }
+    __shared__ double total[K];
+    block_sum<K, 256>(vals, redBuf, total);
+    if (threadIdx.x < RS && mine) forceRep[lay.row(p) * RS + threadIdx.x] = total[threadIdx.x];
+    if (threadIdx.x < 3) partials[(int64_t)blockIdx.x * 3 + threadIdx.x] = total[RS + threadIdx.x];
 }
 
 // ---------------------------------------------------------------------------------------------

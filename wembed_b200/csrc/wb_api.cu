@@ -90,6 +90,8 @@ struct wb_embedder {
     float* iw = nullptr;
     float* edgeWs = nullptr;              // ws(v,u) = iw_v * iw_u of every CSR entry
     int* chunkCounter = nullptr;          // work counter of the persistent repulsion kernel
+    int numHeavy = 0;                     // vertices of weight >= kHeavyWeight x mean, walked by k_repulse_heavy
+    int *heavyVertex = nullptr, *heavySlot = nullptr;
     int numHubs = 0;                      // rows longer than kHubThreshold, pre-summed by k_attract_hubs
     int *hubVertex = nullptr, *hubSlot = nullptr;
     double* hubForce = nullptr;
@@ -100,10 +102,8 @@ struct wb_embedder {
     int adamT = 0;                        // AdamOptimizer::t
 
     // spatial index
-    int mortonBits = 0, bandBits = 0;     // key = band << (mortonBits * dim) | morton
-    uint8_t* band = nullptr;              // weight band of every vertex (radius doubles from band to band), null if one band
-    int keyBits = 32;                     // width of the Morton sort key (a 64-bit path exists; it did not pay at d = 16)
-    void *keysIn = nullptr, *keysOut = nullptr;
+    int mortonBits = 0;                   // bits per dimension of the 32-bit Morton key
+    uint32_t *keysIn = nullptr, *keysOut = nullptr;
     int *valsIn = nullptr, *valsOut = nullptr;
     void* cubTemp = nullptr;
     size_t cubBytes = 0;
@@ -162,7 +162,7 @@ inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 void free_all(wb_embedder* h) {
     auto F = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
     F(h->rowPtr); F(h->col); F(h->x); F(h->xNew); F(h->mom1); F(h->mom2); F(h->forceRep); F(h->force);
-    F(h->iw); F(h->invOrder); F(h->edgeWs); F(h->chunkCounter); F(h->hubVertex); F(h->hubSlot); F(h->hubForce); F(h->band); F(h->keysIn); F(h->keysOut); F(h->valsIn); F(h->valsOut);
+    F(h->iw); F(h->invOrder); F(h->edgeWs); F(h->chunkCounter); F(h->hubVertex); F(h->hubSlot); F(h->hubForce); F(h->heavyVertex); F(h->heavySlot); F(h->keysIn); F(h->keysOut); F(h->valsIn); F(h->valsOut);
     F(h->cubTemp); F(h->momentPartials); F(h->quant); F(h->ids);
     for (int l = 0; l < wb::kMaxLevels; ++l) { F(h->lvlLo[l]); if (l > 0) F(h->lvlHi[l]); F(h->lvlBound[l]); }
     F(h->partialsForce); F(h->partialsRep); F(h->partialsObs); F(h->sumsAll); F(h->gathered); F(h->localSums);
@@ -218,13 +218,14 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
     h->classMax.assign(n, 1.0);
 
     // Morton keys: as many bits per dimension as fit a 32-bit key
-    h->keyBits = 32;   // measured at d = 16 (2 vs 4 bits per dimension): same test counts, so the cheaper 32-bit sort is kept everywhere
-    h->mortonBits = std::max(1, std::min(16, h->keyBits / h->dim));
-    h->keysIn = dalloc<uint64_t>(n); h->keysOut = dalloc<uint64_t>(n);
+    // 32-bit keys: floor(32 / d) bits per dimension.  Measured alternatives that did not pay and were removed: 64-bit keys (d = 16:
+    // 4 instead of 2 bits per dimension, same test counts, dearer sort) and a weight band in the top key bits (c4: separate subtrees
+    // per band cost more spatial coherence than the tighter pruning bounds saved, 150 vs 110 ms per step).
+    h->mortonBits = std::max(1, std::min(16, 32 / h->dim));
+    h->keysIn = dalloc<uint32_t>(n); h->keysOut = dalloc<uint32_t>(n);
     h->valsIn = dalloc<int>(n); h->valsOut = dalloc<int>(n);
     h->cubBytes = 0;
-    WB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, h->cubBytes, (uint64_t*)h->keysIn, (uint64_t*)h->keysOut, h->valsIn, h->valsOut,
-                                            std::max(n, 1), 0, 64, h->stream));
+    WB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, h->cubBytes, h->keysIn, h->keysOut, h->valsIn, h->valsOut, std::max(n, 1), 0, 32, h->stream));
     h->cubTemp = dalloc<char>(h->cubBytes);
     h->momentBlocks = std::max(1, std::min(div_up(n, 256), 592));
     h->momentPartials = dalloc<float>((size_t)h->momentBlocks * 4 * wb::kMaxDim);
@@ -295,18 +296,8 @@ void enqueue_index(wb_embedder* h, const float* pointBound) {
     cudaStream_t s = h->stream;
     WB_DISPATCH_V(V, wb::k_moments<V><<<h->momentBlocks, 256, 0, s>>>(h->x, n, h->momentPartials));
     wb::k_quant_params<<<1, 256, 0, s>>>(h->momentPartials, h->momentBlocks, n, h->dim, h->mortonBits, h->quant);
-    const int sortBits = h->mortonBits * h->dim + h->bandBits;
-    if (h->keyBits == 64) {
-        WB_DISPATCH_V(V, wb::k_morton_keys<V, uint64_t><<<div_up(n, 256), 256, 0, s>>>(h->x, n, h->dim, h->mortonBits, h->quant, h->band,
-                                                                                         (uint64_t*)h->keysIn, h->valsIn));
-        WB_CUDA(cub::DeviceRadixSort::SortPairs(h->cubTemp, h->cubBytes, (uint64_t*)h->keysIn, (uint64_t*)h->keysOut, h->valsIn, h->valsOut, n, 0,
-                                                sortBits, s));
-    } else {
-        WB_DISPATCH_V(V, wb::k_morton_keys<V, uint32_t><<<div_up(n, 256), 256, 0, s>>>(h->x, n, h->dim, h->mortonBits, h->quant, h->band,
-                                                                                         (uint32_t*)h->keysIn, h->valsIn));
-        WB_CUDA(cub::DeviceRadixSort::SortPairs(h->cubTemp, h->cubBytes, (uint32_t*)h->keysIn, (uint32_t*)h->keysOut, h->valsIn, h->valsOut, n, 0,
-                                                sortBits, s));
-    }
+    WB_DISPATCH_V(V, wb::k_morton_keys<V><<<div_up(n, 256), 256, 0, s>>>(h->x, n, h->dim, h->mortonBits, h->quant, h->keysIn, h->valsIn));
+    WB_CUDA(cub::DeviceRadixSort::SortPairs(h->cubTemp, h->cubBytes, h->keysIn, h->keysOut, h->valsIn, h->valsOut, n, 0, h->mortonBits * h->dim, s));
     const wb::TreeView& t = h->tree;
     WB_DISPATCH_V(V, wb::k_build_leaves<V><<<div_up(t.stride[0], 256), 256, 0, s>>>(
                          h->x, pointBound, h->valsOut, n, h->lvlLo[0], t.stride[0], h->lvlBound[0], h->ids, h->invOrder, h->lvlLo[1], h->lvlHi[1],
@@ -375,7 +366,14 @@ void enqueue_step(wb_embedder* h, double learningRate) {
     const int queriesPerUnit = h->repLayout.segRows / 32 >= 8 * residentWarps ? 32 : (h->repLayout.segRows / 16 >= 8 * residentWarps ? 16 : 8);
     WB_CUDA(cudaMemsetAsync(h->chunkCounter, 0, sizeof(int), s));
     WB_DISPATCH_V(V, wb::k_repulse_pairs<V><<<h->repBlocks, 32 * wb::repulse_warps(V), 0, s>>>(h->tree, h->rowPtr, h->col, n, fp, h->forceRep,
-                                                                                                  h->repLayout, queriesPerUnit, h->chunkCounter, h->partialsRep));
+                                                                                                  h->repLayout, queriesPerUnit, h->heavySlot, h->chunkCounter,
+                                                                                                  h->partialsRep));
+    const int repWarps = h->repBlocks * wb::repulse_warps(V);
+    if (h->numHeavy) {
+        WB_DISPATCH_V(V, wb::k_repulse_heavy<V><<<h->numHeavy, 256, 0, s>>>(h->tree, h->rowPtr, h->col, n, fp, h->forceRep, h->repLayout, h->heavyVertex,
+                                                                             h->invOrder, h->partialsRep + (size_t)repWarps * 3));
+        h->launches += 1;
+    }
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[5], s));
     if (sharded) {   // publish the rows this rank produced (its blocks of the sorted order)
         const size_t segDoubles = (size_t)h->repLayout.segRows * (4 * V + 2);
@@ -383,7 +381,7 @@ void enqueue_step(wb_embedder* h, double learningRate) {
             throw std::runtime_error("ncclAllGather (repulsion rows) failed");
         h->launches += 1;
     }
-    wb::k_reduce_partials<<<3, 256, 0, s>>>(h->partialsRep, h->repBlocks * wb::repulse_warps(V), 3, sums + K);
+    wb::k_reduce_partials<<<3, 256, 0, s>>>(h->partialsRep, repWarps + h->numHeavy, 3, sums + K);
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[2], s));
     if (h->numHubs) {
         WB_DISPATCH_V(V, wb::k_attract_hubs<V><<<h->numHubs, 256, 0, s>>>(h->x, h->edgeWs, h->rowPtr, h->col, h->hubVertex, fp, h->hubForce));
@@ -590,24 +588,23 @@ int wb_set_weights(wb_embedder* h, const double* weights) {
         WB_CUDA(cudaStreamSynchronize(h->stream));
         const double minW = *std::min_element(h->weights.begin(), h->weights.end());
         const double maxW = *std::max_element(h->weights.begin(), h->weights.end());
-        {   // weight bands of the device index: band = floor(log2((w / minW)^(1/d))), i.e. the interaction radius doubles
-            // from band to band (the reference's doubling classes double the WEIGHT; in d dimensions that is a factor
-            // 2^(1/d) in radius, too fine a split to pay for the loss of spatial coherence - measured)
-            const double invD = 1.0 / (double)h->dim;
-            const int bands = 1 + (int)std::floor(std::log2(std::pow(maxW / minW, invD)));
-            int bits = 0;
-            while ((1 << bits) < bands) ++bits;
-            bits = std::min(bits, 4);
-            if (!std::getenv("WB_INDEX_BANDS")) bits = 0;   // measured on c4: separate subtrees per band cost more coherence than the tighter bounds save
-            if (h->band) { cudaFree(h->band); h->band = nullptr; }
-            h->bandBits = bits;
-            h->mortonBits = std::max(1, std::min(16, (h->keyBits - bits) / h->dim));
-            if (bits > 0) {
-                std::vector<uint8_t> b(n);
-                for (int v = 0; v < n; ++v)
-                    b[v] = (uint8_t)std::min((1 << bits) - 1, (int)std::floor(std::log2(std::pow(weights[v] / minW, invD))));
-                h->band = dalloc<uint8_t>(n);
-                WB_CUDA(cudaMemcpyAsync(h->band, b.data(), n, cudaMemcpyHostToDevice, h->stream));
+        {   // heavy vertices: weight >= kHeavyWeight x the mean weight (their repulsion is walked by one block each)
+            double mean = 0.0;
+            for (int v = 0; v < n; ++v) mean += weights[v];
+            mean /= (double)n;
+            std::vector<int> heavy, slot(n, -1);
+            for (int v = 0; v < n; ++v)
+                if (weights[v] >= (double)wb::kHeavyWeight * mean) { slot[v] = (int)heavy.size(); heavy.push_back(v); }
+            if (h->heavyVertex) { cudaFree(h->heavyVertex); h->heavyVertex = nullptr; }
+            if (h->heavySlot) { cudaFree(h->heavySlot); h->heavySlot = nullptr; }
+            if (h->partialsRep) { cudaFree(h->partialsRep); h->partialsRep = nullptr; }
+            h->numHeavy = (int)heavy.size();
+            h->partialsRep = dalloc<double>(((size_t)h->repBlocks * 8 + heavy.size()) * 3);
+            if (h->numHeavy) {
+                h->heavyVertex = dalloc<int>(heavy.size());
+                h->heavySlot = dalloc<int>(n);
+                WB_CUDA(cudaMemcpyAsync(h->heavyVertex, heavy.data(), sizeof(int) * heavy.size(), cudaMemcpyHostToDevice, h->stream));
+                WB_CUDA(cudaMemcpyAsync(h->heavySlot, slot.data(), sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
                 WB_CUDA(cudaStreamSynchronize(h->stream));
             }
         }
