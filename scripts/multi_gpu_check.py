@@ -11,7 +11,12 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 n, d, steps = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
-edges, w, x0 = make_problem(n, d)
+if len(sys.argv) > 4 and sys.argv[4] == "heavy":      # heavy-tailed graph: exercises k_attract_hubs and k_repulse_heavy in the sharded step
+    from wembed_b200.datasets import degree_weights, heavy_tailed_graph, initial_coordinates
+    edges, _ = heavy_tailed_graph(n, 20, seed=3)
+    w, x0 = degree_weights(n, edges, d), initial_coordinates(n, d, seed=5)
+else:
+    edges, w, x0 = make_problem(n, d)
 rp, col = cabi.csr_from_edges(n, edges)
 
 def run(shard):
