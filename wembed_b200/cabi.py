@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libwembed_b200.so")
+LIB_PATH = os.environ.get("WB_LIB", os.path.join(_HERE, "lib", "libwembed_b200.so"))   # WB_LIB: A/B builds of the same ABI
 
 WB_OK, WB_ERR_INVALID, WB_ERR_CUDA, WB_ERR_NO_DEVICE, WB_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 WB_OPT_SIMPLE, WB_OPT_ADAM = 0, 1
