@@ -117,7 +117,7 @@ def measured_peak_gbs():
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures under profiles/ (c3, step 100 / 30)
-NCU_TRAFFIC = {"repel": 259.1e6 + 97.1e6, "attract_update": 282.9e6 + 87.4e6}
+NCU_TRAFFIC = {"repel": 168.8e6 + 72.7e6, "attract_update": 410.5e6 + 103.5e6}
 
 
 def algorithmic_bytes_per_step(n, m, d):
@@ -234,10 +234,10 @@ def run_ours(args):
     bytes_step = algorithmic_bytes_per_step(n, m, d)
     V4 = 4 * ((d + 3) // 4)                     # padded row length
     kernel_bytes = {  # algorithmic bytes per launch of each kernel group
-        # sorted points + ids + iw read once, CSR row ends, forceRep (fp64) + loss + coincidence count written
-        "repel": 4 * V4 * n + 8 * n + 8 * n + 8 * V4 * n + 8 * n,
-        # CSR col + per-edge pair weight, rowPtr, x, forceRep (fp64), m, v read; m, v, xNew written; loss / coincidence read
-        "attract_update": 16 * m + 4 * n + 4 * V4 * n + 8 * V4 * n + 8 * V4 * n + 12 * V4 * n + 8 * n,
+        # sorted points + ids + iw read once, result rows [force | loss | coincident] (fp64) written
+        "repel": 4 * V4 * n + 8 * n + 8 * (V4 + 2) * n,
+        # CSR col + per-edge pair weight, rowPtr, invOrder, x, result rows (fp64), m, v read; m, v, xNew written
+        "attract_update": 16 * m + 8 * n + 4 * V4 * n + 8 * (V4 + 2) * n + 8 * V4 * n + 12 * V4 * n,
         # x read twice (moments, keys), key/value sort passes, sorted planes + boxes written
         "index": 2 * 4 * V4 * n + 4 * 16 * n + 4 * V4 * n * 2 + 8 * n,
         "recentre_observe": 3 * 4 * V4 * n,
