@@ -569,11 +569,13 @@ int wb_destroy(wb_embedder* h) {
 
 int wb_set_coordinates(wb_embedder* h, const double* coords) {
     if (h && h->n > 0 && !coords) return fail(WB_ERR_INVALID, "wb_set_coordinates: null buffer");
+    if (h && !h->pending.empty()) return fail(WB_ERR_INVALID, "wb_set_coordinates: collect the asynchronous steps first");
     return guarded(h, [&] { upload_rows(h, coords, h->x); });
 }
 
 int wb_set_weights(wb_embedder* h, const double* weights) {
     if (h && h->n > 0 && !weights) return fail(WB_ERR_INVALID, "wb_set_weights: null buffer");
+    if (h && !h->pending.empty()) return fail(WB_ERR_INVALID, "wb_set_weights: collect the asynchronous steps first");
     return guarded(h, [&] {
         const int n = h->n;
         for (int v = 0; v < n; ++v)
