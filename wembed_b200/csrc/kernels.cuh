@@ -45,6 +45,10 @@ struct ForceParams {
     uint32_t seed, iteration; // tie-break generator key (Rand.cpp:29-35)
     int dim;                  // real embedding dimension (<= 4V)
     int keepForces;
+    // Repulsion results are accumulated as 64-bit fixed-point integers (value * 2^k, k chosen by wb_set_weights so that n terms of
+    // the largest possible magnitude cannot overflow): integer addition is associative, so the atomics that scatter a pair's
+    // term to both of its vertices give bit-identical sums in any order.
+    double fixForce, invFixForce, fixLoss, invFixLoss;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -299,39 +303,44 @@ __device__ __forceinline__ bool is_neighbor(const int* __restrict__ col, int beg
 }
 
 // ---------------------------------------------------------------------------------------------
-// Repulsion (WembedEmbedder.cpp:274-294 + 174-210): pair-stack walk.
+// Repulsion (WembedEmbedder.cpp:274-294 + 174-210): pair-stack walk, every unordered pair found once.
 //
 // A warp owns 32 consecutive queries and one LIFO stack of (level, node, query) pairs in shared memory.  Every
-// round pops four pairs, one per 8-lane group; lane c of the group tests child c of the pair's node against the
+// round pops eight pairs, two per 8-lane group; lane c of the group tests child c of the pair's node against the
 // pair's query (query coordinates come from shared memory, the child box from L1/L2).  Passing children are pushed
-// as new pairs, ordered child-major so that the four pairs popped together usually name the same node (one cache
-// line serves the four groups).  Every round performs 32 useful tests; a query performs exactly the tests of its
-// private depth-first walk.  Level-0 passes are exact-tested by the tester lane and handed to the owner lane of the
-// query, which applies the neighbour filter and accumulates in registers, in stack order: deterministic, no atomics.
+// as new pairs, ordered child-major so that the pairs popped together usually name the same node (one cache
+// line serves the four groups).
+//
+// The repulsive term of a pair is antisymmetric bit for bit (ws and the distance are symmetric, x_v - x_u = -(x_u - x_v)
+// exactly), so the query at sorted position p only searches positions > p - subtrees that end at or before p are cut
+// by an integer comparison - and the lane that finds a partner applies the term to BOTH vertices.  That halves the walk.
+// The scatter uses 64-bit integer atomics on fixed-point rows (see ForceParams): integer sums do not depend on the
+// order of the additions, so the step stays bit-reproducible and there are still no floating-point atomics.
 //
 // The kernel is persistent: every warp fetches the next chunk of 32 queries from an integer counter until none is
 // left, so warps whose queries need long walks do not hold finished warps of the same block hostage (measured: 28 %
-// of all stall samples sat on the final block barrier before).  Which warp handles which chunk does not influence
-// any result: a query's force depends only on its own walk, and the two statistics counters are integers.
-// Layout of the repulsion results.  One row of 4V + 2 doubles per SORTED position p: [force (4V) | loss | coincident partners].
-// The sorted order is cut into blocks of kRepBlockChunks chunks (a chunk = 32 consecutive positions = one warp's queries) and the
-// blocks are dealt round-robin to the ranks of a sharded run: whole blocks, because warps that run at the same time should work
-// on neighbouring chunks (they share tree nodes in L1 / L2; dealing single chunks cost 1.6x in walk time), round-robin because
-// the walk cost varies across space.  The rows a rank produces are contiguous, so one in-place all-gather publishes them:
-// row(p) = owner * segRows + local row.  With world = 1 this is the identity.
+// of all stall samples sat on the final block barrier before).  Chunks are handed out in ascending order, and late
+// positions have short walks (few positions behind them), so the tail of the schedule is cheap by construction.
+// Repulsion results: one row of 4V + 2 fixed-point integers per VERTEX: [force (4V) | loss | coincident partners].
+// The queries are dealt out by SORTED position: the sorted order is cut into blocks of kRepBlockChunks chunks (a chunk = 32
+// consecutive positions = one warp's queries) and the blocks are dealt round-robin to the ranks of a sharded run: whole blocks,
+// because warps that run at the same time should work on neighbouring chunks (they share tree nodes in L1 / L2; dealing single
+// chunks cost 1.6x in walk time), round-robin because the walk cost varies across space.  With world = 1 this is the identity.
 constexpr int kRepBlockChunks = 32;
 struct RepLayout {
     int world, rank, segRows;
-    __host__ __device__ __forceinline__ int64_t row(int p) const {
-        const int c = p >> 5, blk = c / kRepBlockChunks;
-        return (int64_t)(blk % world) * segRows + ((int64_t)(blk / world) * kRepBlockChunks + c % kRepBlockChunks) * 32 + (p & 31);
-    }
-    // l-th row this rank produces (l < segRows) -> sorted position
+    // l-th query this rank walks (l < segRows) -> sorted position
     __host__ __device__ __forceinline__ int position(int l) const {
         constexpr int blockRows = kRepBlockChunks * 32;
         return ((l / blockRows) * world + rank) * blockRows + l % blockRows;
     }
 };
+
+// value -> fixed point (round to nearest even, symmetric in the sign, so a pair's two contributions cancel exactly)
+__device__ __forceinline__ long long to_fixed(float term, double scale) { return __double2ll_rn((double)term * scale); }
+__device__ __forceinline__ void fixed_add(long long* p, long long v) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
+}
 
 // warps per block of k_repulse_pairs: the per-warp shared memory (queries + stack) grows with V
 __host__ __device__ constexpr int repulse_warps(int V) { return V <= 4 ? 8 : 4; }
@@ -339,9 +348,9 @@ __host__ __device__ constexpr int repulse_warps(int V) { return V <= 4 ? 8 : 4; 
 template <int V>
 __global__ void __launch_bounds__(256, (V <= 2 ? 4 : (V <= 4 ? 2 : 1)))
 k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __restrict__ col, int n, const ForceParams fp,
-                double* __restrict__ forceRep, const RepLayout lay, int queriesPerUnit, const int* __restrict__ heavySlot,
+                long long* __restrict__ forceRep, const RepLayout lay, int queriesPerUnit, const int* __restrict__ heavySlot,
                 int* __restrict__ chunkCounter, double* __restrict__ partials) {
-    constexpr int RS = 4 * V + 2;                // doubles per result row
+    constexpr int RS = 4 * V + 2;                // integers per result row
     constexpr int WARPS = repulse_warps(V), STACK = 56 * kMaxLevels + 72;   // LIFO bound: <= 56 leftovers per level + one push of 64
     __shared__ float4 sQ[WARPS][32][V];
     __shared__ float sIw[WARPS][32];
@@ -366,7 +375,7 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
     const int numChunks = lay.segRows / queriesPerUnit;
     int nPairs = 0, nTests = 0, nBoxTests = 0, qBase = 0;
 
-    // One (node, query) pair of the round: lane c tests child c.  Returns pass; lv / idx / qq / d2 / s describe the test.
+    // One (node, query) pair of the round: lane c tests child c.  lv / idx / qq / d2 / s describe the test.
     struct Slot { int lv, idx, qq; float d2, s; bool active, pass; };
     auto testEntry = [&](uint32_t entry, bool active) {
         Slot r;
@@ -387,53 +396,57 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
         for (int k = 0; k < V; ++k) qv[k] = myQ[r.qq * V + k];
         r.s = myIw[r.qq] * bnd;
         r.d2 = box_dist2<V>(qv, lo, hi);
-        r.pass = active && (r.d2 * r.s * r.s <= fp.pruneL2);
+        // the child covers sorted positions [idx << 3 lv, (idx + 1) << 3 lv): keep it only if some of them lie behind the query
+        const uint32_t endPos = (uint32_t)(r.idx + 1) << (kFanLog2 * r.lv);
+        r.pass = active && (r.d2 * r.s * r.s <= fp.pruneL2) && endPos > (uint32_t)(qBase + r.qq + 1);
         return r;
     };
-    // Level-0 passes: the tester lane evaluates the exact predicate, the owner lane of the query applies the neighbour filter
-    // and accumulates into its row of forceRep (read-modify-write in global memory: hits are rare - a handful per query -
-    // and keeping the accumulators out of registers buys occupancy for the walk).
+    // Level-0 passes: the tester lane evaluates the exact predicate and the neighbour filter and adds the term to the rows of
+    // both vertices (hits are rare - a handful per query - so this branch is cold).
     auto resolveHits = [&](const Slot& r) {
-        bool hit = r.pass && r.lv == 0 && (r.idx != qBase + r.qq);
+        bool hit = r.pass && r.lv == 0;
+        float dist = 0.f;
         if (hit) {
-            const float dist = sqrtf(r.d2);
+            dist = sqrtf(r.d2);
             if (dist > 0.f) hit = dist * r.s <= L;           // exact predicate; dist <= 0 is the coincident case
         }
-        uint32_t hb = __ballot_sync(0xffffffffu, hit);
-        while (hb) {
-            const int hl = __ffs(hb) - 1;
-            hb &= hb - 1u;
-            const int owner = __shfl_sync(0xffffffffu, r.qq, hl);
-            const int pidx = __shfl_sync(0xffffffffu, r.idx, hl);
-            if (lane == owner) {
-                float4 q[V], pu[V];
-#pragma unroll
-                for (int k = 0; k < V; ++k) { q[k] = myQ[lane * V + k]; pu[k] = __ldg(t.lo[0] + (int64_t)k * t.stride[0] + pidx); }
-                const float iwu = __ldg(t.bound[0] + pidx);
-                const int u = __ldg(t.ids + pidx);
-                const int v = myVert[lane];
-                const float dist = sqrtf(box_dist2<V>(q, pu, pu));
-                const float ws = myIw[lane] * iwu;
-                double* fr = forceRep + lay.row(qBase + lane) * RS;
+        if (hit) {
+            const int u = __ldg(t.ids + r.idx);
+            const int v = myVert[r.qq];
+            // pairs with a heavy vertex belong to that vertex' block (k_repulse_heavy)
+            if (!(heavySlot && __ldg(heavySlot + u) >= 0) && !is_neighbor(col, __ldg(rowPtr + v), __ldg(rowPtr + v + 1), u)) {
+                long long* fv = forceRep + (int64_t)v * RS;
+                long long* fu = forceRep + (int64_t)u * RS;
                 if (dist <= 0.f) {
-                    if (!is_neighbor(col, __ldg(rowPtr + v), __ldg(rowPtr + v + 1), u)) fr[4 * V + 1] += 1.0;
-                } else if (dist * ws <= L) {
-                    if (!is_neighbor(col, __ldg(rowPtr + v), __ldg(rowPtr + v + 1), u)) {
-                        // summed in double: a vertex can own hundreds of repulsive terms in a collapsed layout and the optimizer
-                        // normalises every component, so a cancellation residue must keep the accuracy of its terms
+                    fixed_add(fv + 4 * V + 1, 1ll);
+                    fixed_add(fu + 4 * V + 1, 1ll);
+                } else {
+                    const float ws = r.s;                    // level 0: bound = iw of the point
+                    if (fp.dim == 1) {                       // unit vector exactly +-1
+                        const float qx = myQ[r.qq * V].x, px = __ldg(t.lo[0] + r.idx).x;
+                        const long long f = to_fixed(copysignf(fp.repulsionScale * ws, qx - px), fp.fixForce);
+                        fixed_add(fv, f);
+                        fixed_add(fu, -f);
+                    } else {
                         const float sc = fp.repulsionScale * ws / dist;
-                        if (fp.dim == 1) fr[0] += (double)copysignf(fp.repulsionScale * ws, q[0].x - pu[0].x);   // unit vector exactly +-1
-                        else
 #pragma unroll
                         for (int k = 0; k < V; ++k) {
-                            fr[4 * k + 0] += (double)(sc * (q[k].x - pu[k].x));
-                            fr[4 * k + 1] += (double)(sc * (q[k].y - pu[k].y));
-                            fr[4 * k + 2] += (double)(sc * (q[k].z - pu[k].z));
-                            fr[4 * k + 3] += (double)(sc * (q[k].w - pu[k].w));
+                            const float4 q = myQ[r.qq * V + k], pu = __ldg(t.lo[0] + (int64_t)k * t.stride[0] + r.idx);
+                            const float e[4] = {sc * (q.x - pu.x), sc * (q.y - pu.y), sc * (q.z - pu.z), sc * (q.w - pu.w)};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                if (4 * k + i < fp.dim) {
+                                    const long long f = to_fixed(e[i], fp.fixForce);
+                                    fixed_add(fv + 4 * k + i, f);
+                                    fixed_add(fu + 4 * k + i, -f);
+                                }
+                            }
                         }
-                        fr[4 * V] += (double)(L / ws - dist);
-                        ++nPairs;
                     }
+                    const long long l = to_fixed(L / ws - dist, fp.fixLoss);
+                    fixed_add(fv + 4 * V, l);
+                    fixed_add(fu + 4 * V, l);
+                    nPairs += 2;                             // counted per direction, like the reference's loop over all v
                 }
             }
         }
@@ -448,17 +461,13 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
         if (qBase >= n) continue;                             // padding of the last block
         const int qi = qBase + lane;
         bool valid = lane < queriesPerUnit && qi < n;
-        // heavy vertices (thousands of partners each) are walked by k_repulse_heavy, one block per vertex: here their hits
-        // would be applied one by one by a single owner lane and the whole grid would wait for that lane
+        // heavy vertices (thousands of partners each) are walked by k_repulse_heavy, one block per vertex
         if (valid && heavySlot && __ldg(heavySlot + __ldg(t.ids + qi)) >= 0) valid = false;
         if (valid) {
 #pragma unroll
             for (int k = 0; k < V; ++k) myQ[lane * V + k] = __ldg(t.lo[0] + (int64_t)k * t.stride[0] + qi);
             myIw[lane] = __ldg(t.bound[0] + qi);
             myVert[lane] = __ldg(t.ids + qi);
-            double* fr = forceRep + lay.row(qi) * RS;
-#pragma unroll
-            for (int k = 0; k < RS; ++k) fr[k] = 0.0;
         }
         const uint32_t validMask = __ballot_sync(0xffffffffu, valid);
         if (valid) myStack[__popc(validMask & ltMask)] = ((uint32_t)(t.numLevels + 1) << 28) | ((uint32_t)lane << 23);
@@ -507,15 +516,17 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
 // Repulsion for heavy vertices (weight >= kHeavyWeight x the mean: hubs of heavy-tailed graphs).  The interaction radius grows
 // like w^(1/d) and the number of partners like w, so a hub of weight 6000 (c4) has tens of thousands of in-radius partners and
 // its ball covers most of the layout.  One block per heavy vertex scans the level-2 boxes with a fixed thread <-> box
-// assignment, descends into passing leaves and points, and every thread applies its own hits to private accumulators; a
-// fixed-order block reduction produces the vertex' result row.  Same predicates as the pair-stack walk, so the same pair set.
+// assignment, descends into passing leaves and points, and every thread applies its own hits: the vertex' own side to private
+// accumulators (fixed-order block reduction, then one fixed-point add per component), the partner's side straight to the
+// partner's row.  Every pair that involves a heavy vertex is handled here and only here (two heavy vertices: by the one at the
+// lower sorted position).  Same predicates as the pair-stack walk, so the same pair set.
 constexpr float kHeavyWeight = 32.0f;
 
 template <int V>
 __global__ void __launch_bounds__(256) k_repulse_heavy(const TreeView t, const int* __restrict__ rowPtr, const int* __restrict__ col, int n,
-                                                       const ForceParams fp, double* __restrict__ forceRep, const RepLayout lay,
-                                                       const int* __restrict__ heavyVertex, const int* __restrict__ invOrder,
-                                                       double* __restrict__ partials /* [block][3] */) {
+                                                       const ForceParams fp, long long* __restrict__ forceRep, const RepLayout lay,
+                                                       const int* __restrict__ heavyVertex, const int* __restrict__ heavySlot,
+                                                       const int* __restrict__ invOrder, double* __restrict__ partials /* [block][3] */) {
     constexpr int RS = 4 * V + 2, K = RS + 3;
     __shared__ double redBuf[8 * K];
     const int v = heavyVertex[blockIdx.x];
@@ -557,20 +568,32 @@ __global__ void __launch_bounds__(256) k_repulse_heavy(const TreeView t, const i
                 const float ws = iwq * iwu;
                 if (dist > 0.f && !(dist * ws <= L)) continue;
                 const int u = __ldg(t.ids + idx);
+                if (idx < p && __ldg(heavySlot + u) >= 0) continue;      // two heavy vertices: the lower position owns the pair
                 if (is_neighbor(col, rowBegin, rowEnd, u)) continue;
-                if (dist <= 0.f) { vals[4 * V + 1] += 1.0; continue; }
+                long long* fu = forceRep + (int64_t)u * RS;
+                if (dist <= 0.f) { vals[4 * V + 1] += 1.0; fixed_add(fu + 4 * V + 1, 1ll); continue; }
                 const float sc = fp.repulsionScale * ws / dist;
-                if (fp.dim == 1) vals[0] += (double)copysignf(fp.repulsionScale * ws, q[0].x - pu[0].x);
-                else
+                if (fp.dim == 1) {
+                    const float e = copysignf(fp.repulsionScale * ws, q[0].x - pu[0].x);
+                    vals[0] += (double)e;
+                    fixed_add(fu, -to_fixed(e, fp.fixForce));
+                } else {
 #pragma unroll
-                for (int k = 0; k < V; ++k) {
-                    vals[4 * k + 0] += (double)(sc * (q[k].x - pu[k].x));
-                    vals[4 * k + 1] += (double)(sc * (q[k].y - pu[k].y));
-                    vals[4 * k + 2] += (double)(sc * (q[k].z - pu[k].z));
-                    vals[4 * k + 3] += (double)(sc * (q[k].w - pu[k].w));
+                    for (int k = 0; k < V; ++k) {
+                        const float e[4] = {sc * (q[k].x - pu[k].x), sc * (q[k].y - pu[k].y), sc * (q[k].z - pu[k].z), sc * (q[k].w - pu[k].w)};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            if (4 * k + i < fp.dim) {
+                                vals[4 * k + i] += (double)e[i];
+                                fixed_add(fu + 4 * k + i, -to_fixed(e[i], fp.fixForce));
+                            }
+                        }
+                    }
                 }
-                vals[4 * V] += (double)(L / ws - dist);
-                vals[RS] += 1.0;
+                const float l = L / ws - dist;
+                vals[4 * V] += (double)l;
+                fixed_add(fu + 4 * V, to_fixed(l, fp.fixLoss));
+                vals[RS] += 2.0;
             }
         };
         for (int node = threadIdx.x; node < t.count[top]; node += 256) {
@@ -588,7 +611,12 @@ __global__ void __launch_bounds__(256) k_repulse_heavy(const TreeView t, const i
     }
     __shared__ double total[K];
     block_sum<K, 256>(vals, redBuf, total);
-    if (threadIdx.x < RS && mine) forceRep[lay.row(p) * RS + threadIdx.x] = total[threadIdx.x];
+    if (threadIdx.x < RS && mine) {
+        // other heavy blocks may be adding their side of a pair to this row at the same time
+        const int k = threadIdx.x;
+        const long long f = k < 4 * V ? __double2ll_rn(total[k] * fp.fixForce) : (k == 4 * V ? __double2ll_rn(total[k] * fp.fixLoss) : (long long)total[k]);
+        fixed_add(forceRep + (int64_t)v * RS + k, f);
+    }
     if (threadIdx.x < 3) partials[(int64_t)blockIdx.x * 3 + threadIdx.x] = total[RS + threadIdx.x];
 }
 
@@ -681,8 +709,7 @@ template <int V>
 __global__ void __launch_bounds__(256, 4) k_attract_update(const float4* __restrict__ x, const float* __restrict__ edgeWs,
                                                         const int* __restrict__ rowPtr, const int* __restrict__ col, int rangeBegin,
                                                         int rangeEnd, int vertsPerBlock, const ForceParams fp,
-                                                        const double* __restrict__ forceRep, const RepLayout lay,
-                                                        const int* __restrict__ invOrder, const int* __restrict__ hubSlot,
+                                                        const long long* __restrict__ forceRep, const int* __restrict__ hubSlot,
                                                         const double* __restrict__ hubForce, float4* __restrict__ xNew,
                                                         float4* __restrict__ mom1, float4* __restrict__ mom2,
                                                         float4* __restrict__ forceOut, double* __restrict__ partials) {
@@ -707,9 +734,9 @@ __global__ void __launch_bounds__(256, 4) k_attract_update(const float4* __restr
         double loss = 0.0;
         int nCoincident = 0;
         int e = 0, end = 0, hub = -1;
-        const double* rep = forceRep;                              // this vertex' row of repulsion results
+        const long long* rep = forceRep;                           // this vertex' row of repulsion results (fixed point)
         if (valid) {
-            rep = forceRep + lay.row(__ldg(invOrder + v)) * RS;
+            rep = forceRep + (int64_t)v * RS;
             if (chunkLane) xv = __ldg(x + at);
             hub = hubSlot ? __ldg(hubSlot + v) : -1;
             if (hub < 0) { e = __ldg(rowPtr + v); end = __ldg(rowPtr + v + 1); }
@@ -769,7 +796,7 @@ __global__ void __launch_bounds__(256, 4) k_attract_update(const float4* __restr
             loss = hf[4 * V];
             nCoincident = (int)hf[4 * V + 1];
         }
-        if (valid) nCoincident += (int)rep[4 * V + 1];
+        if (valid) nCoincident += (int)__ldg(rep + 4 * V + 1);
 
         // coincident partners: every one of them adds the same unit vector (generator re-created per pair, :150-155, :183-188).
         // The generator state (624 words) lives in per-warp shared memory; the rare vertices that need it take turns.
@@ -792,11 +819,13 @@ __global__ void __launch_bounds__(256, 4) k_attract_update(const float4* __restr
 
         if (valid && c == 0) {
             sumLossA += loss;
-            sumLossR += rep[4 * V];
+            sumLossR += (double)__ldg(rep + 4 * V) * fp.invFixLoss;
         }
         if (valid && chunkLane) {
-            const double* fr = rep + 4 * c;
-            float4 f = make_float4((float)(acc[0] + fr[0]), (float)(acc[1] + fr[1]), (float)(acc[2] + fr[2]), (float)(acc[3] + fr[3]));
+            // rows are (32 V + 16) bytes long, so every chunk of four integers is 16-byte aligned
+            const longlong2 f01 = __ldg(reinterpret_cast<const longlong2*>(rep + 4 * c)), f23 = __ldg(reinterpret_cast<const longlong2*>(rep + 4 * c) + 1);
+            float4 f = make_float4((float)(acc[0] + (double)f01.x * fp.invFixForce), (float)(acc[1] + (double)f01.y * fp.invFixForce),
+                                   (float)(acc[2] + (double)f23.x * fp.invFixForce), (float)(acc[3] + (double)f23.y * fp.invFixForce));
             if (fp.centreScale != 0.f) {                   // :296-301
                 f.x = fmaf(-fp.centreScale, xv.x, f.x); f.y = fmaf(-fp.centreScale, xv.y, f.y);
                 f.z = fmaf(-fp.centreScale, xv.z, f.z); f.w = fmaf(-fp.centreScale, xv.w, f.w);

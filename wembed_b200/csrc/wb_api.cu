@@ -32,6 +32,7 @@ struct NcclApi {
     ncclResult_t (*getUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*commInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*allGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*allReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*commDestroy)(ncclComm_t) = nullptr;
     bool ok = false;
 };
@@ -45,8 +46,9 @@ NcclApi& nccl() {
         a.getUniqueId = reinterpret_cast<decltype(a.getUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
         a.commInitRank = reinterpret_cast<decltype(a.commInitRank)>(dlsym(lib, "ncclCommInitRank"));
         a.allGather = reinterpret_cast<decltype(a.allGather)>(dlsym(lib, "ncclAllGather"));
+        a.allReduce = reinterpret_cast<decltype(a.allReduce)>(dlsym(lib, "ncclAllReduce"));
         a.commDestroy = reinterpret_cast<decltype(a.commDestroy)>(dlsym(lib, "ncclCommDestroy"));
-        a.ok = a.getUniqueId && a.commInitRank && a.allGather && a.commDestroy;
+        a.ok = a.getUniqueId && a.commInitRank && a.allGather && a.allReduce && a.commDestroy;
         return a;
     }();
     return api;
@@ -84,8 +86,10 @@ struct wb_embedder {
 
     // layout state
     float4 *x = nullptr, *xNew = nullptr, *mom1 = nullptr, *mom2 = nullptr, *force = nullptr;
-    double* forceRep = nullptr;           // repulsion results, one row of 4V + 2 doubles per sorted position (wb::RepLayout)
-    wb::RepLayout repLayout{1, 0, 0};
+    long long* forceRep = nullptr;        // repulsion results, one row of 4V + 2 fixed-point integers per vertex
+    size_t forceRepBytes = 0;
+    double fixForce = 1.0, fixLoss = 1.0; // fixed-point scales of those rows (powers of two, chosen by wb_set_weights)
+    wb::RepLayout repLayout{1, 0, 0};     // which sorted positions this rank's repulsion walk queries
     int* invOrder = nullptr;              // vertex -> sorted position
     float* iw = nullptr;
     float* edgeWs = nullptr;              // ws(v,u) = iw_v * iw_u of every CSR entry
@@ -176,6 +180,18 @@ void free_all(wb_embedder* h) {
     h->stream = nullptr;
 }
 
+// Fixed-point scales of the repulsion rows: the largest power of two such that n terms of the largest possible magnitude
+// (|force component| <= |repulsionScale| * max ws, loss term <= L / min ws, ws = iw_v * iw_u) stay below 2^62.
+void choose_fixed_scales(wb_embedder* h, double maxIw, double minIw) {
+    auto scale = [&](double maxTerm) {
+        const double bound = (double)std::max(h->n, 2) * maxTerm;
+        if (!(bound > 0.0) || !std::isfinite(bound)) return 1.0;
+        return std::ldexp(1.0, std::max(-900, std::min(900, 61 - (int)std::ceil(std::log2(bound)))));
+    };
+    h->fixForce = scale(std::fabs(h->opt.repulsion_scale) * maxIw * maxIw);
+    h->fixLoss = scale(h->opt.edge_length / (minIw * minIw));
+}
+
 void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
     const int n = h->n, V = h->V;
     WB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -202,8 +218,9 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
     }
     const size_t rows = (size_t)n * V;
     h->repLayout = wb::RepLayout{1, 0, div_up(std::max(n, 1), 32) * 32};
-    h->forceRep = dalloc<double>((size_t)h->repLayout.segRows * (4 * V + 2));
-    WB_CUDA(cudaMemsetAsync(h->forceRep, 0, (size_t)h->repLayout.segRows * (4 * V + 2) * sizeof(double), h->stream));
+    h->forceRepBytes = (size_t)std::max(n, 1) * (4 * V + 2) * sizeof(long long);
+    h->forceRep = dalloc<long long>((size_t)std::max(n, 1) * (4 * V + 2));
+    WB_CUDA(cudaMemsetAsync(h->forceRep, 0, h->forceRepBytes, h->stream));
     h->invOrder = dalloc<int>(n);
     WB_CUDA(cudaMemsetAsync(h->invOrder, 0, std::max(n, 1) * sizeof(int), h->stream));
     for (float4** p : {&h->x, &h->xNew, &h->mom1, &h->mom2, &h->force}) {
@@ -215,6 +232,7 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
     if (n) wb::k_fill<float><<<div_up(n, 256), 256, 0, h->stream>>>(h->iw, n, 1.0f);
     if (h->numDirected) wb::k_fill<float><<<div_up(h->numDirected, 256), 256, 0, h->stream>>>(h->edgeWs, h->numDirected, 1.0f);
     h->weights.assign(n, 1.0);
+    choose_fixed_scales(h, 1.0, 1.0);
     h->classMax.assign(n, 1.0);
 
     // Morton keys: as many bits per dimension as fit a 32-bit key
@@ -353,6 +371,8 @@ void enqueue_step(wb_embedder* h, double learningRate) {
     fp.iteration = (uint32_t)h->iteration;
     fp.dim = h->dim;
     fp.keepForces = h->opt.keep_forces;
+    fp.fixForce = h->fixForce; fp.invFixForce = 1.0 / h->fixForce;
+    fp.fixLoss = h->fixLoss; fp.invFixLoss = 1.0 / h->fixLoss;
     const int K = 2 + 4 * V;
 
     const bool sharded = h->world > 1;
@@ -365,20 +385,20 @@ void enqueue_step(wb_embedder* h, double learningRate) {
     const int64_t residentWarps = (int64_t)h->repBlocks * wb::repulse_warps(V);
     const int queriesPerUnit = h->repLayout.segRows / 32 >= 8 * residentWarps ? 32 : (h->repLayout.segRows / 16 >= 8 * residentWarps ? 16 : 8);
     WB_CUDA(cudaMemsetAsync(h->chunkCounter, 0, sizeof(int), s));
+    WB_CUDA(cudaMemsetAsync(h->forceRep, 0, h->forceRepBytes, s));      // EmbedderState::nextStep zeroes the forces
     WB_DISPATCH_V(V, wb::k_repulse_pairs<V><<<h->repBlocks, 32 * wb::repulse_warps(V), 0, s>>>(h->tree, h->rowPtr, h->col, n, fp, h->forceRep,
                                                                                                   h->repLayout, queriesPerUnit, h->heavySlot, h->chunkCounter,
                                                                                                   h->partialsRep));
     const int repWarps = h->repBlocks * wb::repulse_warps(V);
     if (h->numHeavy) {
         WB_DISPATCH_V(V, wb::k_repulse_heavy<V><<<h->numHeavy, 256, 0, s>>>(h->tree, h->rowPtr, h->col, n, fp, h->forceRep, h->repLayout, h->heavyVertex,
-                                                                             h->invOrder, h->partialsRep + (size_t)repWarps * 3));
+                                                                             h->heavySlot, h->invOrder, h->partialsRep + (size_t)repWarps * 3));
         h->launches += 1;
     }
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[5], s));
-    if (sharded) {   // publish the rows this rank produced (its blocks of the sorted order)
-        const size_t segDoubles = (size_t)h->repLayout.segRows * (4 * V + 2);
-        if (nccl().allGather(h->forceRep + (size_t)h->rank * segDoubles, h->forceRep, segDoubles, ncclDouble, h->comm, s) != ncclSuccess)
-            throw std::runtime_error("ncclAllGather (repulsion rows) failed");
+    if (sharded) {   // every rank found the pairs of its own queries and added each pair's term to both rows: integer sum over the ranks
+        if (nccl().allReduce(h->forceRep, h->forceRep, (size_t)n * (4 * V + 2), ncclInt64, ncclSum, h->comm, s) != ncclSuccess)
+            throw std::runtime_error("ncclAllReduce (repulsion rows) failed");
         h->launches += 1;
     }
     wb::k_reduce_partials<<<3, 256, 0, s>>>(h->partialsRep, repWarps + h->numHeavy, 3, sums + K);
@@ -388,8 +408,8 @@ void enqueue_step(wb_embedder* h, double learningRate) {
         h->launches += 1;
     }
     WB_DISPATCH_V(V, wb::k_attract_update<V><<<h->forceBlocks, 256, 0, s>>>(
-                         h->x, h->edgeWs, h->rowPtr, h->col, h->ownBegin, h->ownEnd, h->forceVertsPerBlock, fp, h->forceRep, h->repLayout,
-                         h->invOrder, h->hubSlot, h->hubForce, h->xNew, h->mom1, h->mom2, h->force, h->partialsForce));
+                         h->x, h->edgeWs, h->rowPtr, h->col, h->ownBegin, h->ownEnd, h->forceVertsPerBlock, fp, h->forceRep,
+                         h->hubSlot, h->hubForce, h->xNew, h->mom1, h->mom2, h->force, h->partialsForce));
     wb::k_reduce_partials<<<K, 256, 0, s>>>(h->partialsForce, h->forceBlocks, K, sums);
     if (sharded) {   // {lossA, lossR, sum xnew[k], pairs, tests}: all-gather, then every rank adds in rank order
         if (nccl().allGather(sums, h->gathered, K + 3, ncclDouble, h->comm, s) != ncclSuccess) throw std::runtime_error("ncclAllGather (force sums) failed");
@@ -590,6 +610,7 @@ int wb_set_weights(wb_embedder* h, const double* weights) {
         WB_CUDA(cudaStreamSynchronize(h->stream));
         const double minW = *std::min_element(h->weights.begin(), h->weights.end());
         const double maxW = *std::max_element(h->weights.begin(), h->weights.end());
+        choose_fixed_scales(h, *std::max_element(iw.begin(), iw.end()), *std::min_element(iw.begin(), iw.end()));
         {   // heavy vertices: weight >= kHeavyWeight x the mean weight (their repulsion is walked by one block each)
             double mean = 0.0;
             for (int v = 0; v < n; ++v) mean += weights[v];
@@ -733,9 +754,6 @@ int wb_comm_init(wb_embedder* h, const char* id128, int32_t rank, int32_t world)
         // repulsion rows: blocks of kRepBlockChunks chunks of the sorted order dealt round-robin to the ranks, each rank's rows contiguous
         const int blocksPerRank = div_up(div_up(div_up(std::max(n, 1), 32), wb::kRepBlockChunks), world);
         h->repLayout = wb::RepLayout{world, rank, blocksPerRank * wb::kRepBlockChunks * 32};
-        cudaFree(h->forceRep);
-        h->forceRep = dalloc<double>((size_t)h->repLayout.segRows * world * (4 * V + 2));
-        WB_CUDA(cudaMemsetAsync(h->forceRep, 0, (size_t)h->repLayout.segRows * world * (4 * V + 2) * sizeof(double), h->stream));
         h->gathered = dalloc<double>((size_t)world * h->sumsTotal);
         h->localSums = dalloc<double>(h->sumsTotal);
         WB_CUDA(cudaMemsetAsync(h->localSums, 0, sizeof(double) * h->sumsTotal, h->stream));
