@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py - WEmbed gradient-descent step throughput on B200 (see DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4|small]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4|c5|small]
 
 One "step" = one WembedEmbedder::calculateStep over the whole graph (index rebuild, attractive and
 repulsive forces, Adam, recentring, observables).  Metric = directed edge-force updates per second =
@@ -40,6 +40,7 @@ WORKLOADS = {
     "c2": (100_000, 10, 4, "geometric"),
     "c3": (1_000_000, 10, 8, "geometric"),
     "c4": (1_000_000, 20, 8, "heavy_tailed"),
+    "c5": (10_000_000, 20, 16, "geometric"),      # ~1e8 undirected edges
 }
 
 
@@ -234,9 +235,9 @@ def run_ours(args):
     bytes_step = algorithmic_bytes_per_step(n, m, d)
     V4 = 4 * ((d + 3) // 4)                     # padded row length
     kernel_bytes = {  # algorithmic bytes per launch of each kernel group
-        # sorted points + ids + iw read once, result rows [force | loss | coincident] (fp64) written
+        # sorted points + ids + iw read once, result rows [force | loss | coincident] (64-bit fixed point) written
         "repel": 4 * V4 * n + 8 * n + 8 * (V4 + 2) * n,
-        # CSR col + per-edge pair weight, rowPtr, invOrder, x, result rows (fp64), m, v read; m, v, xNew written
+        # CSR col + per-edge pair weight, rowPtr, slot order, x, result rows (64-bit fixed point), m, v read; m, v, xNew written
         "attract_update": 16 * m + 8 * n + 4 * V4 * n + 8 * (V4 + 2) * n + 8 * V4 * n + 12 * V4 * n,
         # x read twice (moments, keys), key/value sort passes, sorted planes + boxes written
         "index": 2 * 4 * V4 * n + 4 * 16 * n + 4 * V4 * n * 2 + 8 * n,
@@ -253,7 +254,8 @@ def run_ours(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {WORKLOADS[args.workload][3]} graph n={n} m={m} d={d}, default options, "
                                f"trajectory steps {args.warmup + 1}..{args.warmup + args.steps} from the uniform-cube layout",
-                   "parallelism": f"vertex ranges over {world} GPU(s); positions replicated, owners' rows all-gathered over NCCL each step",
+                   "parallelism": (f"{world} GPU(s): repulsion queries dealt by blocks of the sorted order, integer result rows reduce-scattered; attraction + "
+                                   "optimizer by vertex range, owners' rows all-gathered over NCCL each step"),
                    "l2": "working set (x, m, v, CSR, index: ~260 MB at c3) exceeds the 126 MB L2; no flush needed"},
         "e2e": {"value": units / de, "unit": "directed-edge force updates/s", "steps_per_s": args.steps / de,
                 "h2d_bytes_per_step": n * d * 8 / args.steps + 8, "d2h_bytes_per_step": n * d * 8 / args.steps + 8 * (8 + 4 * ((d + 3) // 4)),

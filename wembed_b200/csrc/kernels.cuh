@@ -345,8 +345,11 @@ __device__ __forceinline__ void fixed_add(long long* p, long long v) {
 // warps per block of k_repulse_pairs: the per-warp shared memory (queries + stack) grows with V
 __host__ __device__ constexpr int repulse_warps(int V) { return V <= 4 ? 8 : 4; }
 
+#ifndef WB_REPULSE_MINBLOCKS
+#define WB_REPULSE_MINBLOCKS 4
+#endif
 template <int V>
-__global__ void __launch_bounds__(256, (V <= 2 ? 4 : (V <= 4 ? 2 : 1)))
+__global__ void __launch_bounds__(256, (V <= 2 ? WB_REPULSE_MINBLOCKS : (V <= 4 ? 2 : 1)))
 k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __restrict__ col, int n, const ForceParams fp,
                 long long* __restrict__ forceRep, const RepLayout lay, int queriesPerUnit, const int* __restrict__ heavySlot,
                 int* __restrict__ chunkCounter, double* __restrict__ partials) {
@@ -356,6 +359,7 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
     __shared__ float sIw[WARPS][32];
     __shared__ int sVert[WARPS][32];             // vertex id of each query
     __shared__ uint32_t sStack[WARPS][STACK];    // (level << 28) | (query lane << 23) | node   (node < 2^23: n <= 6.7e7)
+    __shared__ uint32_t sLeaf[WARPS][80];        // leaves waiting for their point round: (query lane << 23) | leaf
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = lane & (kFan - 1), g = lane >> kFanLog2;
     // lanes that precede this one in child-major order (c, g)
     uint32_t before = 0u;
@@ -368,6 +372,7 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
     float* myIw = &sIw[warp][0];
     int* myVert = &sVert[warp][0];
     uint32_t* myStack = &sStack[warp][0];
+    uint32_t* myLeaf = &sLeaf[warp][0];
     const float L = fp.edgeLength;
     const uint32_t ltMask = (1u << lane) - 1u;
     // Work unit of a warp = queriesPerUnit (8, 16 or 32) consecutive rows of this rank's share of the sorted order.  Small units
@@ -375,18 +380,17 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
     const int numChunks = lay.segRows / queriesPerUnit;
     int nPairs = 0, nTests = 0, nBoxTests = 0, qBase = 0;
 
-    // One (node, query) pair of the round: lane c tests child c.  lv / idx / qq / d2 / s describe the test.
-    struct Slot { int lv, idx, qq; float d2, s; bool active, pass; };
-    auto testEntry = [&](uint32_t entry, bool active) {
-        Slot r;
-        r.active = active;
-        r.lv = active ? (int)(entry >> 28) - 1 : 0;
+    // Box round: one (node, query) pair per 8-lane group and slot; lane c tests child box c (level lv >= 1) of the node.
+    struct BoxSlot { int lv, idx, qq; bool pass; };
+    auto testBox = [&](uint32_t entry, bool active) {
+        BoxSlot r;
+        r.lv = active ? (int)(entry >> 28) - 1 : 1;
         r.idx = active ? (int)(entry & 0x007fffffu) * kFan + c : 0;
         r.qq = (int)((entry >> 23) & 31u);
         float4 lo[V], hi[V], qv[V];
         const int64_t st = t.stride[r.lv];
         const float4* loP = t.lo[r.lv];
-        const float4* hiP = t.hi[r.lv];         // == lo for level 0
+        const float4* hiP = t.hi[r.lv];
 #pragma unroll
         for (int k = 0; k < V; ++k) lo[k] = __ldg(loP + k * st + r.idx);
 #pragma unroll
@@ -394,62 +398,71 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
         const float bnd = __ldg(t.bound[r.lv] + r.idx);
 #pragma unroll
         for (int k = 0; k < V; ++k) qv[k] = myQ[r.qq * V + k];
-        r.s = myIw[r.qq] * bnd;
-        r.d2 = box_dist2<V>(qv, lo, hi);
-        // the child covers sorted positions [idx << 3 lv, (idx + 1) << 3 lv): keep it only if some of them lie behind the query
-        const uint32_t endPos = (uint32_t)(r.idx + 1) << (kFanLog2 * r.lv);
-        r.pass = active && (r.d2 * r.s * r.s <= fp.pruneL2) && endPos > (uint32_t)(qBase + r.qq + 1);
+        const float s = myIw[r.qq] * bnd;
+        const float d2 = box_dist2<V>(qv, lo, hi);
+        // the child covers sorted positions [idx << 3 lv, (idx + 1) << 3 lv): keep it only if some of them lie behind the query,
+        // (idx + 1) << 3 lv > qpos + 1  <=>  idx >= (qpos + 1) >> 3 lv
+        r.pass = active && (d2 * s * s <= fp.pruneL2) && r.idx >= ((qBase + r.qq + 1) >> (kFanLog2 * r.lv));
         return r;
     };
-    // Level-0 passes: the tester lane evaluates the exact predicate and the neighbour filter and adds the term to the rows of
-    // both vertices (hits are rare - a handful per query - so this branch is cold).
-    auto resolveHits = [&](const Slot& r) {
-        bool hit = r.pass && r.lv == 0;
-        float dist = 0.f;
-        if (hit) {
-            dist = sqrtf(r.d2);
-            if (dist > 0.f) hit = dist * r.s <= L;           // exact predicate; dist <= 0 is the coincident case
+    // Point round: one (leaf, query) pair per 8-lane group and slot; lane c tests point c of the leaf with the exact predicate.
+    // A hit is resolved by the lane that found it: neighbour filter, then the term goes to the rows of both vertices
+    // (hits are rare - a handful per query - so this branch is cold).
+    struct PointSlot { int idx, qq; float d2, ws; bool hit; };
+    auto testPoint = [&](uint32_t entry, bool active) {
+        PointSlot r;
+        r.qq = (int)((entry >> 23) & 31u);
+        r.idx = active ? (int)(entry & 0x007fffffu) * kFan + c : 0;
+        float4 pu[V], qv[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) pu[k] = __ldg(t.lo[0] + (int64_t)k * t.stride[0] + r.idx);
+        const float iwu = __ldg(t.bound[0] + r.idx);
+#pragma unroll
+        for (int k = 0; k < V; ++k) qv[k] = myQ[r.qq * V + k];
+        r.ws = myIw[r.qq] * iwu;
+        r.d2 = point_dist2<V>(qv, pu);
+        r.hit = active && r.idx > qBase + r.qq && r.d2 * r.ws * r.ws <= fp.pruneL2;
+        return r;
+    };
+    auto resolveHit = [&](const PointSlot& r) {
+        if (!r.hit) return;
+        const float dist = sqrtf(r.d2), ws = r.ws;
+        if (dist > 0.f && !(dist * ws <= L)) return;         // exact predicate; dist <= 0 is the coincident case
+        const int u = __ldg(t.ids + r.idx);
+        const int v = myVert[r.qq];
+        // pairs with a heavy vertex belong to that vertex' block (k_repulse_heavy)
+        if ((heavySlot && __ldg(heavySlot + u) >= 0) || is_neighbor(col, __ldg(rowPtr + v), __ldg(rowPtr + v + 1), u)) return;
+        long long* fv = forceRep + (int64_t)v * RS;
+        long long* fu = forceRep + (int64_t)u * RS;
+        if (dist <= 0.f) {
+            fixed_add(fv + 4 * V + 1, 1ll);
+            fixed_add(fu + 4 * V + 1, 1ll);
+            return;
         }
-        if (hit) {
-            const int u = __ldg(t.ids + r.idx);
-            const int v = myVert[r.qq];
-            // pairs with a heavy vertex belong to that vertex' block (k_repulse_heavy)
-            if (!(heavySlot && __ldg(heavySlot + u) >= 0) && !is_neighbor(col, __ldg(rowPtr + v), __ldg(rowPtr + v + 1), u)) {
-                long long* fv = forceRep + (int64_t)v * RS;
-                long long* fu = forceRep + (int64_t)u * RS;
-                if (dist <= 0.f) {
-                    fixed_add(fv + 4 * V + 1, 1ll);
-                    fixed_add(fu + 4 * V + 1, 1ll);
-                } else {
-                    const float ws = r.s;                    // level 0: bound = iw of the point
-                    if (fp.dim == 1) {                       // unit vector exactly +-1
-                        const float qx = myQ[r.qq * V].x, px = __ldg(t.lo[0] + r.idx).x;
-                        const long long f = to_fixed(copysignf(fp.repulsionScale * ws, qx - px), fp.fixForce);
-                        fixed_add(fv, f);
-                        fixed_add(fu, -f);
-                    } else {
-                        const float sc = fp.repulsionScale * ws / dist;
+        if (fp.dim == 1) {                                   // unit vector exactly +-1
+            const long long f = to_fixed(copysignf(fp.repulsionScale * ws, myQ[r.qq * V].x - __ldg(t.lo[0] + r.idx).x), fp.fixForce);
+            fixed_add(fv, f);
+            fixed_add(fu, -f);
+        } else {
+            const float sc = fp.repulsionScale * ws / dist;
 #pragma unroll
-                        for (int k = 0; k < V; ++k) {
-                            const float4 q = myQ[r.qq * V + k], pu = __ldg(t.lo[0] + (int64_t)k * t.stride[0] + r.idx);
-                            const float e[4] = {sc * (q.x - pu.x), sc * (q.y - pu.y), sc * (q.z - pu.z), sc * (q.w - pu.w)};
+            for (int k = 0; k < V; ++k) {
+                const float4 q = myQ[r.qq * V + k], pu = __ldg(t.lo[0] + (int64_t)k * t.stride[0] + r.idx);
+                const float e[4] = {sc * (q.x - pu.x), sc * (q.y - pu.y), sc * (q.z - pu.z), sc * (q.w - pu.w)};
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                if (4 * k + i < fp.dim) {
-                                    const long long f = to_fixed(e[i], fp.fixForce);
-                                    fixed_add(fv + 4 * k + i, f);
-                                    fixed_add(fu + 4 * k + i, -f);
-                                }
-                            }
-                        }
+                for (int i = 0; i < 4; ++i) {
+                    if (4 * k + i < fp.dim) {
+                        const long long f = to_fixed(e[i], fp.fixForce);
+                        fixed_add(fv + 4 * k + i, f);
+                        fixed_add(fu + 4 * k + i, -f);
                     }
-                    const long long l = to_fixed(L / ws - dist, fp.fixLoss);
-                    fixed_add(fv + 4 * V, l);
-                    fixed_add(fu + 4 * V, l);
-                    nPairs += 2;                             // counted per direction, like the reference's loop over all v
                 }
             }
         }
+        const long long l = to_fixed(L / ws - dist, fp.fixLoss);
+        fixed_add(fv + 4 * V, l);
+        fixed_add(fu + 4 * V, l);
+        nPairs += 2;                                         // counted per direction, like the reference's loop over all v
     };
 
     for (;;) {
@@ -471,28 +484,46 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
         }
         const uint32_t validMask = __ballot_sync(0xffffffffu, valid);
         if (valid) myStack[__popc(validMask & ltMask)] = ((uint32_t)(t.numLevels + 1) << 28) | ((uint32_t)lane << 23);
-        int sp = __popc(validMask);
+        int sp = __popc(validMask), nLeaf = 0;
         __syncwarp();
-        while (sp > 0) {
-            // a round pops up to eight pairs: two per 8-lane group, tested back to back so their loads overlap
-            const int take = min(8, sp);
-            const bool activeA = g < take, activeB = g + 4 < take;
-            const uint32_t entryA = myStack[activeA ? sp - 1 - g : 0];
-            const uint32_t entryB = myStack[activeB ? sp - 5 - g : 0];
-            sp -= take;
-            const Slot a = testEntry(entryA, activeA);
-            const Slot b = testEntry(entryB, activeB);
-            __syncwarp();                          // every lane has read its entries before the stack is overwritten
-            const bool pushA = a.pass && a.lv > 0, pushB = b.pass && b.lv > 0;
-            const uint32_t pa = __ballot_sync(0xffffffffu, pushA), pb = __ballot_sync(0xffffffffu, pushB);
-            if (pushA) myStack[sp + __popc(pa & before)] = ((uint32_t)a.lv << 28) | ((uint32_t)a.qq << 23) | (uint32_t)a.idx;
-            sp += __popc(pa);
-            if (pushB) myStack[sp + __popc(pb & before)] = ((uint32_t)b.lv << 28) | ((uint32_t)b.qq << 23) | (uint32_t)b.idx;
-            sp += __popc(pb);
-            nTests += (a.active && a.lv == 0) + (b.active && b.lv == 0);
-            nBoxTests += (a.active && a.lv > 0) + (b.active && b.lv > 0);
-            resolveHits(a);
-            resolveHits(b);
+        while (sp > 0 || nLeaf > 0) {
+            // a round pops up to eight pairs: two per 8-lane group, tested back to back so their loads overlap.  Point rounds run
+            // whenever two full slots of leaves are waiting (which keeps the leaf queue below 16 + 64 entries) or nothing else is left.
+            if (nLeaf >= 16 || sp == 0) {
+                const int take = min(8, nLeaf);
+                const bool activeA = g < take, activeB = g + 4 < take;
+                const uint32_t entryA = myLeaf[activeA ? nLeaf - 1 - g : 0];
+                const uint32_t entryB = myLeaf[activeB ? nLeaf - 5 - g : 0];
+                nLeaf -= take;
+                nTests += (int)activeA + (int)activeB;
+                const PointSlot a = testPoint(entryA, activeA);
+                const PointSlot b = testPoint(entryB, activeB);
+                resolveHit(a);
+                resolveHit(b);
+            } else {
+                const int take = min(8, sp);
+                const bool activeA = g < take, activeB = g + 4 < take;
+                const uint32_t entryA = myStack[activeA ? sp - 1 - g : 0];
+                const uint32_t entryB = myStack[activeB ? sp - 5 - g : 0];
+                sp -= take;
+                nBoxTests += (int)activeA + (int)activeB;
+                const BoxSlot a = testBox(entryA, activeA);
+                const BoxSlot b = testBox(entryB, activeB);
+                __syncwarp();                          // every lane has read its entries before the stack is overwritten
+                // passing boxes of level >= 2 go back to the stack, passing leaves (level 1) to the leaf queue
+                const bool leafA = a.pass && a.lv == 1, leafB = b.pass && b.lv == 1;
+                const bool pushA = a.pass && a.lv > 1, pushB = b.pass && b.lv > 1;
+                const uint32_t pa = __ballot_sync(0xffffffffu, pushA), pb = __ballot_sync(0xffffffffu, pushB);
+                const uint32_t la = __ballot_sync(0xffffffffu, leafA), lb = __ballot_sync(0xffffffffu, leafB);
+                if (pushA) myStack[sp + __popc(pa & before)] = ((uint32_t)a.lv << 28) | ((uint32_t)a.qq << 23) | (uint32_t)a.idx;
+                sp += __popc(pa);
+                if (pushB) myStack[sp + __popc(pb & before)] = ((uint32_t)b.lv << 28) | ((uint32_t)b.qq << 23) | (uint32_t)b.idx;
+                sp += __popc(pb);
+                if (leafA) myLeaf[nLeaf + __popc(la & before)] = ((uint32_t)a.qq << 23) | (uint32_t)a.idx;
+                nLeaf += __popc(la);
+                if (leafB) myLeaf[nLeaf + __popc(lb & before)] = ((uint32_t)b.qq << 23) | (uint32_t)b.idx;
+                nLeaf += __popc(lb);
+            }
             __syncwarp();
         }
     }

@@ -32,7 +32,7 @@ struct NcclApi {
     ncclResult_t (*getUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*commInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*allGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*allReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*reduceScatter)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*commDestroy)(ncclComm_t) = nullptr;
     bool ok = false;
 };
@@ -46,9 +46,9 @@ NcclApi& nccl() {
         a.getUniqueId = reinterpret_cast<decltype(a.getUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
         a.commInitRank = reinterpret_cast<decltype(a.commInitRank)>(dlsym(lib, "ncclCommInitRank"));
         a.allGather = reinterpret_cast<decltype(a.allGather)>(dlsym(lib, "ncclAllGather"));
-        a.allReduce = reinterpret_cast<decltype(a.allReduce)>(dlsym(lib, "ncclAllReduce"));
+        a.reduceScatter = reinterpret_cast<decltype(a.reduceScatter)>(dlsym(lib, "ncclReduceScatter"));
         a.commDestroy = reinterpret_cast<decltype(a.commDestroy)>(dlsym(lib, "ncclCommDestroy"));
-        a.ok = a.getUniqueId && a.commInitRank && a.allGather && a.allReduce && a.commDestroy;
+        a.ok = a.getUniqueId && a.commInitRank && a.allGather && a.reduceScatter && a.commDestroy;
         return a;
     }();
     return api;
@@ -396,9 +396,12 @@ void enqueue_step(wb_embedder* h, double learningRate) {
         h->launches += 1;
     }
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[5], s));
-    if (sharded) {   // every rank found the pairs of its own queries and added each pair's term to both rows: integer sum over the ranks
-        if (nccl().allReduce(h->forceRep, h->forceRep, (size_t)n * (4 * V + 2), ncclInt64, ncclSum, h->comm, s) != ncclSuccess)
-            throw std::runtime_error("ncclAllReduce (repulsion rows) failed");
+    if (sharded) {
+        // every rank found the pairs of its own queries and added each pair's term to both rows; a rank needs the totals of the
+        // vertices it owns only: integer reduce-scatter over the ranks, in place (exact, so the result does not depend on the ring)
+        const size_t seg = (size_t)h->rowsPerRank * (4 * V + 2);
+        if (nccl().reduceScatter(h->forceRep, h->forceRep + (size_t)h->rank * seg, seg, ncclInt64, ncclSum, h->comm, s) != ncclSuccess)
+            throw std::runtime_error("ncclReduceScatter (repulsion rows) failed");
         h->launches += 1;
     }
     wb::k_reduce_partials<<<3, 256, 0, s>>>(h->partialsRep, repWarps + h->numHeavy, 3, sums + K);
@@ -748,12 +751,17 @@ int wb_comm_init(wb_embedder* h, const char* id128, int32_t rank, int32_t world)
         h->forceBlocks = std::max(1, std::min(div_up(own, groupsPerBlock), 148 * 16));
         h->forceVertsPerBlock = std::max(groupsPerBlock, div_up(div_up(own, h->forceBlocks), groupsPerBlock) * groupsPerBlock);
         h->forceBlocks = std::max(1, div_up(own, h->forceVertsPerBlock));
-        h->obsBlocks = std::max(1, std::min(div_up(own, 256), 148 * 8));
+            h->obsBlocks = std::max(1, std::min(div_up(own, 256), 148 * 8));
         h->obsVertsPerBlock = std::max(256, div_up(div_up(own, h->obsBlocks), 256) * 256);
         h->obsBlocks = std::max(1, div_up(own, h->obsVertsPerBlock));
         // repulsion rows: blocks of kRepBlockChunks chunks of the sorted order dealt round-robin to the ranks, each rank's rows contiguous
         const int blocksPerRank = div_up(div_up(div_up(std::max(n, 1), 32), wb::kRepBlockChunks), world);
         h->repLayout = wb::RepLayout{world, rank, blocksPerRank * wb::kRepBlockChunks * 32};
+        // equal segments of rowsPerRank rows for the in-place reduce-scatter
+        cudaFree(h->forceRep);
+        h->forceRepBytes = (size_t)h->rowsPerRank * world * (4 * V + 2) * sizeof(long long);
+        h->forceRep = dalloc<long long>((size_t)h->rowsPerRank * world * (4 * V + 2));
+        WB_CUDA(cudaMemsetAsync(h->forceRep, 0, h->forceRepBytes, h->stream));
         h->gathered = dalloc<double>((size_t)world * h->sumsTotal);
         h->localSums = dalloc<double>(h->sumsTotal);
         WB_CUDA(cudaMemsetAsync(h->localSums, 0, sizeof(double) * h->sumsTotal, h->stream));
