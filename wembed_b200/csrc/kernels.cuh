@@ -33,7 +33,46 @@ struct TreeView {             // implicit 8-ary box hierarchy, structure-of-plan
     const float4* hi[kMaxLevels];   // hi[0] == lo[0] (points)
     const float* bound[kMaxLevels]; // min over the subtree of the pruning weight factor (iw of points)
     const int* ids;           // sorted position -> vertex id (-1 for padding)
+    // The same boxes once more, as array-of-blocks for the repulsion walk: a block = the 8 children of one node,
+    // [lo planes: V x 8 float4 | hi planes: V x 8 float4 | meta: 8 x BoxMeta], so all loads of a test share one address register.
+    // Blocks of all levels >= 1 live in one buffer; level l starts at blockOff[l]; block 0 is a null block nothing passes.
+    const float4* blk;
+    int blockOff[kMaxLevels];
 };
+
+// per-child record of a block (16 bytes, read with one 128-bit load)
+struct BoxMeta {
+    float bound;              // min over the subtree of the pruning weight factor
+    uint32_t childRef;        // level >= 2: block holding this node's children; level 1: kLeafFlag | leaf index
+    uint32_t endPos;          // one past the last sorted position of the subtree
+    uint32_t pad;
+};
+constexpr uint32_t kLeafFlag = 0x80000000u;
+__host__ __device__ constexpr int block_float4s(int V) { return (2 * V + 1) * kFan; }
+
+// initial state of the block buffer: coordinates far from everything, meta records all zero (endPos = 0: never passes)
+template <int V>
+__global__ void k_init_blocks(float4* __restrict__ blk, int64_t count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const bool meta = (int)(i % block_float4s(V)) >= 2 * V * kFan;
+    blk[i] = meta ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(kPadCoord, kPadCoord, kPadCoord, kPadCoord);
+}
+
+// writes node `idx` of level `lv` into its block; called by the 8 lanes (j = 0..7) that hold the node's reduced box
+template <int V>
+__device__ __forceinline__ void store_block_node(float4* __restrict__ blk, int blockOffLv, int blockOffBelow, int lv, int idx, int j,
+                                                 const float4 (&lo)[V], const float4 (&hi)[V], float bound) {
+    float4* b = blk + ((int64_t)blockOffLv + (idx >> kFanLog2)) * block_float4s(V) + (idx & (kFan - 1));
+#pragma unroll
+    for (int c = 0; c < V; ++c)
+        if (j == c) { b[c * kFan] = lo[c]; b[(V + c) * kFan] = hi[c]; }
+    if (j == kFan - 1) {
+        const uint32_t childRef = lv == 1 ? (kLeafFlag | (uint32_t)idx) : (uint32_t)(blockOffBelow + idx);
+        const uint32_t endPos = (uint32_t)min((int64_t)(idx + 1) << (kFanLog2 * lv), (int64_t)0x7fffffff);
+        b[2 * V * kFan] = make_float4(bound, __uint_as_float(childRef), __uint_as_float(endPos), 0.f);
+    }
+}
 
 struct ForceParams {
     float edgeLength;         // L
@@ -156,7 +195,7 @@ __global__ void __launch_bounds__(256) k_build_leaves(const float4* __restrict__
                                                       const int* __restrict__ order, int n, float4* __restrict__ pts,
                                                       int stride0, float* __restrict__ bound0, int* __restrict__ ids, int* __restrict__ invOrder,
                                                       float4* __restrict__ lo1, float4* __restrict__ hi1,
-                                                      float* __restrict__ bound1, int stride1) {
+                                                      float* __restrict__ bound1, int stride1, float4* __restrict__ blk, int blockOff1) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;   // sorted position
     const int leaf = i >> kFanLog2, j = i & (kFan - 1);
     const bool real = i < n;
@@ -189,6 +228,7 @@ __global__ void __launch_bounds__(256) k_build_leaves(const float4* __restrict__
         for (int c = 0; c < V; ++c)
             if (j == c) { lo1[(int64_t)c * stride1 + leaf] = lo[c]; hi1[(int64_t)c * stride1 + leaf] = hi[c]; }
         if (j == kFan - 1) bound1[leaf] = b;
+        store_block_node<V>(blk, blockOff1, 0, 1, leaf, j, lo, hi, b);
     }
 }
 
@@ -197,7 +237,8 @@ template <int V>
 __global__ void __launch_bounds__(256) k_build_level(const float4* __restrict__ cLo, const float4* __restrict__ cHi,
                                                      const float* __restrict__ cBound, int cCount, int cStride,
                                                      float4* __restrict__ pLo, float4* __restrict__ pHi,
-                                                     float* __restrict__ pBound, int pCount, int pStride) {
+                                                     float* __restrict__ pBound, int pCount, int pStride, float4* __restrict__ blk,
+                                                     int blockOffP, int blockOffC, int pLevel) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;   // child index
     const int parent = i >> kFanLog2, j = i & (kFan - 1);
     float4 lo[V], hi[V];
@@ -221,6 +262,7 @@ __global__ void __launch_bounds__(256) k_build_level(const float4* __restrict__ 
         for (int c = 0; c < V; ++c)
             if (j == c) { pLo[(int64_t)c * pStride + parent] = lo[c]; pHi[(int64_t)c * pStride + parent] = hi[c]; }
         if (j == kFan - 1) pBound[parent] = b;
+        store_block_node<V>(blk, blockOffP, blockOffC, pLevel, parent, j, lo, hi, b);
     }
 }
 
@@ -355,11 +397,11 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
                 int* __restrict__ chunkCounter, double* __restrict__ partials) {
     constexpr int RS = 4 * V + 2;                // integers per result row
     constexpr int WARPS = repulse_warps(V), STACK = 56 * kMaxLevels + 72;   // LIFO bound: <= 56 leftovers per level + one push of 64
-    __shared__ float4 sQ[WARPS][32][V];
-    __shared__ float sIw[WARPS][32];
-    __shared__ int sVert[WARPS][32];             // vertex id of each query
-    __shared__ uint32_t sStack[WARPS][STACK];    // (level << 28) | (query lane << 23) | node   (node < 2^23: n <= 6.7e7)
-    __shared__ uint32_t sLeaf[WARPS][80];        // leaves waiting for their point round: (query lane << 23) | leaf
+    constexpr int QROW = V + 1, BLK = block_float4s(V);
+    constexpr uint32_t kRefMask = 0x07ffffffu;   // low 27 bits of an entry: block (stack) or leaf (leaf queue); high 5 bits: query lane
+    __shared__ float4 sQ[WARPS][32][QROW];       // query row: V coordinate chunks + {iw, sorted position + 1, vertex id, -}
+    __shared__ uint32_t sStack[WARPS][8 + STACK];   // 8 null entries below the stack: a short pop reads them and nothing passes
+    __shared__ uint32_t sLeaf[WARPS][80];        // leaves waiting for their point round
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = lane & (kFan - 1), g = lane >> kFanLog2;
     // lanes that precede this one in child-major order (c, g)
     uint32_t before = 0u;
@@ -369,67 +411,70 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
         if (lc < c || (lc == c && lg < g)) before |= 1u << l;
     }
     float4* myQ = &sQ[warp][0][0];
-    float* myIw = &sIw[warp][0];
-    int* myVert = &sVert[warp][0];
-    uint32_t* myStack = &sStack[warp][0];
+    uint32_t* myStack = &sStack[warp][8];
     uint32_t* myLeaf = &sLeaf[warp][0];
+    if (lane < 8) sStack[warp][lane] = 0u;       // entry 0 = (query 0, null block)
+    const float4* myBlk = t.blk + c;             // lane c tests child c of every block
     const float L = fp.edgeLength;
     const uint32_t ltMask = (1u << lane) - 1u;
+    const uint32_t rootBlock = (uint32_t)t.blockOff[t.numLevels];
     // Work unit of a warp = queriesPerUnit (8, 16 or 32) consecutive rows of this rank's share of the sorted order.  Small units
     // keep the dynamic schedule balanced when a rank (or a small graph) has few queries per resident warp.
     const int numChunks = lay.segRows / queriesPerUnit;
-    int nPairs = 0, nTests = 0, nBoxTests = 0, qBase = 0;
+    int nPairs = 0, nTests = 0, boxSlots = 0;
 
-    // Box round: one (node, query) pair per 8-lane group and slot; lane c tests child box c (level lv >= 1) of the node.
-    struct BoxSlot { int lv, idx, qq; bool pass; };
-    auto testBox = [&](uint32_t entry, bool active) {
+    // Box round: one (block, query) pair per 8-lane group and slot; lane c tests child box c of the block.
+    struct BoxSlot { uint32_t entry, childRef; bool pass; };
+    auto testBox = [&](uint32_t entry) {
         BoxSlot r;
-        r.lv = active ? (int)(entry >> 28) - 1 : 1;
-        r.idx = active ? (int)(entry & 0x007fffffu) * kFan + c : 0;
-        r.qq = (int)((entry >> 23) & 31u);
+        r.entry = entry;
+        const float4* b = myBlk + (size_t)(entry & kRefMask) * BLK;
+        const float4* qrow = myQ + (entry >> 27) * QROW;
         float4 lo[V], hi[V], qv[V];
-        const int64_t st = t.stride[r.lv];
-        const float4* loP = t.lo[r.lv];
-        const float4* hiP = t.hi[r.lv];
 #pragma unroll
-        for (int k = 0; k < V; ++k) lo[k] = __ldg(loP + k * st + r.idx);
+        for (int k = 0; k < V; ++k) lo[k] = __ldg(b + k * kFan);
 #pragma unroll
-        for (int k = 0; k < V; ++k) hi[k] = __ldg(hiP + k * st + r.idx);
-        const float bnd = __ldg(t.bound[r.lv] + r.idx);
+        for (int k = 0; k < V; ++k) hi[k] = __ldg(b + (V + k) * kFan);
+        const float4 meta = __ldg(b + 2 * V * kFan);
 #pragma unroll
-        for (int k = 0; k < V; ++k) qv[k] = myQ[r.qq * V + k];
-        const float s = myIw[r.qq] * bnd;
+        for (int k = 0; k < V; ++k) qv[k] = qrow[k];
+        const float4 qm = qrow[V];
+        const float s = qm.x * meta.x;
         const float d2 = box_dist2<V>(qv, lo, hi);
-        // the child covers sorted positions [idx << 3 lv, (idx + 1) << 3 lv): keep it only if some of them lie behind the query,
-        // (idx + 1) << 3 lv > qpos + 1  <=>  idx >= (qpos + 1) >> 3 lv
-        r.pass = active && (d2 * s * s <= fp.pruneL2) && r.idx >= ((qBase + r.qq + 1) >> (kFanLog2 * r.lv));
+        r.childRef = __float_as_uint(meta.y);
+        // the child covers sorted positions [.., endPos): keep it only if some of them lie behind the query (endPos > qpos + 1);
+        // null and padding children have endPos = 0
+        r.pass = (d2 * s * s <= fp.pruneL2) && __float_as_uint(meta.z) > __float_as_uint(qm.y);
         return r;
     };
     // Point round: one (leaf, query) pair per 8-lane group and slot; lane c tests point c of the leaf with the exact predicate.
-    // A hit is resolved by the lane that found it: neighbour filter, then the term goes to the rows of both vertices
-    // (hits are rare - a handful per query - so this branch is cold).
-    struct PointSlot { int idx, qq; float d2, ws; bool hit; };
+    struct PointSlot { int idx; uint32_t qq; float d2, ws; bool hit; };
     auto testPoint = [&](uint32_t entry, bool active) {
         PointSlot r;
-        r.qq = (int)((entry >> 23) & 31u);
-        r.idx = active ? (int)(entry & 0x007fffffu) * kFan + c : 0;
+        r.qq = entry >> 27;
+        r.idx = active ? (int)(entry & kRefMask) * kFan + c : 0;
+        const float4* qrow = myQ + r.qq * QROW;
         float4 pu[V], qv[V];
 #pragma unroll
         for (int k = 0; k < V; ++k) pu[k] = __ldg(t.lo[0] + (int64_t)k * t.stride[0] + r.idx);
         const float iwu = __ldg(t.bound[0] + r.idx);
 #pragma unroll
-        for (int k = 0; k < V; ++k) qv[k] = myQ[r.qq * V + k];
-        r.ws = myIw[r.qq] * iwu;
+        for (int k = 0; k < V; ++k) qv[k] = qrow[k];
+        const float4 qm = qrow[V];
+        r.ws = qm.x * iwu;
         r.d2 = point_dist2<V>(qv, pu);
-        r.hit = active && r.idx > qBase + r.qq && r.d2 * r.ws * r.ws <= fp.pruneL2;
+        r.hit = active && (uint32_t)r.idx >= __float_as_uint(qm.y) && r.d2 * r.ws * r.ws <= fp.pruneL2;   // idx > qpos
         return r;
     };
+    // A hit is resolved by the lane that found it: exact predicate, neighbour filter, then the term goes to the rows of both
+    // vertices (hits are rare - a handful per query - so this branch is cold).
     auto resolveHit = [&](const PointSlot& r) {
         if (!r.hit) return;
         const float dist = sqrtf(r.d2), ws = r.ws;
         if (dist > 0.f && !(dist * ws <= L)) return;         // exact predicate; dist <= 0 is the coincident case
+        const float4* qrow = myQ + r.qq * QROW;
         const int u = __ldg(t.ids + r.idx);
-        const int v = myVert[r.qq];
+        const int v = (int)__float_as_uint(qrow[V].z);
         // pairs with a heavy vertex belong to that vertex' block (k_repulse_heavy)
         if ((heavySlot && __ldg(heavySlot + u) >= 0) || is_neighbor(col, __ldg(rowPtr + v), __ldg(rowPtr + v + 1), u)) return;
         long long* fv = forceRep + (int64_t)v * RS;
@@ -440,14 +485,14 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
             return;
         }
         if (fp.dim == 1) {                                   // unit vector exactly +-1
-            const long long f = to_fixed(copysignf(fp.repulsionScale * ws, myQ[r.qq * V].x - __ldg(t.lo[0] + r.idx).x), fp.fixForce);
+            const long long f = to_fixed(copysignf(fp.repulsionScale * ws, qrow[0].x - __ldg(t.lo[0] + r.idx).x), fp.fixForce);
             fixed_add(fv, f);
             fixed_add(fu, -f);
         } else {
             const float sc = fp.repulsionScale * ws / dist;
 #pragma unroll
             for (int k = 0; k < V; ++k) {
-                const float4 q = myQ[r.qq * V + k], pu = __ldg(t.lo[0] + (int64_t)k * t.stride[0] + r.idx);
+                const float4 q = qrow[k], pu = __ldg(t.lo[0] + (int64_t)k * t.stride[0] + r.idx);
                 const float e[4] = {sc * (q.x - pu.x), sc * (q.y - pu.y), sc * (q.z - pu.z), sc * (q.w - pu.w)};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -470,20 +515,21 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
         if (lane == 0) chunk = atomicAdd(chunkCounter, 1);
         chunk = __shfl_sync(0xffffffffu, chunk, 0);
         if (chunk >= numChunks) break;
-        qBase = lay.position(chunk * queriesPerUnit);         // sorted position of lane 0's query (a unit never straddles a block)
+        const int qBase = lay.position(chunk * queriesPerUnit);   // sorted position of lane 0's query (a unit never straddles a block)
         if (qBase >= n) continue;                             // padding of the last block
         const int qi = qBase + lane;
         bool valid = lane < queriesPerUnit && qi < n;
+        int vertex = valid ? __ldg(t.ids + qi) : 0;
         // heavy vertices (thousands of partners each) are walked by k_repulse_heavy, one block per vertex
-        if (valid && heavySlot && __ldg(heavySlot + __ldg(t.ids + qi)) >= 0) valid = false;
-        if (valid) {
+        if (valid && heavySlot && __ldg(heavySlot + vertex) >= 0) valid = false;
+        {
+            float4* row = myQ + lane * QROW;
 #pragma unroll
-            for (int k = 0; k < V; ++k) myQ[lane * V + k] = __ldg(t.lo[0] + (int64_t)k * t.stride[0] + qi);
-            myIw[lane] = __ldg(t.bound[0] + qi);
-            myVert[lane] = __ldg(t.ids + qi);
+            for (int k = 0; k < V; ++k) row[k] = valid ? __ldg(t.lo[0] + (int64_t)k * t.stride[0] + qi) : make_float4(0.f, 0.f, 0.f, 0.f);
+            row[V] = make_float4(valid ? __ldg(t.bound[0] + qi) : 1.f, __uint_as_float((uint32_t)qi + 1u), __uint_as_float((uint32_t)vertex), 0.f);
         }
         const uint32_t validMask = __ballot_sync(0xffffffffu, valid);
-        if (valid) myStack[__popc(validMask & ltMask)] = ((uint32_t)(t.numLevels + 1) << 28) | ((uint32_t)lane << 23);
+        if (valid) myStack[__popc(validMask & ltMask)] = ((uint32_t)lane << 27) | rootBlock;
         int sp = __popc(validMask), nLeaf = 0;
         __syncwarp();
         while (sp > 0 || nLeaf > 0) {
@@ -501,34 +547,36 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
                 resolveHit(a);
                 resolveHit(b);
             } else {
+                // a pop of fewer than eight pairs reads the null entries below the stack (they fail the position test)
+                const uint32_t entryA = myStack[sp - 1 - g];
+                const uint32_t entryB = myStack[sp - 5 - g];
                 const int take = min(8, sp);
-                const bool activeA = g < take, activeB = g + 4 < take;
-                const uint32_t entryA = myStack[activeA ? sp - 1 - g : 0];
-                const uint32_t entryB = myStack[activeB ? sp - 5 - g : 0];
                 sp -= take;
-                nBoxTests += (int)activeA + (int)activeB;
-                const BoxSlot a = testBox(entryA, activeA);
-                const BoxSlot b = testBox(entryB, activeB);
+                boxSlots += take;
+                const BoxSlot a = testBox(entryA);
+                const BoxSlot b = testBox(entryB);
                 __syncwarp();                          // every lane has read its entries before the stack is overwritten
-                // passing boxes of level >= 2 go back to the stack, passing leaves (level 1) to the leaf queue
-                const bool leafA = a.pass && a.lv == 1, leafB = b.pass && b.lv == 1;
-                const bool pushA = a.pass && a.lv > 1, pushB = b.pass && b.lv > 1;
-                const uint32_t pa = __ballot_sync(0xffffffffu, pushA), pb = __ballot_sync(0xffffffffu, pushB);
-                const uint32_t la = __ballot_sync(0xffffffffu, leafA), lb = __ballot_sync(0xffffffffu, leafB);
-                if (pushA) myStack[sp + __popc(pa & before)] = ((uint32_t)a.lv << 28) | ((uint32_t)a.qq << 23) | (uint32_t)a.idx;
-                sp += __popc(pa);
-                if (pushB) myStack[sp + __popc(pb & before)] = ((uint32_t)b.lv << 28) | ((uint32_t)b.qq << 23) | (uint32_t)b.idx;
-                sp += __popc(pb);
-                if (leafA) myLeaf[nLeaf + __popc(la & before)] = ((uint32_t)a.qq << 23) | (uint32_t)a.idx;
-                nLeaf += __popc(la);
-                if (leafB) myLeaf[nLeaf + __popc(lb & before)] = ((uint32_t)b.qq << 23) | (uint32_t)b.idx;
-                nLeaf += __popc(lb);
+                // passing boxes of level >= 2 go back to the stack (as their children's block), passing leaves to the leaf queue
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const BoxSlot& r = h == 0 ? a : b;
+                    const bool isLeaf = (r.childRef & kLeafFlag) != 0u;
+                    const uint32_t pm = __ballot_sync(0xffffffffu, r.pass), lm = __ballot_sync(0xffffffffu, isLeaf);
+                    const int rank = __popc((isLeaf ? (pm & lm) : (pm & ~lm)) & before);
+                    const uint32_t e = (r.entry & ~kRefMask) | (r.childRef & kRefMask);
+                    uint32_t* dst = isLeaf ? myLeaf + nLeaf : myStack + sp;
+                    if (r.pass) dst[rank] = e;
+                    const int leaves = __popc(pm & lm);
+                    nLeaf += leaves;
+                    sp += __popc(pm) - leaves;
+                }
             }
             __syncwarp();
         }
     }
-    // per-warp statistics (integers, so the order in which warps took chunks cannot change the reduced value)
-    double totalPairs = (double)nPairs, totalTests = (double)nTests, totalBoxTests = (double)nBoxTests;
+    // per-warp statistics (integers, so the order in which warps took chunks cannot change the reduced value);
+    // every box slot is 8 lane tests and all 32 lanes counted it: 8 / 32 per lane
+    double totalPairs = (double)nPairs, totalTests = (double)nTests, totalBoxTests = 0.25 * (double)boxSlots;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         totalPairs += __shfl_xor_sync(0xffffffffu, totalPairs, o);

@@ -118,6 +118,7 @@ struct wb_embedder {
     float4* lvlHi[wb::kMaxLevels] = {};
     float* lvlBound[wb::kMaxLevels] = {};
     int* ids = nullptr;
+    float4* blk = nullptr;                // array-of-blocks copy of the boxes (wb::TreeView::blk)
     wb::TreeView tree{};
 
     // reductions: sumsAll = [ force sums (2 + 4V) | repulsion counters (2) | observe sums (2) ]
@@ -167,7 +168,7 @@ void free_all(wb_embedder* h) {
     auto F = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
     F(h->rowPtr); F(h->col); F(h->x); F(h->xNew); F(h->mom1); F(h->mom2); F(h->forceRep); F(h->force);
     F(h->iw); F(h->invOrder); F(h->edgeWs); F(h->chunkCounter); F(h->hubVertex); F(h->hubSlot); F(h->hubForce); F(h->heavyVertex); F(h->heavySlot); F(h->keysIn); F(h->keysOut); F(h->valsIn); F(h->valsOut);
-    F(h->cubTemp); F(h->momentPartials); F(h->quant); F(h->ids);
+    F(h->cubTemp); F(h->momentPartials); F(h->quant); F(h->ids); F(h->blk);
     for (int l = 0; l < wb::kMaxLevels; ++l) { F(h->lvlLo[l]); if (l > 0) F(h->lvlHi[l]); F(h->lvlBound[l]); }
     F(h->partialsForce); F(h->partialsRep); F(h->partialsObs); F(h->sumsAll); F(h->gathered); F(h->localSums);
     if (h->comm) { nccl().commDestroy(h->comm); h->comm = nullptr; }
@@ -276,6 +277,14 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
         if (level >= wb::kMaxLevels - 1) throw wb::CudaError{cudaErrorInvalidValue, "graph too large for the index", __FILE__, __LINE__};
     }
     t.numLevels = level;
+    {   // array-of-blocks copy of levels >= 1 (block 0 = null block); padding nodes keep the fill value, which no query passes
+        int blocks = 1;
+        for (int l = 1; l <= level; ++l) { t.blockOff[l] = blocks; blocks += t.stride[l] / kFan; }
+        const size_t f4 = (size_t)blocks * wb::block_float4s(V);
+        h->blk = dalloc<float4>(f4);
+        WB_DISPATCH_V(V, wb::k_init_blocks<V><<<div_up(f4, 256), 256, 0, h->stream>>>(h->blk, (int64_t)f4));
+        t.blk = h->blk;
+    }
     h->ids = dalloc<int>(t.stride[0]);
     WB_CUDA(cudaMemsetAsync(h->ids, 0xff, sizeof(int) * t.stride[0], h->stream));
     t.ids = h->ids;
@@ -319,11 +328,11 @@ void enqueue_index(wb_embedder* h, const float* pointBound) {
     const wb::TreeView& t = h->tree;
     WB_DISPATCH_V(V, wb::k_build_leaves<V><<<div_up(t.stride[0], 256), 256, 0, s>>>(
                          h->x, pointBound, h->valsOut, n, h->lvlLo[0], t.stride[0], h->lvlBound[0], h->ids, h->invOrder, h->lvlLo[1], h->lvlHi[1],
-                         h->lvlBound[1], t.stride[1]));
+                         h->lvlBound[1], t.stride[1], h->blk, t.blockOff[1]));
     for (int l = 2; l <= t.numLevels; ++l) {
         WB_DISPATCH_V(V, wb::k_build_level<V><<<div_up((int64_t)t.count[l] * kFan, 256), 256, 0, s>>>(
                              h->lvlLo[l - 1], h->lvlHi[l - 1], h->lvlBound[l - 1], t.count[l - 1], t.stride[l - 1], h->lvlLo[l], h->lvlHi[l],
-                             h->lvlBound[l], t.count[l], t.stride[l]));
+                             h->lvlBound[l], t.count[l], t.stride[l], h->blk, t.blockOff[l], t.blockOff[l - 1], l));
     }
     h->launches += 5 + (t.numLevels - 1);
     WB_CUDA(cudaGetLastError());
