@@ -118,7 +118,7 @@ def measured_peak_gbs():
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures under profiles/ (c3, step 100 / 30)
-NCU_TRAFFIC = {"repel": 168.8e6 + 72.7e6, "attract_update": 410.5e6 + 103.5e6}
+NCU_TRAFFIC = {"repel": 211.3e6 + 45.2e6, "attract_update": 294.5e6 + 93.9e6}
 
 
 def algorithmic_bytes_per_step(n, m, d):
@@ -127,6 +127,7 @@ def algorithmic_bytes_per_step(n, m, d):
 
 
 def run_ours(args):
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries exactly one JSON line
     import torch
     import torch.distributed as dist
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -238,7 +239,7 @@ def run_ours(args):
         # sorted points + ids + iw read once, result rows [force | loss | coincident] (64-bit fixed point) written
         "repel": 4 * V4 * n + 8 * n + 8 * (V4 + 2) * n,
         # CSR col + per-edge pair weight, rowPtr, slot order, x, result rows (64-bit fixed point), m, v read; m, v, xNew written
-        "attract_update": 16 * m + 8 * n + 4 * V4 * n + 8 * (V4 + 2) * n + 8 * V4 * n + 12 * V4 * n,
+        "attract_update": 16 * m + 4 * n + 4 * V4 * n + 8 * (V4 + 2) * n + 8 * V4 * n + 12 * V4 * n,
         # x read twice (moments, keys), key/value sort passes, sorted planes + boxes written
         "index": 2 * 4 * V4 * n + 4 * 16 * n + 4 * V4 * n * 2 + 8 * n,
         "recentre_observe": 3 * 4 * V4 * n,
@@ -265,8 +266,9 @@ def run_ours(args):
         "phases_ms": ph,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_TRAFFIC.get(dom), "peak_source": peak_src, "algorithmic_bytes": dom_bytes,
-                     "note": ("the dominant kernel (k_repulse_pairs, exact radius search in d dimensions) is bound by instruction issue, "
-                              "not by HBM: ncu shows DRAM < 1 % of peak, L2 hit 99.5 %, issue slots 73 % busy (profiles/). The HBM-bound "
+                     "note": ("the dominant kernel (k_repulse_pairs, exact radius search in d dimensions) is bound by the SM's load/store data path and "
+                              "instruction issue, not by HBM: ncu shows DRAM < 1 % of peak, L2 hit 99.3 %, L1 data-pipe wavefronts 84 %, "
+                              "issue slots 69 % busy (profiles/r1_summary.md). The HBM-bound "
                               "kernels are listed in `kernels`; `fused_step_kernel` is north_star's attraction + optimizer kernel."),
                      "kernels": rooflines, "fused_step_kernel": rooflines["attract_update"],
                      "whole_step": {"algorithmic_bytes": bytes_step, "achieved": bytes_step / (ph["total"] * 1e-3) / 1e9,
