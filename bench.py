@@ -55,20 +55,21 @@ def make_workload(name, rank=0, world=1):
     from wembed_b200.datasets import degree_weights, geometric_graph, heavy_tailed_graph, initial_coordinates
     n, deg, d, family = WORKLOADS[name]
     seed = 42         # every rank builds the same graph: at N > 1 it is sharded by vertex range (strong scaling)
-    cache = os.path.join(ROOT, "gpurun_out", f"_wl_{name}_{seed}.npy")
+    cache = os.path.join("/tmp", f"wembed_wl_{name}_{seed}.npy")
+    if world > 1 and rank != 0:            # one generator per box: the other ranks wait for rank 0's file
+        while not os.path.exists(cache):
+            time.sleep(0.2)
     if os.path.exists(cache):
         edges = np.load(cache)
     else:
         edges = geometric_graph(n, deg, seed)[0] if family == "geometric" else heavy_tailed_graph(n, deg, seed=seed)[0]
-        if rank == 0:
-            try:
-                os.makedirs(os.path.dirname(cache), exist_ok=True)
-                tmp = cache + f".tmp{os.getpid()}.npy"
-                np.save(tmp, edges)
-                os.replace(tmp, cache)      # atomic: other ranks either see the whole file or none
-            except OSError:
-                pass
-    rp, col = cabi.csr_from_edges(n, edges)
+        if world > 1:
+            tmp = cache + f".tmp{os.getpid()}.npy"
+            np.save(tmp, edges)
+            os.replace(tmp, cache)          # atomic: other ranks either see the whole file or none
+    from wembed_b200 import datagen
+    csr = datagen.csr_canonical(n, edges)   # generator output is unique, sorted, src < dst
+    rp, col = csr if csr is not None else cabi.csr_from_edges(n, edges)
     w = degree_weights(n, edges, d)
     x0 = initial_coordinates(n, d, seed=1234)
     return dict(name=name, n=n, d=d, m=len(edges), edges=edges, row_ptr=rp, col=col, weights=w, x0=x0)

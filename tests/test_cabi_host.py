@@ -110,3 +110,20 @@ def test_datasets_shapes():
     assert abs(dw.sum() - 20000) < 1e-6
     x = initial_coordinates(100, 3)
     assert (x.astype(np.float32) == x).all() and x.max() < 100 ** (1 / 3) + 1e-6
+
+
+def test_datagen_helper_matches_numpy_paths():
+    """The C++ workload helper (bench / test infrastructure) returns exactly what the numpy code paths return."""
+    from wembed_b200 import cabi, datagen
+    from wembed_b200.datasets import _pairs_within
+    rng = np.random.default_rng(5)
+    for n, deg in ((1, 10), (50, 4), (20_000, 10), (5_000, 40)):
+        pts = rng.random((n, 2)) * np.sqrt(n)
+        r = float(np.sqrt(deg / np.pi))
+        a, b = datagen.pairs_within(pts, r), _pairs_within(pts, r)
+        assert a.dtype == b.dtype and a.shape == b.shape and (a == b).all()
+        rp, col = datagen.csr_canonical(n, a)
+        rp2, col2 = cabi.csr_from_edges(n, a)
+        assert (rp == rp2).all() and (col == col2).all()
+    assert datagen.csr_canonical(3, np.asarray([[1, 0]], np.int32)) is None          # src > dst: not canonical
+    assert datagen.csr_canonical(3, np.asarray([[0, 1], [0, 1]], np.int32)) is None  # duplicate
