@@ -111,6 +111,20 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+class native_stdout_to_stderr:
+    """The reference's C++ logs warnings with std::cout; stdout of this script carries exactly one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -289,13 +303,14 @@ def cpu_baseline(wl, x_start, iteration):
     oracle.build("port")
     n, d, m = wl["n"], wl["d"], wl["m"]
     cores = os.cpu_count() or 1
-    cpu = oracle.CpuEmbedder("port", wl["edges"], n=n, embeddingDimension=d, init_state=False, numThreads=cores)
-    cpu.set_weights(wl["weights"])
-    cpu.set_coordinates(x_start)
-    t0 = time.perf_counter()
-    cpu.step()
-    dt = time.perf_counter() - t0
-    cpu.close()
+    with native_stdout_to_stderr():
+        cpu = oracle.CpuEmbedder("port", wl["edges"], n=n, embeddingDimension=d, init_state=False, numThreads=cores)
+        cpu.set_weights(wl["weights"])
+        cpu.set_coordinates(x_start)
+        t0 = time.perf_counter()
+        cpu.step()
+        dt = time.perf_counter() - t0
+        cpu.close()
     return {"value": 2.0 * m / dt, "unit": "directed-edge force updates/s", "steps_per_s": 1.0 / dt, "cores": cores, "kind": "port",
             "sample": f"1 step of the same workload from the device state after {iteration} steps (oracle/wembed_port.cpp, OpenMP, fp64)"}
 
@@ -314,15 +329,16 @@ def run_reference(args):
     n = min(n_full, 20_000 if kind == "reference" else 100_000)
     edges = geometric_graph(n, deg, 42)[0] if family == "geometric" else heavy_tailed_graph(n, deg, seed=42)[0]
     cores = os.cpu_count() or 1
-    cpu = oracle.CpuEmbedder("ref" if kind == "reference" else "port", edges, n=n, embeddingDimension=d, init_state=False, numThreads=cores)
-    cpu.set_weights(degree_weights(n, edges, d))
-    cpu.set_coordinates(initial_coordinates(n, d, seed=1234))
-    for _ in range(args.warmup):
-        cpu.step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu.step()
-    dt = time.perf_counter() - t0
+    with native_stdout_to_stderr():
+        cpu = oracle.CpuEmbedder("ref" if kind == "reference" else "port", edges, n=n, embeddingDimension=d, init_state=False, numThreads=cores)
+        cpu.set_weights(degree_weights(n, edges, d))
+        cpu.set_coordinates(initial_coordinates(n, d, seed=1234))
+        for _ in range(args.warmup):
+            cpu.step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cpu.step()
+        dt = time.perf_counter() - t0
     m = len(edges)
     value = 2.0 * m * args.steps / dt
     sample = (f"{family} graph n={n} m={m} d={d} (same generator and options as the workload, smaller n: the reference's SNN index "
