@@ -159,7 +159,7 @@ int wb_query_candidates(wb_embedder* h, int32_t nq, const int32_t* queries, int6
                         int32_t* out_ids, int64_t cap);
 
 /* Device time (ms, CUDA events) of each phase of the most recent wb_step:
- * [0] index  [1] attract + optimizer (fused)  [2] repel (kernel + row all-gather)  [3] row all-gather of a sharded run
+ * [0] index  [1] attract + optimizer (fused)  [2] repel (kernels + row reduce-scatter)  [3] row reduce-scatter of a sharded run
  * [4] recentre+observe  [5] total.
  * Mirrors the util::Timer keys of WembedEmbedder.cpp:28-58. Requires wb_enable_timing(h,1). */
 int wb_enable_timing(wb_embedder* h, int enable);
@@ -170,10 +170,12 @@ int wb_get_phase_times(wb_embedder* h, double* ms6);
 /*
  * One process (or thread) per GPU creates the SAME problem (same CSR, weights, coordinates) on its device and then
  * joins a communicator: rank 0 calls wb_comm_unique_id and ships the 128 bytes to the other ranks by any means
- * (bench.py uses torch.distributed), every rank calls wb_comm_init.  From then on wb_step computes the forces and
+ * (bench.py uses torch.distributed), every rank calls wb_comm_init.  From then on wb_step walks the repulsion queries of
+ * this rank's blocks of the sorted order (the integer result rows are reduce-scattered), and computes the attraction and
  * the optimizer update only for the vertices [rank * ceil(n / world), ...) it owns; positions stay replicated: the
  * owners' updated rows are all-gathered (NCCL over NVLink) at the end of every step, the scalar sums (losses,
- * centroid, displacement) are all-gathered and added in rank order, so all ranks return identical statistics.
+ * centroid, displacement) are all-gathered and added in rank order, so all ranks return identical statistics and the
+ * sharded step is bit-identical to the single-GPU step.
  * The reference has no distributed code; this is the multi-GPU form of its OpenMP `parallel for` over vertices
  * (WembedEmbedder.cpp:262,279), every vertex still being written by exactly one owner.
  */
