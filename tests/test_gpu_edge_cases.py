@@ -119,3 +119,34 @@ def test_small_graph_reaches_zero_loss(device_lib):
     iters, st = run_to_convergence(dev, {})
     assert st["loss_attract"] + st["loss_repel"] == 0.0
     assert 0.5 * int(g["iterations"]) <= iters <= 2.0 * int(g["iterations"]), (iters, int(g["iterations"]))
+
+
+@pytest.mark.parametrize("d,lo,hi,rep", [(2, 1e-3, 1e3, 1.0), (1, 1e-2, 1e2, 1.0), (3, 1e-4, 1.0, 250.0), (8, 1.0, 1e6, 1e-3)])
+def test_wide_weight_ranges_fixed_point_rows(device_lib, port_lib, d, lo, hi, rep):
+    """The repulsion rows are 64-bit fixed point with a scale derived from the weights and repulsionScale
+    (wb_set_weights): forces and losses must keep the 1e-5 parity for weight ranges of six decades."""
+    n = 3000
+    rng = np.random.default_rng(11)
+    edges = np.asarray([(i, (i + 1) % n) for i in range(n)] + [(i, (i + 17) % n) for i in range(n)], np.int32)
+    w = np.exp(rng.uniform(np.log(lo), np.log(hi), n))
+    side = 3.0 * float(np.median(w)) ** (2.0 / d) * n ** (1.0 / d) / 4.0     # a few partners per vertex at the median radius
+    x0 = (rng.random((n, d)) * max(side, 1.0)).astype(np.float32).astype(np.float64)
+    rp, col = device_lib.csr_from_edges(n, edges)
+    cpu = oracle.CpuEmbedder("port", edges, n=n, embeddingDimension=d, init_state=False, repulsionScale=rep)
+    dev = device_lib.DeviceEmbedder(rp, col, embedding_dimension=d, keep_forces=1, repulsion_scale=rep)
+    for e in (cpu, dev):
+        e.set_weights(w)
+        e.set_coordinates(x0)
+    cpu.step()
+    st = dev.step(lr_exponential(1))
+    cs = cpu.stats()
+    fr, fd = cpu.forces(), dev.forces()
+    from helpers import near_threshold_vertices
+    ok = ~near_threshold_vertices(x0, w, rp, col)
+    assert ok.mean() > 0.95
+    assert cs["num_rep_pairs"] > 0
+    assert np.abs(fr[ok] - fd[ok]).max() <= 1e-5 * np.abs(fr).max()
+    assert abs(st["num_repulsion_pairs"] - cs["num_rep_pairs"]) <= 2 * (~ok).sum()
+    if ok.all():
+        np.testing.assert_allclose(st["loss_repel"], cs["loss_repel"], rtol=1e-5)
+        np.testing.assert_allclose(st["loss_attract"], cs["loss_attract"], rtol=1e-5)
