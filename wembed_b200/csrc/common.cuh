@@ -46,6 +46,14 @@ struct CudaError {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float sq(float a) { return a * a; }
 
+// Single-instruction special functions (MUFU, relative error <= 2^-22): used where the result feeds fp32 terms whose own rounding
+// is of the same size; IEEE sqrtf / division cost ~12 instructions and a branch each.
+// The .ftz forms are one MUFU without the subnormal pre-scaling; callers must keep subnormal arguments away from them.
+__device__ __forceinline__ float rsqrt_approx(float a) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+__device__ __forceinline__ float sqrt_approx(float a) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+__device__ __forceinline__ float rcp_approx(float a) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+constexpr float kFltMin = 1.17549435e-38f;
+
 // squared distance between a point q (V chunks in registers) and the box [lo, hi] (lo == hi for a point)
 template <int V>
 __device__ __forceinline__ float box_dist2(const float4 (&q)[V], const float4 (&lo)[V], const float4 (&hi)[V]) {

@@ -782,10 +782,19 @@ __global__ void __launch_bounds__(256) k_attract_hubs(const float4* __restrict__
     block_sum<K, 256>(vals, redBuf, hubForce + (int64_t)blockIdx.x * K);
 }
 
+#ifndef WB_ATTRACT_FAST
+#define WB_ATTRACT_FAST 1          // 0: IEEE sqrtf / divisions behind per-edge branches (the round-1 kernel, kept for A/B builds)
+#endif
+#ifndef WB_ATTRACT_BATCH
+#define WB_ATTRACT_BATCH 4         // neighbour rows in flight per lane (measured: 2, 6 and 8 are slower, profiles/r1_summary.md)
+#endif
+#ifndef WB_ATTRACT_MINBLOCKS
+#define WB_ATTRACT_MINBLOCKS 4
+#endif
 // The north_star's "fused step kernel".  Each block owns a fixed contiguous vertex range and emits
 // {lossA, lossR, sum_v xnew[v][k]} for the deterministic reducer.
 template <int V>
-__global__ void __launch_bounds__(256, 4) k_attract_update(const float4* __restrict__ x, const float* __restrict__ edgeWs,
+__global__ void __launch_bounds__(256, WB_ATTRACT_MINBLOCKS) k_attract_update(const float4* __restrict__ x, const float* __restrict__ edgeWs,
                                                         const int* __restrict__ rowPtr, const int* __restrict__ col, int rangeBegin,
                                                         int rangeEnd, int vertsPerBlock, const ForceParams fp,
                                                         const long long* __restrict__ forceRep, const int* __restrict__ hubSlot,
@@ -825,31 +834,52 @@ __global__ void __launch_bounds__(256, 4) k_attract_update(const float4* __restr
         int len = end - e;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
-        for (int i = 0; i < len; i += 4) {                         // neighbours in ascending order, four rows in flight
-            bool has[4];
-            int u[4];
-            float wsE[4], dd[4];
-            float4 r[4];
+        constexpr int B = WB_ATTRACT_BATCH;
+        for (int i = 0; i < len; i += B) {                         // neighbours in ascending order, B rows in flight
+            bool has[B];
+            int u[B];
+            float wsE[B], dd[B];
+            float4 r[B];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < B; ++j) {
                 has[j] = e + i + j < end;
                 u[j] = has[j] ? __ldg(col + e + i + j) : 0;
                 wsE[j] = has[j] ? __ldg(edgeWs + e + i + j) : 0.f;
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) r[j] = (has[j] && chunkLane) ? __ldg(x + (int64_t)u[j] * V + c) : xv;
+            for (int j = 0; j < B; ++j) r[j] = (has[j] && chunkLane) ? __ldg(x + (int64_t)u[j] * V + c) : xv;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dd[j] = chunkLane ? chunk_dist2(r[j], xv) : 0.f;
+            for (int j = 0; j < B; ++j) dd[j] = chunkLane ? chunk_dist2(r[j], xv) : 0.f;
 #pragma unroll
             for (int o = G / 2; o > 0; o >>= 1) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dd[j] += __shfl_xor_sync(0xffffffffu, dd[j], o);
+                for (int j = 0; j < B; ++j) dd[j] += __shfl_xor_sync(0xffffffffu, dd[j], o);
             }
-            // the four terms of the batch are added in fp32 (their sum carries the same relative error as each term), the batch
-            // sum goes into the double accumulator: one conversion + one DADD per component per four edges
+            // the terms of a batch are added in fp32 (their sum carries the same relative error as each term), the batch
+            // sum goes into the double accumulator: one conversion + one DADD per component per batch
             float bx = 0.f, by = 0.f, bz = 0.f, bw = 0.f, bl = 0.f;
+#if WB_ATTRACT_FAST
+            // Branch-free pair arithmetic with single-instruction rsqrt / rcp (relative error <= 2^-22, the size of the fp32
+            // rounding of the terms themselves): ~30 instructions per edge instead of ~85 with IEEE sqrtf and two IEEE divisions
+            // behind per-edge branches.  One-dimensional embeddings keep the exact +-1 unit vectors below.
+            if (V > 1 || fp.dim > 1) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < B; ++j) {
+                    // squared distances below FLT_MIN (dist < 1.1e-19) are neither coincident (that is dist == 0 exactly, as with
+                    // sqrtf) nor can they exceed the edge length: they contribute nothing and stay away from the .ftz rsqrt
+                    const float inv = rsqrt_approx(dd[j]);
+                    const float dist = dd[j] * inv;
+                    nCoincident += (int)(has[j] && dd[j] == 0.f);                        // :150-155, resolved below
+                    const bool act = has[j] && dd[j] >= kFltMin && dist * wsE[j] > L;     // :163-168
+                    const float sc = act ? fp.attractionScale * wsE[j] * inv : 0.f;
+                    bx = fmaf(sc, r[j].x - xv.x, bx); by = fmaf(sc, r[j].y - xv.y, by);
+                    bz = fmaf(sc, r[j].z - xv.z, bz); bw = fmaf(sc, r[j].w - xv.w, bw);
+                    bl += act ? fmaf(-L, rcp_approx(wsE[j]), dist) : 0.f;
+                }
+            } else
+#endif
+#pragma unroll
+            for (int j = 0; j < B; ++j) {
                 if (!has[j]) continue;
                 const float dist = sqrtf(dd[j]);
                 if (dist <= 0.f) { ++nCoincident; continue; }           // :150-155, resolved below
@@ -921,7 +951,11 @@ __global__ void __launch_bounds__(256, 4) k_attract_update(const float4* __restr
                     me[i] = fp.beta1 * me[i] + (1.f - fp.beta1) * fe[i];
                     se[i] = fp.beta2 * se[i] + (1.f - fp.beta2) * fe[i] * fe[i];
                     const float mHat = me[i] * fp.invBias1, vHat = se[i] * fp.invBias2;
+#if WB_ATTRACT_FAST
+                    xe[i] = fmaf(fp.lr * mHat, rcp_approx(sqrt_approx(vHat) + fp.eps), xe[i]);
+#else
                     xe[i] += fp.lr * mHat / (sqrtf(vHat) + fp.eps);
+#endif
                 }
                 mom1[at] = make_float4(me[0], me[1], me[2], me[3]);
                 mom2[at] = make_float4(se[0], se[1], se[2], se[3]);
