@@ -12,6 +12,8 @@
 // every reduction has a fixed shape, so a step is bit-reproducible from run to run
 // (tests/TestDeterminism.cpp protocol).  V = number of float4 chunks per position row.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "mt19937.cuh"
 
@@ -23,6 +25,8 @@ namespace wb {
 struct QuantParams {          // Morton quantisation frame, rebuilt every step on the device
     float lo[kMaxDim];
     float invCell[kMaxDim];
+    float centre[kMaxDim];    // per-dimension mean: origin of the half-precision copy of the boxes (0 for padding dimensions)
+    int halfBoxes;            // 1: this step's repulsion walk tests the half-precision boxes (layout narrow enough, see k_quant_params)
 };
 
 struct TreeView {             // implicit 8-ary box hierarchy, structure-of-planes (see common.cuh)
@@ -38,6 +42,10 @@ struct TreeView {             // implicit 8-ary box hierarchy, structure-of-plan
     // Blocks of all levels >= 1 live in one buffer; level l starts at blockOff[l]; block 0 is a null block nothing passes.
     const float4* blk;
     int blockOff[kMaxLevels];
+    // and once more in half precision (same block numbering), relative to QuantParams::centre, rounded outwards:
+    // [lo: HV x 8 chunks of 8 halves | hi: HV x 8 | meta: 8 x BoxMeta], HV = ceil(V / 2); see k_repulse_pairs
+    const float4* blkH;
+    const QuantParams* quant;
 };
 
 // per-child record of a block (16 bytes, read with one 128-bit load)
@@ -49,6 +57,8 @@ struct BoxMeta {
 };
 constexpr uint32_t kLeafFlag = 0x80000000u;
 __host__ __device__ constexpr int block_float4s(int V) { return (2 * V + 1) * kFan; }
+__host__ __device__ constexpr int half_chunks(int V) { return (V + 1) / 2; }            // 16-byte chunks of 8 halves per row
+__host__ __device__ constexpr int half_block_float4s(int V) { return (2 * half_chunks(V) + 1) * kFan; }
 
 // initial state of the block buffer: coordinates far from everything, meta records all zero (endPos = 0: never passes)
 template <int V>
@@ -61,17 +71,53 @@ __global__ void k_init_blocks(float4* __restrict__ blk, int64_t count) {
 
 // writes node `idx` of level `lv` into its block; called by the 8 lanes (j = 0..7) that hold the node's reduced box
 template <int V>
-__device__ __forceinline__ void store_block_node(float4* __restrict__ blk, int blockOffLv, int blockOffBelow, int lv, int idx, int j,
+__device__ __forceinline__ void store_block_node(float4* __restrict__ blk, float4* __restrict__ blkH, const QuantParams* __restrict__ qp,
+                                                 int blockOffLv, int blockOffBelow, int lv, int idx, int j,
                                                  const float4 (&lo)[V], const float4 (&hi)[V], float bound) {
     float4* b = blk + ((int64_t)blockOffLv + (idx >> kFanLog2)) * block_float4s(V) + (idx & (kFan - 1));
 #pragma unroll
     for (int c = 0; c < V; ++c)
         if (j == c) { b[c * kFan] = lo[c]; b[(V + c) * kFan] = hi[c]; }
-    if (j == kFan - 1) {
-        const uint32_t childRef = lv == 1 ? (kLeafFlag | (uint32_t)idx) : (uint32_t)(blockOffBelow + idx);
-        const uint32_t endPos = (uint32_t)min((int64_t)(idx + 1) << (kFanLog2 * lv), (int64_t)0x7fffffff);
-        b[2 * V * kFan] = make_float4(bound, __uint_as_float(childRef), __uint_as_float(endPos), 0.f);
+    const uint32_t childRef = lv == 1 ? (kLeafFlag | (uint32_t)idx) : (uint32_t)(blockOffBelow + idx);
+    const uint32_t endPos = (uint32_t)min((int64_t)(idx + 1) << (kFanLog2 * lv), (int64_t)0x7fffffff);
+    const float4 meta = make_float4(bound, __uint_as_float(childRef), __uint_as_float(endPos), 0.f);
+    if (j == kFan - 1) b[2 * V * kFan] = meta;
+    // half-precision copy: the box relative to the frame centre, lo rounded down and hi rounded up (subtraction and conversion both
+    // directed), so it contains the fp32 box; lanes 0..HV-1 pack the lo chunks, lanes HV..2HV-1 the hi chunks
+    constexpr int HV = half_chunks(V);
+    float4* bh = blkH + ((int64_t)blockOffLv + (idx >> kFanLog2)) * half_block_float4s(V) + (idx & (kFan - 1));
+    if (j < 2 * HV) {
+        const bool up = j >= HV;
+        const int k = up ? j - HV : j;
+        __half2 h[4];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float e[4] = {0.f, 0.f, 0.f, 0.f}, ctr[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < V; ++c) {
+                if (c == 2 * k + half) {
+                    const float4 src = up ? hi[c] : lo[c];
+                    e[0] = src.x; e[1] = src.y; e[2] = src.z; e[3] = src.w;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) ctr[i] = qp->centre[4 * c + i];
+                }
+            }
+            if (up) {
+                h[2 * half] = __halves2half2(__float2half_ru(__fsub_ru(e[0], ctr[0])), __float2half_ru(__fsub_ru(e[1], ctr[1])));
+                h[2 * half + 1] = __halves2half2(__float2half_ru(__fsub_ru(e[2], ctr[2])), __float2half_ru(__fsub_ru(e[3], ctr[3])));
+            } else {
+                h[2 * half] = __halves2half2(__float2half_rd(__fsub_rd(e[0], ctr[0])), __float2half_rd(__fsub_rd(e[1], ctr[1])));
+                h[2 * half + 1] = __halves2half2(__float2half_rd(__fsub_rd(e[2], ctr[2])), __float2half_rd(__fsub_rd(e[3], ctr[3])));
+            }
+        }
+        float4 packed;
+        packed.x = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h[0]));
+        packed.y = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h[1]));
+        packed.z = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h[2]));
+        packed.w = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h[3]));
+        bh[j * kFan] = packed;
     }
+    if (j == kFan - 1) bh[2 * HV * kFan] = meta;
 }
 
 struct ForceParams {
@@ -136,8 +182,11 @@ __global__ void __launch_bounds__(256) k_moments(const float4* __restrict__ x, i
 
 // Index, stage 2: quantisation frame = [mean - 4 sd, mean + 4 sd] clipped to [min, max] per dimension, so a few
 // far outliers do not eat the key resolution of the bulk.  Only locality depends on this frame, never results.
+// It also decides whether this step's repulsion walk may test the half-precision copy of the boxes: the rounding of a
+// centred coordinate to half precision is ~sd * 2^-11, which has to stay small against the smallest interaction radius or the
+// outward-rounded boxes stop pruning; halfSigmaLimit = that radius times a constant (wb_set_weights), <= 0 disables, +inf forces.
 __global__ void __launch_bounds__(256) k_quant_params(const float* __restrict__ partial, int numBlocks, int n, int dim, int bits,
-                                                      QuantParams* __restrict__ qp) {
+                                                      float halfSigmaLimit, QuantParams* __restrict__ qp) {
     // thread (k, j) = (dimension, slice): slice j folds blocks j, j+8, .. in order; the 8 slices are combined in slice order
     __shared__ float sMin[8][kMaxDim], sMax[8][kMaxDim];
     __shared__ double sS1[8][kMaxDim], sS2[8][kMaxDim];
@@ -150,16 +199,31 @@ __global__ void __launch_bounds__(256) k_quant_params(const float* __restrict__ 
         }
     }
     sMin[j][k] = mn; sMax[j][k] = mx; sS1[j][k] = s1; sS2[j][k] = s2;
+    __shared__ float sSd[kMaxDim];
     __syncthreads();
-    if (j != 0 || k >= dim) return;
-    for (int t = 1; t < 8; ++t) { mn = fminf(mn, sMin[t][k]); mx = fmaxf(mx, sMax[t][k]); s1 += sS1[t][k]; s2 += sS2[t][k]; }
-    const double mean = s1 / n;
-    const double var = fmax(0.0, s2 / n - mean * mean);
-    const float sd = (float)sqrt(var);
-    float lo = fmaxf(mn, (float)mean - 4.f * sd), hi = fminf(mx, (float)mean + 4.f * sd);
-    if (!(hi > lo)) hi = lo + 1.f;
-    qp->lo[k] = lo;
-    qp->invCell[k] = (float)(1u << bits) / (hi - lo);
+    if (j == 0) {
+        float sd = 0.f;
+        if (k < dim) {
+            for (int t = 1; t < 8; ++t) { mn = fminf(mn, sMin[t][k]); mx = fmaxf(mx, sMax[t][k]); s1 += sS1[t][k]; s2 += sS2[t][k]; }
+            const double mean = s1 / n;
+            const double var = fmax(0.0, s2 / n - mean * mean);
+            sd = (float)sqrt(var);
+            float lo = fmaxf(mn, (float)mean - 4.f * sd), hi = fminf(mx, (float)mean + 4.f * sd);
+            if (!(hi > lo)) hi = lo + 1.f;
+            qp->lo[k] = lo;
+            qp->invCell[k] = (float)(1u << bits) / (hi - lo);
+            qp->centre[k] = (float)mean;
+        } else {
+            qp->centre[k] = 0.f;
+        }
+        sSd[k] = sd;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float sdMax = 0.f;
+        for (int t = 0; t < dim; ++t) sdMax = fmaxf(sdMax, sSd[t]);
+        qp->halfBoxes = (sdMax <= halfSigmaLimit) ? 1 : 0;      // false for NaN layouts as well
+    }
 }
 
 // Index, stage 3: Morton key of every vertex (bit b of dimension k -> key bit b*dim + k).
@@ -195,7 +259,8 @@ __global__ void __launch_bounds__(256) k_build_leaves(const float4* __restrict__
                                                       const int* __restrict__ order, int n, float4* __restrict__ pts,
                                                       int stride0, float* __restrict__ bound0, int* __restrict__ ids, int* __restrict__ invOrder,
                                                       float4* __restrict__ lo1, float4* __restrict__ hi1,
-                                                      float* __restrict__ bound1, int stride1, float4* __restrict__ blk, int blockOff1) {
+                                                      float* __restrict__ bound1, int stride1, float4* __restrict__ blk, int blockOff1,
+                                                      float4* __restrict__ blkH, const QuantParams* __restrict__ qp) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;   // sorted position
     const int leaf = i >> kFanLog2, j = i & (kFan - 1);
     const bool real = i < n;
@@ -228,7 +293,7 @@ __global__ void __launch_bounds__(256) k_build_leaves(const float4* __restrict__
         for (int c = 0; c < V; ++c)
             if (j == c) { lo1[(int64_t)c * stride1 + leaf] = lo[c]; hi1[(int64_t)c * stride1 + leaf] = hi[c]; }
         if (j == kFan - 1) bound1[leaf] = b;
-        store_block_node<V>(blk, blockOff1, 0, 1, leaf, j, lo, hi, b);
+        store_block_node<V>(blk, blkH, qp, blockOff1, 0, 1, leaf, j, lo, hi, b);
     }
 }
 
@@ -238,7 +303,8 @@ __global__ void __launch_bounds__(256) k_build_level(const float4* __restrict__ 
                                                      const float* __restrict__ cBound, int cCount, int cStride,
                                                      float4* __restrict__ pLo, float4* __restrict__ pHi,
                                                      float* __restrict__ pBound, int pCount, int pStride, float4* __restrict__ blk,
-                                                     int blockOffP, int blockOffC, int pLevel) {
+                                                     int blockOffP, int blockOffC, int pLevel, float4* __restrict__ blkH,
+                                                     const QuantParams* __restrict__ qp) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;   // child index
     const int parent = i >> kFanLog2, j = i & (kFan - 1);
     float4 lo[V], hi[V];
@@ -262,7 +328,7 @@ __global__ void __launch_bounds__(256) k_build_level(const float4* __restrict__ 
         for (int c = 0; c < V; ++c)
             if (j == c) { pLo[(int64_t)c * pStride + parent] = lo[c]; pHi[(int64_t)c * pStride + parent] = hi[c]; }
         if (j == kFan - 1) pBound[parent] = b;
-        store_block_node<V>(blk, blockOffP, blockOffC, pLevel, parent, j, lo, hi, b);
+        store_block_node<V>(blk, blkH, qp, blockOffP, blockOffC, pLevel, parent, j, lo, hi, b);
     }
 }
 
@@ -387,21 +453,46 @@ __device__ __forceinline__ void fixed_add(long long* p, long long v) {
 // warps per block of k_repulse_pairs: the per-warp shared memory (queries + stack) grows with V
 __host__ __device__ constexpr int repulse_warps(int V) { return V <= 4 ? 8 : 4; }
 
+// dynamic shared memory of k_repulse_pairs<V, HALF>
+__host__ __device__ constexpr int repulse_smem_bytes(int V, bool half) {
+    return repulse_warps(V) * (32 * (V + 1 + (half ? half_chunks(V) : 0)) * 16 + (8 + 56 * kMaxLevels + 72 + 80) * 4);
+}
+
 #ifndef WB_REPULSE_MINBLOCKS
 #define WB_REPULSE_MINBLOCKS 4
 #endif
-template <int V>
+// HALF selects the box format of the box rounds.  false: the fp32 array-of-blocks.  true: the half-precision copy (lo rounded
+// down, hi rounded up, relative to the frame centre) tested with packed half2 arithmetic against the query rounded to half
+// precision: 3 instead of 5 128-bit loads per child, one instead of V shared-memory loads for the query and ~5 instructions
+// per PAIR of dimensions.  The test stays conservative: with e = the gap vector computed from the rounded operands and
+// delta = |q - round(q)| (exact, kept per query), the true distance to the box is >= |e| (1 - eps) - |delta|, so a child is
+// kept iff |e|^2 <= (L' / s + |delta|)^2 * margin, where margin covers the half-precision rounding of the sum (and always
+// if that threshold is beyond the half range).  Only the
+// number of boxes that pass changes (+1..2 % at c3), never the pair set: points are still tested exactly in fp32.
+// Both instantiations are launched every step; QuantParams::halfBoxes (decided on the device from the layout's spread) says
+// which one runs, the other returns at once.
+template <int V, bool HALF>
 __global__ void __launch_bounds__(256, (V <= 2 ? WB_REPULSE_MINBLOCKS : (V <= 4 ? 2 : 1)))
 k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __restrict__ col, int n, const ForceParams fp,
                 long long* __restrict__ forceRep, const RepLayout lay, int queriesPerUnit, const int* __restrict__ heavySlot,
                 int* __restrict__ chunkCounter, double* __restrict__ partials) {
+    if ((t.quant->halfBoxes != 0) != HALF) return;
     constexpr int RS = 4 * V + 2;                // integers per result row
     constexpr int WARPS = repulse_warps(V), STACK = 56 * kMaxLevels + 72;   // LIFO bound: <= 56 leftovers per level + one push of 64
-    constexpr int QROW = V + 1, BLK = block_float4s(V);
+    constexpr int HV = half_chunks(V);
+    constexpr int QROW = V + 1 + (HALF ? HV : 0), BLK = HALF ? half_block_float4s(V) : block_float4s(V);
+    // relative slack of the half-precision sum of squares: (4 HV + 2) roundings of 2^-11 each, doubled
+    constexpr float kHalfMargin = 1.f + (float)(4 * HV + 6) * 9.8e-4f;
     constexpr uint32_t kRefMask = 0x07ffffffu;   // low 27 bits of an entry: block (stack) or leaf (leaf queue); high 5 bits: query lane
-    __shared__ float4 sQ[WARPS][32][QROW];       // query row: V coordinate chunks + {iw, sorted position + 1, vertex id, -}
-    __shared__ uint32_t sStack[WARPS][8 + STACK];   // 8 null entries below the stack: a short pop reads them and nothing passes
-    __shared__ uint32_t sLeaf[WARPS][80];        // leaves waiting for their point round
+    // dynamic shared memory (repulse_smem_bytes): per warp
+    //   query rows [32][QROW]: V coordinate chunks + {iw, sorted position + 1, vertex id, |delta|} (+ HV chunks of 8 halves: q - centre)
+    //   stack [8 + STACK]: 8 null entries below the stack (a short pop reads them and nothing passes)
+    //   leaf queue [80]: leaves waiting for their point round
+    extern __shared__ float4 smemRep[];
+    static_assert(repulse_smem_bytes(V, HALF) == WARPS * (32 * QROW * 16 + (8 + STACK + 80) * 4), "host and kernel disagree on the layout");
+    float4 (*sQ)[32][QROW] = reinterpret_cast<float4 (*)[32][QROW]>(smemRep);
+    uint32_t (*sStack)[8 + STACK] = reinterpret_cast<uint32_t (*)[8 + STACK]>(smemRep + WARPS * 32 * QROW);
+    uint32_t (*sLeaf)[80] = reinterpret_cast<uint32_t (*)[80]>(reinterpret_cast<uint32_t*>(smemRep + WARPS * 32 * QROW) + WARPS * (8 + STACK));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = lane & (kFan - 1), g = lane >> kFanLog2;
     // lanes that precede this one in child-major order (c, g)
     uint32_t before = 0u;
@@ -414,7 +505,8 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
     uint32_t* myStack = &sStack[warp][8];
     uint32_t* myLeaf = &sLeaf[warp][0];
     if (lane < 8) sStack[warp][lane] = 0u;       // entry 0 = (query 0, null block)
-    const float4* myBlk = t.blk + c;             // lane c tests child c of every block
+    const float4* myBlk = (HALF ? t.blkH : t.blk) + c;   // lane c tests child c of every block
+    const float pruneL = sqrtf(fp.pruneL2);
     const float L = fp.edgeLength;
     const uint32_t ltMask = (1u << lane) - 1u;
     const uint32_t rootBlock = (uint32_t)t.blockOff[t.numLevels];
@@ -430,22 +522,57 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
         r.entry = entry;
         const float4* b = myBlk + (size_t)(entry & kRefMask) * BLK;
         const float4* qrow = myQ + (entry >> 27) * QROW;
-        float4 lo[V], hi[V], qv[V];
+        if constexpr (HALF) {
+            float4 lo[HV], hi[HV], qv[HV];
 #pragma unroll
-        for (int k = 0; k < V; ++k) lo[k] = __ldg(b + k * kFan);
+            for (int k = 0; k < HV; ++k) lo[k] = __ldg(b + k * kFan);
 #pragma unroll
-        for (int k = 0; k < V; ++k) hi[k] = __ldg(b + (V + k) * kFan);
-        const float4 meta = __ldg(b + 2 * V * kFan);
+            for (int k = 0; k < HV; ++k) hi[k] = __ldg(b + (HV + k) * kFan);
+            const float4 meta = __ldg(b + 2 * HV * kFan);
 #pragma unroll
-        for (int k = 0; k < V; ++k) qv[k] = qrow[k];
-        const float4 qm = qrow[V];
-        const float s = qm.x * meta.x;
-        const float d2 = box_dist2<V>(qv, lo, hi);
-        r.childRef = __float_as_uint(meta.y);
-        // the child covers sorted positions [.., endPos): keep it only if some of them lie behind the query (endPos > qpos + 1);
-        // null and padding children have endPos = 0
-        r.pass = (d2 * s * s <= fp.pruneL2) && __float_as_uint(meta.z) > __float_as_uint(qm.y);
-        return r;
+            for (int k = 0; k < HV; ++k) qv[k] = qrow[V + 1 + k];
+            const float4 qm = qrow[V];
+            const __half2 zero2 = __float2half2_rn(0.f);
+            __half2 acc0 = zero2, acc1 = zero2;
+#pragma unroll
+            for (int k = 0; k < HV; ++k) {
+                const float lw[4] = {lo[k].x, lo[k].y, lo[k].z, lo[k].w}, hw[4] = {hi[k].x, hi[k].y, hi[k].z, hi[k].w};
+                const float qw[4] = {qv[k].x, qv[k].y, qv[k].z, qv[k].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const __half2 l2 = *reinterpret_cast<const __half2*>(&lw[i]), h2 = *reinterpret_cast<const __half2*>(&hw[i]);
+                    const __half2 q2 = *reinterpret_cast<const __half2*>(&qw[i]);
+                    // a NaN gap (inf - inf: coordinates beyond the half range) is dropped by hmax2, and such a query has |delta| = inf
+                    const __half2 e = __hmax2(__hmax2(__hsub2(l2, q2), __hsub2(q2, h2)), zero2);
+                    if (i & 1) acc1 = __hfma2(e, e, acc1); else acc0 = __hfma2(e, e, acc0);
+                }
+            }
+            const float2 a0 = __half22float2(acc0), a1 = __half22float2(acc1);
+            const float sum = (a0.x + a0.y) + (a1.x + a1.y);
+            const float thr = fmaf(pruneL, rcp_approx(qm.x * meta.x), qm.w);
+            r.childRef = __float_as_uint(meta.y);
+            // a half-precision sum saturates at 65504: thresholds beyond that cannot be decided here, the child is kept
+            const float lim = thr * thr * kHalfMargin;
+            r.pass = (sum <= lim || lim >= 6.0e4f) && __float_as_uint(meta.z) > __float_as_uint(qm.y);
+            return r;
+        } else {
+            float4 lo[V], hi[V], qv[V];
+#pragma unroll
+            for (int k = 0; k < V; ++k) lo[k] = __ldg(b + k * kFan);
+#pragma unroll
+            for (int k = 0; k < V; ++k) hi[k] = __ldg(b + (V + k) * kFan);
+            const float4 meta = __ldg(b + 2 * V * kFan);
+#pragma unroll
+            for (int k = 0; k < V; ++k) qv[k] = qrow[k];
+            const float4 qm = qrow[V];
+            const float s = qm.x * meta.x;
+            const float d2 = box_dist2<V>(qv, lo, hi);
+            r.childRef = __float_as_uint(meta.y);
+            // the child covers sorted positions [.., endPos): keep it only if some of them lie behind the query (endPos > qpos + 1);
+            // null and padding children have endPos = 0
+            r.pass = (d2 * s * s <= fp.pruneL2) && __float_as_uint(meta.z) > __float_as_uint(qm.y);
+            return r;
+        }
     };
     // Point round: one (leaf, query) pair per 8-lane group and slot; lane c tests point c of the leaf with the exact predicate.
     struct PointSlot { int idx; uint32_t qq; float d2, ws; bool hit; };
@@ -526,7 +653,40 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
             float4* row = myQ + lane * QROW;
 #pragma unroll
             for (int k = 0; k < V; ++k) row[k] = valid ? __ldg(t.lo[0] + (int64_t)k * t.stride[0] + qi) : make_float4(0.f, 0.f, 0.f, 0.f);
-            row[V] = make_float4(valid ? __ldg(t.bound[0] + qi) : 1.f, __uint_as_float((uint32_t)qi + 1u), __uint_as_float((uint32_t)vertex), 0.f);
+            float delta = 0.f;
+            if constexpr (HALF) {
+                // the query as the box rounds see it: q - centre rounded to half precision, and how far that moved it
+                float d2 = 0.f;
+#pragma unroll
+                for (int k = 0; k < HV; ++k) {
+                    __half2 h[4];
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const int ch = 2 * k + half;
+                        float e[4] = {0.f, 0.f, 0.f, 0.f};
+                        if (ch < V) {
+                            const float4 q = row[ch];
+                            e[0] = q.x - t.quant->centre[4 * ch]; e[1] = q.y - t.quant->centre[4 * ch + 1];
+                            e[2] = q.z - t.quant->centre[4 * ch + 2]; e[3] = q.w - t.quant->centre[4 * ch + 3];
+                        }
+                        h[2 * half] = __floats2half2_rn(e[0], e[1]);
+                        h[2 * half + 1] = __floats2half2_rn(e[2], e[3]);
+                        const float2 b0 = __half22float2(h[2 * half]), b1 = __half22float2(h[2 * half + 1]);
+                        d2 = fmaf(e[0] - b0.x, e[0] - b0.x, d2); d2 = fmaf(e[1] - b0.y, e[1] - b0.y, d2);
+                        d2 = fmaf(e[2] - b1.x, e[2] - b1.x, d2); d2 = fmaf(e[3] - b1.y, e[3] - b1.y, d2);
+                    }
+                    float4 packed;
+                    packed.x = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h[0]));
+                    packed.y = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h[1]));
+                    packed.z = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h[2]));
+                    packed.w = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h[3]));
+                    row[V + 1 + k] = packed;
+                }
+                // rounded up generously; a coordinate beyond the half range gives inf - x = inf (or NaN): everything passes for it
+                delta = sqrtf(d2) * 1.001f;
+                if (!(delta >= 0.f)) delta = __int_as_float(0x7f800000);
+            }
+            row[V] = make_float4(valid ? __ldg(t.bound[0] + qi) : 1.f, __uint_as_float((uint32_t)qi + 1u), __uint_as_float((uint32_t)vertex), delta);
         }
         const uint32_t validMask = __ballot_sync(0xffffffffu, valid);
         if (valid) myStack[__popc(validMask & ltMask)] = ((uint32_t)lane << 27) | rootBlock;

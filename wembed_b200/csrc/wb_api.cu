@@ -114,6 +114,9 @@ struct wb_embedder {
     int momentBlocks = 0;
     float* momentPartials = nullptr;
     wb::QuantParams* quant = nullptr;
+    float4* blkH = nullptr;               // half-precision copy of the array-of-blocks tree (box rounds of k_repulse_pairs)
+    float halfSigmaLimit = 0.f;           // layouts with a larger per-dimension sd walk the fp32 boxes (k_quant_params)
+    int halfMode = -1;                    // WB_HALF_BOXES: 0 never, 1 always, unset: by the layout
     float4* lvlLo[wb::kMaxLevels] = {};
     float4* lvlHi[wb::kMaxLevels] = {};
     float* lvlBound[wb::kMaxLevels] = {};
@@ -168,7 +171,7 @@ void free_all(wb_embedder* h) {
     auto F = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
     F(h->rowPtr); F(h->col); F(h->x); F(h->xNew); F(h->mom1); F(h->mom2); F(h->forceRep); F(h->force);
     F(h->iw); F(h->invOrder); F(h->edgeWs); F(h->chunkCounter); F(h->hubVertex); F(h->hubSlot); F(h->hubForce); F(h->heavyVertex); F(h->heavySlot); F(h->keysIn); F(h->keysOut); F(h->valsIn); F(h->valsOut);
-    F(h->cubTemp); F(h->momentPartials); F(h->quant); F(h->ids); F(h->blk);
+    F(h->cubTemp); F(h->momentPartials); F(h->quant); F(h->ids); F(h->blk); F(h->blkH);
     for (int l = 0; l < wb::kMaxLevels; ++l) { F(h->lvlLo[l]); if (l > 0) F(h->lvlHi[l]); F(h->lvlBound[l]); }
     F(h->partialsForce); F(h->partialsRep); F(h->partialsObs); F(h->sumsAll); F(h->gathered); F(h->localSums);
     if (h->comm) { nccl().commDestroy(h->comm); h->comm = nullptr; }
@@ -191,6 +194,19 @@ void choose_fixed_scales(wb_embedder* h, double maxIw, double minIw) {
     };
     h->fixForce = scale(std::fabs(h->opt.repulsion_scale) * maxIw * maxIw);
     h->fixLoss = scale(h->opt.edge_length / (minIw * minIw));
+    // Box format of the repulsion walk (k_quant_params decides every step): half-precision boxes while the layout's largest
+    // per-dimension sd is at most kHalfSpread smallest interaction radii (L / max ws); the rounding of a centred coordinate is
+    // ~sd * 2^-11, i.e. below 1 % of that radius.  WB_HALF_BOXES=0 / 1 forces one format (A/B runs, tests).
+    constexpr double kHalfSpread = 16.0;
+    if (h->halfMode < 0) {
+        const char* env = std::getenv("WB_HALF_BOXES");
+        h->halfMode = env ? (std::atoi(env) != 0 ? 1 : 0) : 2;
+    }
+    const double rMin = h->opt.edge_length / (maxIw * maxIw), rMax = h->opt.edge_length / (minIw * minIw);
+    // squared gaps are summed in half precision (max 65504): radii beyond ~200 cannot be tested there at all
+    const bool representable = rMax < 200.0;
+    h->halfSigmaLimit = h->halfMode == 0 ? -1.f : (h->halfMode == 1 ? std::numeric_limits<float>::infinity()
+                                                                    : (representable ? (float)(kHalfSpread * rMin) : -1.f));
 }
 
 void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
@@ -284,6 +300,15 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
         h->blk = dalloc<float4>(f4);
         WB_DISPATCH_V(V, wb::k_init_blocks<V><<<div_up(f4, 256), 256, 0, h->stream>>>(h->blk, (int64_t)f4));
         t.blk = h->blk;
+        // half-precision copy: all-zero records never pass (end position 0)
+        const size_t h4 = (size_t)blocks * wb::half_block_float4s(V);
+        h->blkH = dalloc<float4>(h4);
+        WB_CUDA(cudaMemsetAsync(h->blkH, 0, h4 * sizeof(float4), h->stream));
+        t.blkH = h->blkH;
+        t.quant = h->quant;
+        // the walk's per-warp queries + stacks exceed the 48 KB static limit for the wider rows
+        WB_DISPATCH_V(V, WB_CUDA(cudaFuncSetAttribute(wb::k_repulse_pairs<V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wb::repulse_smem_bytes(V, false)));
+                         WB_CUDA(cudaFuncSetAttribute(wb::k_repulse_pairs<V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wb::repulse_smem_bytes(V, true))));
     }
     h->ids = dalloc<int>(t.stride[0]);
     WB_CUDA(cudaMemsetAsync(h->ids, 0xff, sizeof(int) * t.stride[0], h->stream));
@@ -322,17 +347,17 @@ void enqueue_index(wb_embedder* h, const float* pointBound) {
     const int n = h->n, V = h->V;
     cudaStream_t s = h->stream;
     WB_DISPATCH_V(V, wb::k_moments<V><<<h->momentBlocks, 256, 0, s>>>(h->x, n, h->momentPartials));
-    wb::k_quant_params<<<1, 256, 0, s>>>(h->momentPartials, h->momentBlocks, n, h->dim, h->mortonBits, h->quant);
+    wb::k_quant_params<<<1, 256, 0, s>>>(h->momentPartials, h->momentBlocks, n, h->dim, h->mortonBits, h->halfSigmaLimit, h->quant);
     WB_DISPATCH_V(V, wb::k_morton_keys<V><<<div_up(n, 256), 256, 0, s>>>(h->x, n, h->dim, h->mortonBits, h->quant, h->keysIn, h->valsIn));
     WB_CUDA(cub::DeviceRadixSort::SortPairs(h->cubTemp, h->cubBytes, h->keysIn, h->keysOut, h->valsIn, h->valsOut, n, 0, h->mortonBits * h->dim, s));
     const wb::TreeView& t = h->tree;
     WB_DISPATCH_V(V, wb::k_build_leaves<V><<<div_up(t.stride[0], 256), 256, 0, s>>>(
                          h->x, pointBound, h->valsOut, n, h->lvlLo[0], t.stride[0], h->lvlBound[0], h->ids, h->invOrder, h->lvlLo[1], h->lvlHi[1],
-                         h->lvlBound[1], t.stride[1], h->blk, t.blockOff[1]));
+                         h->lvlBound[1], t.stride[1], h->blk, t.blockOff[1], h->blkH, h->quant));
     for (int l = 2; l <= t.numLevels; ++l) {
         WB_DISPATCH_V(V, wb::k_build_level<V><<<div_up((int64_t)t.count[l] * kFan, 256), 256, 0, s>>>(
                              h->lvlLo[l - 1], h->lvlHi[l - 1], h->lvlBound[l - 1], t.count[l - 1], t.stride[l - 1], h->lvlLo[l], h->lvlHi[l],
-                             h->lvlBound[l], t.count[l], t.stride[l], h->blk, t.blockOff[l], t.blockOff[l - 1], l));
+                             h->lvlBound[l], t.count[l], t.stride[l], h->blk, t.blockOff[l], t.blockOff[l - 1], l, h->blkH, h->quant));
     }
     h->launches += 5 + (t.numLevels - 1);
     WB_CUDA(cudaGetLastError());
@@ -395,9 +420,13 @@ void enqueue_step(wb_embedder* h, double learningRate) {
     const int queriesPerUnit = h->repLayout.segRows / 32 >= 8 * residentWarps ? 32 : (h->repLayout.segRows / 16 >= 8 * residentWarps ? 16 : 8);
     WB_CUDA(cudaMemsetAsync(h->chunkCounter, 0, sizeof(int), s));
     WB_CUDA(cudaMemsetAsync(h->forceRep, 0, h->forceRepBytes, s));      // EmbedderState::nextStep zeroes the forces
-    WB_DISPATCH_V(V, wb::k_repulse_pairs<V><<<h->repBlocks, 32 * wb::repulse_warps(V), 0, s>>>(h->tree, h->rowPtr, h->col, n, fp, h->forceRep,
-                                                                                                  h->repLayout, queriesPerUnit, h->heavySlot, h->chunkCounter,
-                                                                                                  h->partialsRep));
+    // both box formats are launched; the one QuantParams::halfBoxes does not name returns at once (the choice is made on the device
+    // from this step's layout, the host never waits for it)
+    WB_DISPATCH_V(V, (wb::k_repulse_pairs<V, false><<<h->repBlocks, 32 * wb::repulse_warps(V), wb::repulse_smem_bytes(V, false), s>>>(
+                         h->tree, h->rowPtr, h->col, n, fp, h->forceRep, h->repLayout, queriesPerUnit, h->heavySlot, h->chunkCounter, h->partialsRep)));
+    WB_DISPATCH_V(V, (wb::k_repulse_pairs<V, true><<<h->repBlocks, 32 * wb::repulse_warps(V), wb::repulse_smem_bytes(V, true), s>>>(
+                         h->tree, h->rowPtr, h->col, n, fp, h->forceRep, h->repLayout, queriesPerUnit, h->heavySlot, h->chunkCounter, h->partialsRep)));
+    h->launches += 1;
     const int repWarps = h->repBlocks * wb::repulse_warps(V);
     if (h->numHeavy) {
         WB_DISPATCH_V(V, wb::k_repulse_heavy<V><<<h->numHeavy, 256, 0, s>>>(h->tree, h->rowPtr, h->col, n, fp, h->forceRep, h->repLayout, h->heavyVertex,
