@@ -150,3 +150,47 @@ def test_wide_weight_ranges_fixed_point_rows(device_lib, port_lib, d, lo, hi, re
     if ok.all():
         np.testing.assert_allclose(st["loss_repel"], cs["loss_repel"], rtol=1e-5)
         np.testing.assert_allclose(st["loss_attract"], cs["loss_attract"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("d", [1, 2, 4, 8, 11, 16])
+def test_half_precision_boxes_find_the_same_pairs(device_lib, monkeypatch, d):
+    """The box rounds of the repulsion walk may test a half-precision copy of the boxes (k_repulse_pairs<V, true>); it only
+    prunes, the pair test stays exact fp32, and the rows are integer sums: forced on and forced off must agree BIT FOR BIT in
+    forces, coordinates and pair counts - on a blob, a layout 300 radii wide, outliers beyond the half range (1e5, where
+    coordinates round to inf) and weights spanning four decades (radii beyond what half precision can square)."""
+    n = 6000
+    edges, _ = geometric_graph_small(n)
+    rp, col = device_lib.csr_from_edges(n, edges)
+    rng = np.random.default_rng(d)
+    blob = rng.normal(0.0, {1: 1.5, 2: 1.5, 4: 1.2, 8: 0.5, 11: 0.35, 16: 0.25}[d], (n, d))   # dense enough for repulsive pairs
+    wide = blob * 200.0
+    outliers = blob.copy()
+    outliers[rng.choice(n, 40, replace=False)] *= 1.0e5
+    outliers[rng.choice(n, 5, replace=False), 0] = 7.0e4
+    shifted = blob + 3000.0                                # far from the origin: the frame centre has to absorb it
+    from wembed_b200.datasets import degree_weights
+    w_deg = degree_weights(n, edges, d)
+    w_wide = np.exp(rng.uniform(np.log(1e-2), np.log(1e2), n))
+    w_wide *= n / w_wide.sum()
+    for name, x0, w in (("blob", blob, w_deg), ("wide", wide, w_deg), ("outliers", outliers, w_deg), ("shifted", shifted, w_deg),
+                        ("weights", blob, w_wide)):
+        x0 = x0.astype(np.float32).astype(np.float64)
+        out = {}
+        for mode in ("0", "1"):
+            monkeypatch.setenv("WB_HALF_BOXES", mode)
+            dev = device_lib.DeviceEmbedder(rp, col, embedding_dimension=d, keep_forces=1, seed=7)
+            dev.set_weights(w)
+            dev.set_coordinates(x0)
+            pairs = []
+            for it in range(1, 4):
+                pairs.append(dev.step(lr_exponential(it))["num_repulsion_pairs"])
+            out[mode] = (pairs, dev.forces().copy(), dev.coordinates().copy())
+        assert out["0"][0] == out["1"][0], (name, out["0"][0], out["1"][0])
+        np.testing.assert_array_equal(out["0"][1], out["1"][1], err_msg=name)
+        np.testing.assert_array_equal(out["0"][2], out["1"][2], err_msg=name)
+        assert name not in ("blob", "shifted", "weights") or out["0"][0][0] > 0, name   # the comparison is not vacuous
+
+
+def geometric_graph_small(n):
+    from wembed_b200.datasets import geometric_graph
+    return geometric_graph(n, 10, 11)

@@ -80,7 +80,8 @@ __device__ __forceinline__ void store_block_node(float4* __restrict__ blk, float
         if (j == c) { b[c * kFan] = lo[c]; b[(V + c) * kFan] = hi[c]; }
     const uint32_t childRef = lv == 1 ? (kLeafFlag | (uint32_t)idx) : (uint32_t)(blockOffBelow + idx);
     const uint32_t endPos = (uint32_t)min((int64_t)(idx + 1) << (kFanLog2 * lv), (int64_t)0x7fffffff);
-    const float4 meta = make_float4(bound, __uint_as_float(childRef), __uint_as_float(endPos), 0.f);
+    // .w = 1 / bound, rounded up (the half-precision box rounds turn it into a distance threshold; 0 for the empty boxes' inf bound)
+    const float4 meta = make_float4(bound, __uint_as_float(childRef), __uint_as_float(endPos), __frcp_ru(bound));
     if (j == kFan - 1) b[2 * V * kFan] = meta;
     // half-precision copy: the box relative to the frame centre, lo rounded down and hi rounded up (subtraction and conversion both
     // directed), so it contains the fp32 box; lanes 0..HV-1 pack the lo chunks, lanes HV..2HV-1 the hi chunks
@@ -482,10 +483,11 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
     constexpr int HV = half_chunks(V);
     constexpr int QROW = V + 1 + (HALF ? HV : 0), BLK = HALF ? half_block_float4s(V) : block_float4s(V);
     // relative slack of the half-precision sum of squares: (4 HV + 2) roundings of 2^-11 each, doubled
-    constexpr float kHalfMargin = 1.f + (float)(4 * HV + 6) * 9.8e-4f;
+    // (the threshold is scaled by its square root before it is squared; a first-order expansion rounded up)
+    constexpr float kHalfMarginRoot = 1.f + (float)(4 * HV + 6) * 4.9e-4f + 1.0e-6f;
     constexpr uint32_t kRefMask = 0x07ffffffu;   // low 27 bits of an entry: block (stack) or leaf (leaf queue); high 5 bits: query lane
     // dynamic shared memory (repulse_smem_bytes): per warp
-    //   query rows [32][QROW]: V coordinate chunks + {iw, sorted position + 1, vertex id, |delta|} (+ HV chunks of 8 halves: q - centre)
+    //   query rows [32][QROW]: V coordinate chunks + {iw, sorted position + 1, threshold factor, |delta|} (+ HV chunks of 8 halves: q - centre)
     //   stack [8 + STACK]: 8 null entries below the stack (a short pop reads them and nothing passes)
     //   leaf queue [80]: leaves waiting for their point round
     extern __shared__ float4 smemRep[];
@@ -547,12 +549,14 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
                     if (i & 1) acc1 = __hfma2(e, e, acc1); else acc0 = __hfma2(e, e, acc0);
                 }
             }
-            const float2 a0 = __half22float2(acc0), a1 = __half22float2(acc1);
-            const float sum = (a0.x + a0.y) + (a1.x + a1.y);
-            const float thr = fmaf(pruneL, rcp_approx(qm.x * meta.x), qm.w);
+            // the two accumulators and then their two halves are added in half precision (two more roundings, inside the margin)
+            const __half2 acc = __hadd2(acc0, acc1);
+            const float sum = __half2float(__hadd(__low2half(acc), __high2half(acc)));
+            // qm.z = pruneL / iw_q and qm.w = |delta|, both scaled by sqrt(margin); meta.w = 1 / bound of the child
+            const float thr = fmaf(qm.z, meta.w, qm.w);
             r.childRef = __float_as_uint(meta.y);
             // a half-precision sum saturates at 65504: thresholds beyond that cannot be decided here, the child is kept
-            const float lim = thr * thr * kHalfMargin;
+            const float lim = thr * thr;
             r.pass = (sum <= lim || lim >= 6.0e4f) && __float_as_uint(meta.z) > __float_as_uint(qm.y);
             return r;
         } else {
@@ -601,7 +605,7 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
         if (dist > 0.f && !(dist * ws <= L)) return;         // exact predicate; dist <= 0 is the coincident case
         const float4* qrow = myQ + r.qq * QROW;
         const int u = __ldg(t.ids + r.idx);
-        const int v = (int)__float_as_uint(qrow[V].z);
+        const int v = __ldg(t.ids + (__float_as_uint(qrow[V].y) - 1u));   // the query's vertex (hits are rare: looked up here, not carried)
         // pairs with a heavy vertex belong to that vertex' block (k_repulse_heavy)
         if ((heavySlot && __ldg(heavySlot + u) >= 0) || is_neighbor(col, __ldg(rowPtr + v), __ldg(rowPtr + v + 1), u)) return;
         long long* fv = forceRep + (int64_t)v * RS;
@@ -683,10 +687,12 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
                     row[V + 1 + k] = packed;
                 }
                 // rounded up generously; a coordinate beyond the half range gives inf - x = inf (or NaN): everything passes for it
-                delta = sqrtf(d2) * 1.001f;
+                delta = sqrtf(d2) * 1.001f * kHalfMarginRoot;
                 if (!(delta >= 0.f)) delta = __int_as_float(0x7f800000);
             }
-            row[V] = make_float4(valid ? __ldg(t.bound[0] + qi) : 1.f, __uint_as_float((uint32_t)qi + 1u), __uint_as_float((uint32_t)vertex), delta);
+            // {iw (point rounds), sorted position + 1, box-round threshold factor pruneL * sqrt(margin) / iw, |delta| * sqrt(margin)}
+            const float iwq = valid ? __ldg(t.bound[0] + qi) : 1.f;
+            row[V] = make_float4(iwq, __uint_as_float((uint32_t)qi + 1u), pruneL * kHalfMarginRoot * 1.000001f * __frcp_ru(iwq), delta);
         }
         const uint32_t validMask = __ballot_sync(0xffffffffu, valid);
         if (valid) myStack[__popc(validMask & ltMask)] = ((uint32_t)lane << 27) | rootBlock;
