@@ -186,15 +186,15 @@ __global__ void __launch_bounds__(256) k_moments(const float4* __restrict__ x, i
 // It also decides whether this step's repulsion walk may test the half-precision copy of the boxes: the rounding of a
 // centred coordinate to half precision is ~sd * 2^-11, which has to stay small against the smallest interaction radius or the
 // outward-rounded boxes stop pruning; halfSigmaLimit = that radius times a constant (wb_set_weights), <= 0 disables, +inf forces.
-__global__ void __launch_bounds__(256) k_quant_params(const float* __restrict__ partial, int numBlocks, int n, int dim, int bits,
+__global__ void __launch_bounds__(1024) k_quant_params(const float* __restrict__ partial, int numBlocks, int n, int dim, int bits,
                                                       float halfSigmaLimit, QuantParams* __restrict__ qp) {
-    // thread (k, j) = (dimension, slice): slice j folds blocks j, j+8, .. in order; the 8 slices are combined in slice order
-    __shared__ float sMin[8][kMaxDim], sMax[8][kMaxDim];
-    __shared__ double sS1[8][kMaxDim], sS2[8][kMaxDim];
+    // thread (k, j) = (dimension, slice): slice j folds blocks j, j+32, .. in order; the 32 slices are combined in slice order
+    __shared__ float sMin[32][kMaxDim], sMax[32][kMaxDim];
+    __shared__ double sS1[32][kMaxDim], sS2[32][kMaxDim];
     const int k = threadIdx.x & 31, j = threadIdx.x >> 5;
     float mn = 3.0e38f, mx = -3.0e38f; double s1 = 0.0, s2 = 0.0;
     if (k < dim) {
-        for (int b = j; b < numBlocks; b += 8) {
+        for (int b = j; b < numBlocks; b += 32) {
             const float* p = partial + (int64_t)b * 4 * kMaxDim;
             mn = fminf(mn, p[k]); mx = fmaxf(mx, p[kMaxDim + k]); s1 += p[2 * kMaxDim + k]; s2 += p[3 * kMaxDim + k];
         }
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(256) k_quant_params(const float* __restrict__ 
     if (j == 0) {
         float sd = 0.f;
         if (k < dim) {
-            for (int t = 1; t < 8; ++t) { mn = fminf(mn, sMin[t][k]); mx = fmaxf(mx, sMax[t][k]); s1 += sS1[t][k]; s2 += sS2[t][k]; }
+            for (int t = 1; t < 32; ++t) { mn = fminf(mn, sMin[t][k]); mx = fmaxf(mx, sMax[t][k]); s1 += sS1[t][k]; s2 += sS2[t][k]; }
             const double mean = s1 / n;
             const double var = fmax(0.0, s2 / n - mean * mean);
             sd = (float)sqrt(var);
@@ -401,6 +401,8 @@ __device__ __forceinline__ void walk_tree(const TreeView& t, const float4 (&q)[V
 }
 
 // u in N(v)?  Rows are sorted ascending (Graph.cpp:87-150), so a binary search equals Graph::areNeighbors (:67-83).
+// (Measured and rejected: reading rows of <= 16 entries with four independent 128-bit loads and comparing in registers instead of
+// the dependent search - c3 repel 3.06 -> 3.16 ms; the extra instructions cost more than the shorter latency chain saves.)
 __device__ __forceinline__ bool is_neighbor(const int* __restrict__ col, int begin, int end, int u) {
     while (begin < end) {
         const int mid = (begin + end) >> 1;

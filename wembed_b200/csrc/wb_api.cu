@@ -347,7 +347,7 @@ void enqueue_index(wb_embedder* h, const float* pointBound) {
     const int n = h->n, V = h->V;
     cudaStream_t s = h->stream;
     WB_DISPATCH_V(V, wb::k_moments<V><<<h->momentBlocks, 256, 0, s>>>(h->x, n, h->momentPartials));
-    wb::k_quant_params<<<1, 256, 0, s>>>(h->momentPartials, h->momentBlocks, n, h->dim, h->mortonBits, h->halfSigmaLimit, h->quant);
+    wb::k_quant_params<<<1, 1024, 0, s>>>(h->momentPartials, h->momentBlocks, n, h->dim, h->mortonBits, h->halfSigmaLimit, h->quant);
     WB_DISPATCH_V(V, wb::k_morton_keys<V><<<div_up(n, 256), 256, 0, s>>>(h->x, n, h->dim, h->mortonBits, h->quant, h->keysIn, h->valsIn));
     WB_CUDA(cub::DeviceRadixSort::SortPairs(h->cubTemp, h->cubBytes, h->keysIn, h->keysOut, h->valsIn, h->valsOut, n, 0, h->mortonBits * h->dim, s));
     const wb::TreeView& t = h->tree;
