@@ -133,7 +133,7 @@ def measured_peak_gbs():
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures under profiles/ (c3, step 100 / 30)
-NCU_TRAFFIC = {"repel": 211.3e6 + 45.2e6, "attract_update": 294.5e6 + 93.9e6}
+NCU_TRAFFIC = {"repel": 202.8e6 + 43.9e6, "attract_update": 293.8e6 + 89.2e6}
 
 
 def algorithmic_bytes_per_step(n, m, d):
@@ -282,8 +282,8 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_TRAFFIC.get(dom), "peak_source": peak_src, "algorithmic_bytes": dom_bytes,
                      "note": ("the dominant kernel (k_repulse_pairs, exact radius search in d dimensions) is bound by the SM's load/store data path and "
-                              "instruction issue, not by HBM: ncu shows DRAM < 1 % of peak, L2 hit 99.3 %, L1 data-pipe wavefronts 84 %, "
-                              "issue slots 69 % busy (profiles/r1_summary.md). The HBM-bound "
+                              "instruction issue, not by HBM: ncu shows DRAM < 1 % of peak, L2 hit 99.0 %, L1 data-pipe wavefronts 85 %, "
+                              "issue slots 77 % busy (profiles/r1_summary.md section 6). The HBM-bound "
                               "kernels are listed in `kernels`; `fused_step_kernel` is north_star's attraction + optimizer kernel."),
                      "kernels": rooflines, "fused_step_kernel": rooflines["attract_update"],
                      "whole_step": {"algorithmic_bytes": bytes_step, "achieved": bytes_step / (ph["total"] * 1e-3) / 1e9,
