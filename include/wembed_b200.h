@@ -192,6 +192,17 @@ int wb_comm_init(wb_embedder* h, const char* id128, int32_t rank, int32_t world)
  */
 int wb_reconstruction(wb_embedder* h, int32_t count, const int32_t* nodes, double* out2);
 
+/*
+ * evaluationLib's EdgeDetection metric (src/evaluationLib/src/metrics/EdgeDetection.cpp:6-66) of the CURRENT layout on the
+ * WeightedGeometric similarity, over the vertex pairs (v[i], w[i]) an EdgeSampler drew (EdgeSampler.cpp:7-66: every edge once,
+ * plus non-edges at a chosen rate; is_edge[i] says which).  The pairs are sorted by similarity on the device (stable: ties keep
+ * the caller's order) and every prefix of the sorted list is scored as "these are the edges"; out3 = {precision, recall, F1}
+ * of the prefix with the best F1 (the first one on ties), with the sampled counts scaled to the graph's m edges and
+ * n(n-1)/2 - m non-edges exactly as the reference does.  The caller chooses the sample (wembed_b200/metrics.py mirrors the
+ * reference's sampler).
+ */
+int wb_edge_detection(wb_embedder* h, int64_t count, const int32_t* v, const int32_t* w, const uint8_t* is_edge, double* out3);
+
 /* -- measurement ------------------------------------------------------------------------- */
 
 /* Records CUDA event `slot` (0..7) on the handle's stream; wb_elapsed_ms waits for event `to` and returns the

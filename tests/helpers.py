@@ -127,3 +127,32 @@ def reconstruction_metrics(x, w, row_ptr, col, nodes=None):
         deg_prec.append(prec[len(nb) - 1])
         avg_prec.append(prec[hits].mean())
     return float(np.mean(deg_prec)), float(np.mean(avg_prec))
+
+
+def edge_detection_metrics(x, w, v, u, is_edge, n, m):
+    """EdgeDetection::getMetricValues (src/evaluationLib/src/metrics/EdgeDetection.cpp:6-66) on the WeightedGeometric
+    similarity, restated loop for loop (running percentages, strict `F1 > best`); the pairs are sorted by similarity like
+    EdgeSampler.cpp:62 (stable here, so ties keep the sampler's order).  Returns (precision, recall, F1)."""
+    d = x.shape[1]
+    iw = w ** (-1.0 / d)
+    v, u, is_edge = np.asarray(v), np.asarray(u), np.asarray(is_edge).astype(bool)
+    wr = w ** (1.0 / d)
+    sim = np.sqrt(((x[v] - x[u]) ** 2).sum(1)) / (wr[v] * wr[u])          # WeightedGeometric.cpp:17-21
+    order = np.argsort(sim, kind="stable")
+    n_e, n_ne = int(is_edge.sum()), int((~is_edge).sum())
+    M, no_m = float(m), float(n * (n - 1) // 2 - m)
+    wrong_e, wrong_ne = 1.0, 0.0
+    best = (-1.0, -1.0, -1.0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for i in order:
+            if is_edge[i]:
+                wrong_e -= 1.0 / n_e
+            else:
+                wrong_ne += 1.0 / n_ne
+            tp = (1.0 - wrong_e) * M
+            retrieved = tp + wrong_ne * no_m
+            precision, recall = np.float64(tp) / np.float64(retrieved), np.float64(tp) / np.float64(M)
+            f1 = np.float64(2.0) / (np.float64(1.0) / precision + np.float64(1.0) / recall)
+            if f1 > best[2]:
+                best = (float(precision), float(recall), float(f1))
+    return best

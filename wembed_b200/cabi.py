@@ -24,6 +24,7 @@ EXPORTS = (
     "wb_set_coordinates", "wb_set_weights", "wb_get_coordinates", "wb_get_weights", "wb_get_forces", "wb_reset_optimizer",
     "wb_set_iteration", "wb_step", "wb_step_async", "wb_step_collect", "wb_synchronize", "wb_query_candidates",
     "wb_enable_timing", "wb_get_phase_times", "wb_mark", "wb_elapsed_ms", "wb_launch_count", "wb_comm_unique_id", "wb_comm_init", "wb_reconstruction",
+    "wb_edge_detection",
 )
 
 
@@ -80,6 +81,7 @@ def lib():
         "wb_mark": (C.c_int, [H, C.c_int]), "wb_elapsed_ms": (C.c_int, [H, C.c_int, C.c_int, dp]),
         "wb_launch_count": (C.c_int64, [H]),
         "wb_reconstruction": (C.c_int, [H, i32, ip, dp]),
+        "wb_edge_detection": (C.c_int, [H, C.c_int64, ip, ip, C.POINTER(C.c_uint8), dp]),
         "wb_comm_unique_id": (C.c_int, [C.c_char_p]), "wb_comm_init": (C.c_int, [H, C.c_char_p, i32, i32]),
     }
     for name, (res, args) in sig.items():
@@ -210,6 +212,17 @@ class DeviceEmbedder:
         out = np.zeros(2, np.float64)
         self._check(self._l.wb_reconstruction(self._h, len(q), _ip(q), _dp(out)))
         return float(out[0]), float(out[1])
+
+    def edge_detection(self, v, w, is_edge):
+        """(precision, recall, F1) at the best similarity threshold over the sampled pairs (evaluationLib EdgeDetection);
+        wembed_b200.metrics.sample_edge_pairs mirrors the reference's sampler."""
+        a = np.ascontiguousarray(v, dtype=np.int32)
+        b = np.ascontiguousarray(w, dtype=np.int32)
+        f = np.ascontiguousarray(is_edge, dtype=np.uint8)
+        assert len(a) == len(b) == len(f)
+        out = np.zeros(3, np.float64)
+        self._check(self._l.wb_edge_detection(self._h, len(a), _ip(a), _ip(b), f.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(out)))
+        return float(out[0]), float(out[1]), float(out[2])
 
     def comm_init(self, unique_id: bytes, rank: int, world: int):
         """Join the vertex-sharded multi-GPU step (see include/wembed_b200.h)."""

@@ -1387,4 +1387,66 @@ __global__ void __launch_bounds__(256) k_candidates(const TreeView t, const floa
     if (valid && !writePass && j == 0) counts[qn] = found;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Edge detection quality: evaluationLib's EdgeDetection over the pairs an EdgeSampler drew
+// (src/evaluationLib/src/metrics/EdgeDetection.cpp:6-66, EdgeSampler.cpp:7-66): similarity of every sampled pair, ascending
+// sort, and the best F1 over all prefixes of the sorted list - prefix i classifies entries 0..i as edges.
+
+// WeightedGeometric similarity of the sampled pairs (WeightedGeometric.cpp:17-21), in double on the fp32 positions
+template <int V>
+__global__ void __launch_bounds__(256) k_pair_similarity(const float4* __restrict__ x, const double* __restrict__ wroot, const int* __restrict__ pv,
+                                                         const int* __restrict__ pw, int64_t count, double* __restrict__ sim) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int a = pv[i], b = pw[i];
+    float4 xa[V];
+    load_row<V>(x, a, xa);
+    sim[i] = similarity<V>(x, wroot, a, xa, wroot[a], b);
+}
+
+struct F1Best {        // best prefix so far; ties keep the lowest index (the reference updates on F1 > best only, :52-57)
+    double f1, precision, recall;
+    long long index;
+};
+__device__ __forceinline__ bool f1_better(const F1Best& a, const F1Best& b) { return a.f1 > b.f1 || (a.f1 == b.f1 && a.index < b.index); }
+
+// edgePrefix[i] = number of edges among the sorted entries 0..i.  Closed form of the reference's running percentages
+// (wrongEdgesPercent = 1 - e / numSampledEdges, wrongNonEdgesPercent = ne / numSampledNonEdges, :30-35), then its F1 (:39-45).
+__global__ void __launch_bounds__(256) k_f1_curve(const int* __restrict__ edgePrefix, int64_t count, double numEdges, double numNonEdges,
+                                                  double M, double noM, F1Best* __restrict__ partial) {
+    __shared__ F1Best sm[256];
+    F1Best best{-1.0, -1.0, -1.0, 0x7fffffffffffffffll};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        const double e = (double)edgePrefix[i], ne = (double)(i + 1) - e;
+        const double wrongEdges = 1.0 - (numEdges > 0.0 ? e / numEdges : 0.0);
+        const double wrongNonEdges = numNonEdges > 0.0 ? ne / numNonEdges : 0.0;
+        const double truePositives = (1.0 - wrongEdges) * M;
+        const double retrieved = truePositives + wrongNonEdges * noM;
+        const double precision = truePositives / retrieved, recall = truePositives / M;
+        const F1Best cur{2.0 / (1.0 / precision + 1.0 / recall), precision, recall, (long long)i};
+        if (f1_better(cur, best)) best = cur;
+    }
+    sm[threadIdx.x] = best;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o && f1_better(sm[threadIdx.x + o], sm[threadIdx.x])) sm[threadIdx.x] = sm[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sm[0];
+}
+
+__global__ void __launch_bounds__(256) k_f1_best(const F1Best* __restrict__ partial, int blocks, F1Best* __restrict__ out) {
+    __shared__ F1Best sm[256];
+    F1Best best{-1.0, -1.0, -1.0, 0x7fffffffffffffffll};
+    for (int i = threadIdx.x; i < blocks; i += 256)
+        if (f1_better(partial[i], best)) best = partial[i];
+    sm[threadIdx.x] = best;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o && f1_better(sm[threadIdx.x + o], sm[threadIdx.x])) sm[threadIdx.x] = sm[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sm[0];
+}
+
 }  // namespace wb

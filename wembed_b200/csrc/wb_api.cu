@@ -4,6 +4,7 @@
 // kernel launches on that stream (see enqueue_step); the only host<->device traffic per step is one
 // small D2H copy of the reduced sums.  There is no CPU fallback anywhere in this file.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -849,6 +850,60 @@ int wb_reconstruction(wb_embedder* h, int32_t count, const int32_t* nodes, doubl
             for (int i = 0; i < count; ++i)
                 if (res[3 * i + 2] != 0.0) { a += res[3 * i]; b += res[3 * i + 1]; k += 1.0; }
             if (k > 0.0) { out2[0] = a / k; out2[1] = b / k; }
+        } catch (...) { cleanup(); throw; }
+        cleanup();
+    });
+}
+
+int wb_edge_detection(wb_embedder* h, int64_t count, const int32_t* v, const int32_t* w, const uint8_t* is_edge, double* out3) {
+    if (h && (count < 0 || count > 0x7fffffff || (count > 0 && (!v || !w || !is_edge)) || !out3))
+        return fail(WB_ERR_INVALID, "wb_edge_detection: bad arguments");
+    if (h && !h->pending.empty()) return fail(WB_ERR_INVALID, "wb_edge_detection: steps in flight");
+    return guarded(h, [&] {
+        out3[0] = out3[1] = out3[2] = -1.0;                    // the reference's values when nothing was sampled (EdgeDetection.cpp:23-26)
+        const int n = h->n, d = h->dim;
+        if (count == 0 || n == 0) return;
+        std::vector<int> flags((size_t)count);
+        double numEdges = 0.0;
+        for (int64_t i = 0; i < count; ++i) {
+            if (v[i] < 0 || v[i] >= n || w[i] < 0 || w[i] >= n) throw std::runtime_error("wb_edge_detection: vertex id out of range");
+            flags[(size_t)i] = is_edge[i] ? 1 : 0;
+            numEdges += flags[(size_t)i];
+        }
+        const double N = (double)n, M = (double)(h->numDirected / 2), noM = N * (N - 1.0) / 2.0 - M;   // EdgeDetection.cpp:7-9
+        std::vector<double> wroot(n);
+        for (int u = 0; u < n; ++u) wroot[u] = std::pow(h->weights[u], 1.0 / (double)d);
+        const int items = (int)count, blocks = std::max(1, std::min(div_up(count, 256), 148 * 8));
+        double *dW = dalloc<double>(n), *dSimIn = dalloc<double>(count), *dSimOut = dalloc<double>(count);
+        int *dV = dalloc<int>(count), *dU = dalloc<int>(count), *dFlagIn = dalloc<int>(count), *dFlagOut = dalloc<int>(count), *dPrefix = dalloc<int>(count);
+        wb::F1Best* dBest = dalloc<wb::F1Best>(blocks + 1);
+        void* dTemp = nullptr;
+        auto cleanup = [&] {
+            for (void* p : {(void*)dW, (void*)dSimIn, (void*)dSimOut, (void*)dV, (void*)dU, (void*)dFlagIn, (void*)dFlagOut, (void*)dPrefix, (void*)dBest, dTemp})
+                if (p) cudaFree(p);
+        };
+        try {
+            cudaStream_t s = h->stream;
+            size_t sortBytes = 0, scanBytes = 0;
+            WB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sortBytes, dSimIn, dSimOut, dFlagIn, dFlagOut, items, 0, 64, s));
+            WB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, scanBytes, dFlagOut, dPrefix, items, s));
+            WB_CUDA(cudaMalloc(&dTemp, std::max<size_t>(std::max(sortBytes, scanBytes), 1)));
+            WB_CUDA(cudaMemcpyAsync(dW, wroot.data(), sizeof(double) * n, cudaMemcpyHostToDevice, s));
+            WB_CUDA(cudaMemcpyAsync(dV, v, sizeof(int) * count, cudaMemcpyHostToDevice, s));
+            WB_CUDA(cudaMemcpyAsync(dU, w, sizeof(int) * count, cudaMemcpyHostToDevice, s));
+            WB_CUDA(cudaMemcpyAsync(dFlagIn, flags.data(), sizeof(int) * count, cudaMemcpyHostToDevice, s));
+            WB_DISPATCH_V(h->V, wb::k_pair_similarity<V><<<div_up(count, 256), 256, 0, s>>>(h->x, dW, dV, dU, count, dSimIn));
+            // std::sort by similarity (EdgeSampler.cpp:62); the radix sort is stable, so ties keep the sampler's order
+            WB_CUDA(cub::DeviceRadixSort::SortPairs(dTemp, sortBytes, dSimIn, dSimOut, dFlagIn, dFlagOut, items, 0, 64, s));
+            WB_CUDA(cub::DeviceScan::InclusiveSum(dTemp, scanBytes, dFlagOut, dPrefix, items, s));
+            wb::k_f1_curve<<<blocks, 256, 0, s>>>(dPrefix, count, numEdges, (double)count - numEdges, M, noM, dBest);
+            wb::k_f1_best<<<1, 256, 0, s>>>(dBest, blocks, dBest + blocks);
+            h->launches += 3;
+            wb::F1Best best{};
+            WB_CUDA(cudaMemcpyAsync(&best, dBest + blocks, sizeof(best), cudaMemcpyDeviceToHost, s));
+            WB_CUDA(cudaStreamSynchronize(s));
+            WB_CUDA(cudaGetLastError());
+            out3[0] = best.precision; out3[1] = best.recall; out3[2] = best.f1;
         } catch (...) { cleanup(); throw; }
         cleanup();
     });
