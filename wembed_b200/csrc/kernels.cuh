@@ -1161,6 +1161,284 @@ __global__ void __launch_bounds__(256, WB_ATTRACT_MINBLOCKS) k_attract_update(co
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_attract_staged (WB_ATTRACT_STAGED=1; A/B candidate, NOT the default and not yet measured on a GPU):
+// the same fused step with every once-read stream staged through shared memory by bulk asynchronous copies
+// (cp.async.bulk + mbarrier), two stages deep, so that the only loads that occupy registers and scoreboards are the
+// neighbour-row gathers.  profiles/r1_summary.md section 7: k_attract_update is bound by memory latency / memory-level
+// parallelism - its dependent chain per pass is rowPtr -> {col, ws} -> rows -> {m, v, result row} - and every
+// register-based prefetch lost to the register budget.  Here one elected thread copies, for the pass after the current
+// one, the block's 256 / G own rows of x, m, v and forceRep, its window of rowPtr and the CSR entries {col, ws} of
+// those rows (at most kStageEdges of them; a pass with more reads the rest from global memory), and the warps find all
+// of it in shared memory when they get there.  Arithmetic and summation order are exactly those of k_attract_update, so
+// results are bit-identical to it.
+// Requirements on the host side (allocate(), WB_ATTRACT_STAGED): rowPtr, col and edgeWs padded by 8 entries (the copies
+// move whole 16-byte groups), vertex ranges of a block a multiple of 256 / G.
+#ifndef WB_ATTRACT_STAGED
+#define WB_ATTRACT_STAGED 0
+#endif
+constexpr int kStageEdges = 2048;         // CSR entries staged per pass (c3: ~1 280 per 128 vertices)
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WB_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WB_DONE_%=;\n"
+        "bra WB_WAIT_%=;\n"
+        "WB_DONE_%=:\n"
+        "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (bytes: multiple of 16, both addresses 16-byte aligned); completion is counted on `bar`
+__device__ __forceinline__ void bulk_copy(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+
+template <int V>
+struct AttractStage {                     // one pass of one block
+    static constexpr int G = attract_lanes(V), VPB = 256 / G, RS = 4 * V + 2;
+    float4 x[VPB * V], m[VPB * V], s[VPB * V];
+    long long rep[VPB * RS];
+    int col[kStageEdges + 8];
+    float ws[kStageEdges + 8];
+    int rowPtr[VPB + 8];
+};
+
+template <int V>
+__global__ void __launch_bounds__(256, 2)
+k_attract_staged(const float4* __restrict__ x, const float* __restrict__ edgeWs, const int* __restrict__ rowPtr, const int* __restrict__ col,
+                 int rangeBegin, int rangeEnd, int vertsPerBlock, const ForceParams fp, const long long* __restrict__ forceRep,
+                 const int* __restrict__ hubSlot, const double* __restrict__ hubForce, float4* __restrict__ xNew, float4* __restrict__ mom1,
+                 float4* __restrict__ mom2, float4* __restrict__ forceOut, double* __restrict__ partials, uint32_t* __restrict__ mtScratch) {
+    using Stage = AttractStage<V>;
+    constexpr int G = Stage::G, VPW = 32 / G, VPB = Stage::VPB, K = 2 + 4 * V, RS = Stage::RS, B = 4;
+    extern __shared__ __align__(128) unsigned char smemAtt[];
+    Stage* stage = reinterpret_cast<Stage*>(smemAtt);                                  // [2]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smemAtt + 2 * sizeof(Stage));         // [2]
+    double (*unitBuf)[4 * V] = reinterpret_cast<double (*)[4 * V]>(full + 2);          // [8]
+    double (*redBuf)[K] = reinterpret_cast<double (*)[K]>(unitBuf + 8);                // [8]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = lane % G, gi = lane / G;
+    const bool chunkLane = c < V;
+    const int vBegin = rangeBegin + blockIdx.x * vertsPerBlock;
+    const int vEnd = min(rangeEnd, vBegin + vertsPerBlock);
+    const int passes = vBegin < vEnd ? (vEnd - vBegin + VPB - 1) / VPB : 0;
+    double sumLossA = 0.0, sumLossR = 0.0, sumX[4] = {0.0, 0.0, 0.0, 0.0};
+    const float L = fp.edgeLength;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* xc = x + c;
+
+    // producer state (thread 0 only): CSR bounds of the pass to be copied next
+    int nextLo = 0, nextHi = 0;
+    auto passBounds = [&](int p, int& lo, int& hi) {
+        const int v0 = vBegin + p * VPB;
+        lo = __ldg(rowPtr + v0);
+        hi = __ldg(rowPtr + min(v0 + VPB, vEnd));
+    };
+    auto issue = [&](int p, int lo, int hi) {     // bulk copies of pass p into stage p & 1
+        Stage& st = stage[p & 1];
+        uint64_t* bar = full + (p & 1);
+        const int v0 = vBegin + p * VPB, rows = min(VPB, vEnd - v0);
+        const uint32_t rowBytes = (uint32_t)rows * V * 16u, repBytes = (uint32_t)rows * RS * 8u;
+        const int rp0 = v0 & ~3;                                            // rowPtr window from an aligned entry
+        const uint32_t rpBytes = (uint32_t)((v0 - rp0 + rows + 1 + 3) & ~3) * 4u;
+        const int e0 = lo & ~3;                                             // entries from an aligned entry
+        const int staged = min(hi - e0, kStageEdges + 4);
+        const uint32_t edgeBytes = (uint32_t)((max(staged, 0) + 3) & ~3) * 4u;
+        mbar_expect_tx(bar, 3u * rowBytes + repBytes + rpBytes + 2u * edgeBytes);
+        bulk_copy(st.x, x + (int64_t)v0 * V, rowBytes, bar);
+        bulk_copy(st.m, mom1 + (int64_t)v0 * V, rowBytes, bar);
+        bulk_copy(st.s, mom2 + (int64_t)v0 * V, rowBytes, bar);
+        bulk_copy(st.rep, forceRep + (int64_t)v0 * RS, repBytes, bar);
+        bulk_copy(st.rowPtr, rowPtr + rp0, rpBytes, bar);
+        if (edgeBytes) {
+            bulk_copy(st.col, col + e0, edgeBytes, bar);
+            bulk_copy(st.ws, edgeWs + e0, edgeBytes, bar);
+        }
+    };
+    if (threadIdx.x == 0) {
+        mbar_init(full, 1);
+        mbar_init(full + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && passes > 0) {
+        int lo, hi;
+        passBounds(0, lo, hi);
+        issue(0, lo, hi);
+        if (passes > 1) passBounds(1, nextLo, nextHi);
+    }
+
+    for (int p = 0; p < passes; ++p) {
+        // every warp has left stage (p + 1) & 1 (barrier at the end of pass p - 1): refill it, and fetch the bounds after that
+        if (threadIdx.x == 0 && p + 1 < passes) {
+            issue(p + 1, nextLo, nextHi);
+            if (p + 2 < passes) passBounds(p + 2, nextLo, nextHi);
+        }
+        mbar_wait(full + (p & 1), (uint32_t)(p >> 1) & 1u);
+        const Stage& st = stage[p & 1];
+        const int v0 = vBegin + p * VPB;
+        const int slot = warp * VPW + gi, v = v0 + slot;
+        const bool valid = v < vEnd;
+        const int rpOff = v0 - (v0 & ~3);
+        const int e0 = st.rowPtr[rpOff] & ~3;                               // global index of staged entry 0
+        float4 xv = zero4;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0}, loss = 0.0;
+        int nCoincident = 0, e = 0, end = 0, hub = -1;
+        if (valid) {
+            if (chunkLane) xv = st.x[slot * V + c];
+            hub = hubSlot ? __ldg(hubSlot + v) : -1;
+            if (hub < 0) { e = st.rowPtr[rpOff + slot]; end = st.rowPtr[rpOff + slot + 1]; }
+        }
+        int len = end - e;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+        for (int i = 0; i < len; i += B) {
+            bool has[B];
+            int u[B];
+            float wsE[B], dd[B];
+            float4 r[B];
+#pragma unroll
+            for (int j = 0; j < B; ++j) {
+                const int idx = e + i + j, at = idx - e0;
+                has[j] = idx < end;
+                const bool inStage = at < kStageEdges + 4;
+                u[j] = has[j] ? (inStage ? st.col[at] : __ldg(col + idx)) : 0;
+                wsE[j] = has[j] ? (inStage ? st.ws[at] : __ldg(edgeWs + idx)) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < B; ++j) r[j] = (has[j] && chunkLane) ? __ldg(xc + (int64_t)u[j] * V) : xv;
+#pragma unroll
+            for (int j = 0; j < B; ++j) dd[j] = chunkLane ? chunk_dist2(r[j], xv) : 0.f;
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) {
+#pragma unroll
+                for (int j = 0; j < B; ++j) dd[j] += __shfl_xor_sync(0xffffffffu, dd[j], o);
+            }
+            float bx = 0.f, by = 0.f, bz = 0.f, bw = 0.f, bl = 0.f;
+            if (V > 1 || fp.dim > 1) {                          // same arithmetic as k_attract_update (WB_ATTRACT_FAST)
+#pragma unroll
+                for (int j = 0; j < B; ++j) {
+                    const float inv = rsqrt_approx(dd[j]);
+                    const float dist = dd[j] * inv;
+                    nCoincident += (int)(has[j] && dd[j] == 0.f);
+                    const bool act = has[j] && dd[j] >= kFltMin && dist * wsE[j] > L;
+                    const float sc = act ? fp.attractionScale * wsE[j] * inv : 0.f;
+                    bx = fmaf(sc, r[j].x - xv.x, bx); by = fmaf(sc, r[j].y - xv.y, by);
+                    bz = fmaf(sc, r[j].z - xv.z, bz); bw = fmaf(sc, r[j].w - xv.w, bw);
+                    bl += act ? fmaf(-L, rcp_approx(wsE[j]), dist) : 0.f;
+                }
+            } else {                                            // one dimension: exact +-1 unit vectors, IEEE arithmetic
+#pragma unroll
+                for (int j = 0; j < B; ++j) {
+                    if (!has[j]) continue;
+                    const float dist = sqrtf(dd[j]);
+                    if (dist <= 0.f) { ++nCoincident; continue; }
+                    if (dist * wsE[j] > L) {
+                        bx += copysignf(fp.attractionScale * wsE[j], r[j].x - xv.x);
+                        bl += dist - L / wsE[j];
+                    }
+                }
+            }
+            acc[0] += (double)bx; acc[1] += (double)by; acc[2] += (double)bz; acc[3] += (double)bw;
+            loss += (double)bl;
+        }
+        const long long* rep = st.rep + slot * RS;
+        if (valid && hub >= 0) {
+            const double* hf = hubForce + (int64_t)hub * (4 * V + 2);
+            if (chunkLane) { acc[0] = hf[4 * c]; acc[1] = hf[4 * c + 1]; acc[2] = hf[4 * c + 2]; acc[3] = hf[4 * c + 3]; }
+            loss = hf[4 * V];
+            nCoincident = (int)hf[4 * V + 1];
+        }
+        if (valid) nCoincident += (int)rep[4 * V + 1];
+        uint32_t todo = __ballot_sync(0xffffffffu, nCoincident > 0 && c == 0);
+        while (todo) {                                          // coincident partners (:150-155, :183-188), one vertex at a time
+            const int l = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            if (lane == l)
+                random_unit_vector(mtScratch + ((size_t)blockIdx.x * 8 + warp) * 624, fp.seed, (uint32_t)v, fp.iteration, fp.dim, unitBuf[warp]);
+            __syncwarp();
+            if (lane / G == l / G && chunkLane) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (4 * c + i < fp.dim) acc[i] += nCoincident * unitBuf[warp][4 * c + i];
+            }
+            __syncwarp();
+        }
+        if (valid && c == 0) {
+            sumLossA += loss;
+            sumLossR += (double)rep[4 * V] * fp.invFixLoss;
+        }
+        if (valid && chunkLane) {
+            const int64_t at = (int64_t)v * V + c;
+            const longlong2 f01 = *reinterpret_cast<const longlong2*>(rep + 4 * c), f23 = *(reinterpret_cast<const longlong2*>(rep + 4 * c) + 1);
+            float4 f = make_float4((float)(acc[0] + (double)f01.x * fp.invFixForce), (float)(acc[1] + (double)f01.y * fp.invFixForce),
+                                   (float)(acc[2] + (double)f23.x * fp.invFixForce), (float)(acc[3] + (double)f23.y * fp.invFixForce));
+            if (fp.centreScale != 0.f) {
+                f.x = fmaf(-fp.centreScale, xv.x, f.x); f.y = fmaf(-fp.centreScale, xv.y, f.y);
+                f.z = fmaf(-fp.centreScale, xv.z, f.z); f.w = fmaf(-fp.centreScale, xv.w, f.w);
+            }
+            if (fp.keepForces) forceOut[at] = f;
+            float4 xn;
+            if (fp.optimizer == 1) {
+                const float4 m = st.m[slot * V + c], s = st.s[slot * V + c];
+                const float fe[4] = {f.x, f.y, f.z, f.w};
+                float me[4] = {m.x, m.y, m.z, m.w}, se[4] = {s.x, s.y, s.z, s.w};
+                float xe[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    me[i] = fp.beta1 * me[i] + (1.f - fp.beta1) * fe[i];
+                    se[i] = fp.beta2 * se[i] + (1.f - fp.beta2) * fe[i] * fe[i];
+                    const float mHat = me[i] * fp.invBias1, vHat = se[i] * fp.invBias2;
+                    xe[i] = fmaf(fp.lr * mHat, rcp_approx(sqrt_approx(vHat) + fp.eps), xe[i]);
+                }
+                mom1[at] = make_float4(me[0], me[1], me[2], me[3]);
+                mom2[at] = make_float4(se[0], se[1], se[2], se[3]);
+                xn = make_float4(xe[0], xe[1], xe[2], xe[3]);
+            } else {
+                const float cap = fp.maxDisplacement;
+                xn.x = xv.x + fminf(fmaxf(f.x, -cap), cap) * fp.lr;
+                xn.y = xv.y + fminf(fmaxf(f.y, -cap), cap) * fp.lr;
+                xn.z = xv.z + fminf(fmaxf(f.z, -cap), cap) * fp.lr;
+                xn.w = xv.w + fminf(fmaxf(f.w, -cap), cap) * fp.lr;
+            }
+            xNew[at] = xn;
+            sumX[0] += (double)xn.x; sumX[1] += (double)xn.y; sumX[2] += (double)xn.z; sumX[3] += (double)xn.w;
+        }
+        __syncthreads();                                        // stage p & 1 may be refilled (pass p + 2) from here on
+    }
+#pragma unroll
+    for (int o = G; o < 32; o <<= 1) {
+        sumLossA += __shfl_xor_sync(0xffffffffu, sumLossA, o);
+        sumLossR += __shfl_xor_sync(0xffffffffu, sumLossR, o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sumX[i] += __shfl_xor_sync(0xffffffffu, sumX[i], o);
+    }
+    if (lane == 0) { redBuf[warp][0] = sumLossA; redBuf[warp][1] = sumLossR; }
+    if (lane < G && chunkLane) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) redBuf[warp][2 + 4 * c + i] = sumX[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < K) {
+        double sacc = 0.0;
+        for (int w = 0; w < 8; ++w) sacc += redBuf[w][threadIdx.x];
+        partials[(int64_t)blockIdx.x * K + threadIdx.x] = sacc;
+    }
+}
+template <int V>
+constexpr size_t attract_staged_smem() { return 2 * sizeof(AttractStage<V>) + 2 * sizeof(uint64_t) + 8 * (4 * V) * sizeof(double) + 8 * (2 + 4 * V) * sizeof(double); }
+
+
+// ---------------------------------------------------------------------------------------------
 // Deterministic reduction of per-block partial sums: block k reduces column k.
 // Thread t adds rows t, t+256, ... in order, then the 256 thread sums are combined by a fixed tree.
 __global__ void __launch_bounds__(256) k_reduce_partials(const double* __restrict__ partials, int rows, int cols,

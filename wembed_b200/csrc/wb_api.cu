@@ -94,6 +94,7 @@ struct wb_embedder {
     int* invOrder = nullptr;              // vertex -> sorted position
     float* iw = nullptr;
     float* edgeWs = nullptr;              // ws(v,u) = iw_v * iw_u of every CSR entry
+    uint32_t* mtScratch = nullptr;        // WB_ATTRACT_STAGED: tie-break generator state, one row of 624 words per warp
     int* chunkCounter = nullptr;          // work counter of the persistent repulsion kernel
     int numHeavy = 0;                     // vertices of weight >= kHeavyWeight x mean, walked by k_repulse_heavy
     int *heavyVertex = nullptr, *heavySlot = nullptr;
@@ -168,10 +169,24 @@ constexpr int kHubThreshold = 96;   // CSR rows longer than this are summed by o
 
 inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// Block -> vertex-range assignment of the fused attraction + optimizer kernel over `own` vertices.  k_attract_update: many blocks of
+// a few passes; k_attract_staged (WB_ATTRACT_STAGED): four blocks per SM's two resident slots, each a long pipelined run of passes.
+inline void attract_grid(int V, int own, int& blocks, int& vertsPerBlock) {
+    const int perPass = 256 / wb::attract_lanes(V);      // vertices per block iteration
+#if WB_ATTRACT_STAGED
+    const int maxBlocks = 148 * 4;
+#else
+    const int maxBlocks = 148 * 16;
+#endif
+    blocks = std::max(1, std::min(div_up(own, perPass), maxBlocks));
+    vertsPerBlock = std::max(perPass, div_up(div_up(own, blocks), perPass) * perPass);
+    blocks = std::max(1, div_up(own, vertsPerBlock));
+}
+
 void free_all(wb_embedder* h) {
     auto F = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
     F(h->rowPtr); F(h->col); F(h->x); F(h->xNew); F(h->mom1); F(h->mom2); F(h->forceRep); F(h->force);
-    F(h->iw); F(h->invOrder); F(h->edgeWs); F(h->chunkCounter); F(h->hubVertex); F(h->hubSlot); F(h->hubForce); F(h->heavyVertex); F(h->heavySlot); F(h->keysIn); F(h->keysOut); F(h->valsIn); F(h->valsOut);
+    F(h->iw); F(h->invOrder); F(h->edgeWs); F(h->mtScratch); F(h->chunkCounter); F(h->hubVertex); F(h->hubSlot); F(h->hubForce); F(h->heavyVertex); F(h->heavySlot); F(h->keysIn); F(h->keysOut); F(h->valsIn); F(h->valsOut);
     F(h->cubTemp); F(h->momentPartials); F(h->quant); F(h->ids); F(h->blk); F(h->blkH);
     for (int l = 0; l < wb::kMaxLevels; ++l) { F(h->lvlLo[l]); if (l > 0) F(h->lvlHi[l]); F(h->lvlBound[l]); }
     F(h->partialsForce); F(h->partialsRep); F(h->partialsObs); F(h->sumsAll); F(h->gathered); F(h->localSums);
@@ -213,8 +228,9 @@ void choose_fixed_scales(wb_embedder* h, double maxIw, double minIw) {
 void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
     const int n = h->n, V = h->V;
     WB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    h->rowPtr = dalloc<int>(n + 1);
-    h->col = dalloc<int>(h->numDirected);
+    // (+ 8: k_attract_staged copies whole 16-byte groups of these arrays)
+    h->rowPtr = dalloc<int>(n + 1 + 8);
+    h->col = dalloc<int>(h->numDirected + 8);
     WB_CUDA(cudaMemcpyAsync(h->rowPtr, rowPtr, sizeof(int) * (n + 1), cudaMemcpyHostToDevice, h->stream));
     if (h->numDirected) WB_CUDA(cudaMemcpyAsync(h->col, col, sizeof(int) * h->numDirected, cudaMemcpyHostToDevice, h->stream));
 
@@ -246,7 +262,7 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
         WB_CUDA(cudaMemsetAsync(*p, 0, std::max<size_t>(rows, 1) * sizeof(float4), h->stream));
     }
     h->iw = dalloc<float>(n);
-    h->edgeWs = dalloc<float>(h->numDirected);
+    h->edgeWs = dalloc<float>(h->numDirected + 8);
     if (n) wb::k_fill<float><<<div_up(n, 256), 256, 0, h->stream>>>(h->iw, n, 1.0f);
     if (h->numDirected) wb::k_fill<float><<<div_up(h->numDirected, 256), 256, 0, h->stream>>>(h->edgeWs, h->numDirected, 1.0f);
     h->weights.assign(n, 1.0);
@@ -316,10 +332,11 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
     t.ids = h->ids;
 
     // reductions: fixed block -> vertex-range assignment so the sums do not depend on scheduling
-    const int groupsPerBlock = 256 / wb::attract_lanes(V);      // vertices per block iteration
-    h->forceBlocks = std::max(1, std::min(div_up(n, groupsPerBlock), 148 * 16));
-    h->forceVertsPerBlock = std::max(groupsPerBlock, div_up(div_up(n, h->forceBlocks), groupsPerBlock) * groupsPerBlock);
-    h->forceBlocks = std::max(1, div_up(n, h->forceVertsPerBlock));
+    attract_grid(V, n, h->forceBlocks, h->forceVertsPerBlock);
+#if WB_ATTRACT_STAGED
+    h->mtScratch = dalloc<uint32_t>((size_t)h->forceBlocks * 8 * 624);   // sharding only shrinks the grid
+    WB_DISPATCH_V(V, WB_CUDA(cudaFuncSetAttribute(wb::k_attract_staged<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wb::attract_staged_smem<V>())));
+#endif
     {   // persistent repulsion grid: enough resident blocks to fill every SM, never more than there are chunks
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->opt.device);
@@ -449,9 +466,15 @@ void enqueue_step(wb_embedder* h, double learningRate) {
         WB_DISPATCH_V(V, wb::k_attract_hubs<V><<<h->numHubs, 256, 0, s>>>(h->x, h->edgeWs, h->rowPtr, h->col, h->hubVertex, fp, h->hubForce));
         h->launches += 1;
     }
+#if WB_ATTRACT_STAGED
+    WB_DISPATCH_V(V, wb::k_attract_staged<V><<<h->forceBlocks, 256, wb::attract_staged_smem<V>(), s>>>(
+                         h->x, h->edgeWs, h->rowPtr, h->col, h->ownBegin, h->ownEnd, h->forceVertsPerBlock, fp, h->forceRep,
+                         h->hubSlot, h->hubForce, h->xNew, h->mom1, h->mom2, h->force, h->partialsForce, h->mtScratch));
+#else
     WB_DISPATCH_V(V, wb::k_attract_update<V><<<h->forceBlocks, 256, 0, s>>>(
                          h->x, h->edgeWs, h->rowPtr, h->col, h->ownBegin, h->ownEnd, h->forceVertsPerBlock, fp, h->forceRep,
                          h->hubSlot, h->hubForce, h->xNew, h->mom1, h->mom2, h->force, h->partialsForce));
+#endif
     wb::k_reduce_partials<<<K, 256, 0, s>>>(h->partialsForce, h->forceBlocks, K, sums);
     if (sharded) {   // {lossA, lossR, sum xnew[k], pairs, tests}: all-gather, then every rank adds in rank order
         if (nccl().allGather(sums, h->gathered, K + 3, ncclDouble, h->comm, s) != ncclSuccess) throw std::runtime_error("ncclAllGather (force sums) failed");
@@ -786,10 +809,8 @@ int wb_comm_init(wb_embedder* h, const char* id128, int32_t rank, int32_t world)
             *p = q;
         }
         // block -> vertex-range assignment over the owned range
-        const int own = std::max(1, h->ownEnd - h->ownBegin), groupsPerBlock = 256 / wb::attract_lanes(V), K = 2 + 4 * V;
-        h->forceBlocks = std::max(1, std::min(div_up(own, groupsPerBlock), 148 * 16));
-        h->forceVertsPerBlock = std::max(groupsPerBlock, div_up(div_up(own, h->forceBlocks), groupsPerBlock) * groupsPerBlock);
-        h->forceBlocks = std::max(1, div_up(own, h->forceVertsPerBlock));
+        const int own = std::max(1, h->ownEnd - h->ownBegin), K = 2 + 4 * V;
+        attract_grid(V, own, h->forceBlocks, h->forceVertsPerBlock);
             h->obsBlocks = std::max(1, std::min(div_up(own, 256), 148 * 8));
         h->obsVertsPerBlock = std::max(256, div_up(div_up(own, h->obsBlocks), 256) * 256);
         h->obsBlocks = std::max(1, div_up(own, h->obsVertsPerBlock));
