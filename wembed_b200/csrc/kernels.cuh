@@ -46,6 +46,10 @@ struct TreeView {             // implicit 8-ary box hierarchy, structure-of-plan
     // [lo: HV x 8 chunks of 8 halves | hi: HV x 8 | meta: 8 x BoxMeta], HV = ceil(V / 2); see k_repulse_pairs
     const float4* blkH;
     const QuantParams* quant;
+    // WB_POINT_HALF: the sorted points once more as half_chunks(V) planes of 8 halves (point - centre, rounded to nearest) and per
+    // point {iw, 1 / iw rounded up, length of the rounding displacement * margin, -}
+    const float4* ptsH;
+    const float4* pmeta;
 };
 
 // per-child record of a block (16 bytes, read with one 128-bit load)
@@ -59,6 +63,12 @@ constexpr uint32_t kLeafFlag = 0x80000000u;
 __host__ __device__ constexpr int block_float4s(int V) { return (2 * V + 1) * kFan; }
 __host__ __device__ constexpr int half_chunks(int V) { return (V + 1) / 2; }            // 16-byte chunks of 8 halves per row
 __host__ __device__ constexpr int half_block_float4s(int V) { return (2 * half_chunks(V) + 1) * kFan; }
+// relative slack of a half-precision sum of squares over 8 * half_chunks(V) dimensions, as a factor on the threshold BEFORE it is
+// squared: (4 HV + 2) roundings of 2^-11 each, doubled, first-order square root rounded up
+__host__ __device__ constexpr float half_margin_root(int V) { return 1.f + (float)(4 * half_chunks(V) + 6) * 4.9e-4f + 1.0e-6f; }
+#ifndef WB_POINT_HALF
+#define WB_POINT_HALF 0            // 1: the point rounds prefilter in half precision too (A/B candidate, not yet measured)
+#endif
 
 // initial state of the block buffer: coordinates far from everything, meta records all zero (endPos = 0: never passes)
 template <int V>
@@ -261,7 +271,8 @@ __global__ void __launch_bounds__(256) k_build_leaves(const float4* __restrict__
                                                       int stride0, float* __restrict__ bound0, int* __restrict__ ids, int* __restrict__ invOrder,
                                                       float4* __restrict__ lo1, float4* __restrict__ hi1,
                                                       float* __restrict__ bound1, int stride1, float4* __restrict__ blk, int blockOff1,
-                                                      float4* __restrict__ blkH, const QuantParams* __restrict__ qp) {
+                                                      float4* __restrict__ blkH, const QuantParams* __restrict__ qp,
+                                                      float4* __restrict__ ptsH, float4* __restrict__ pmeta) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;   // sorted position
     const int leaf = i >> kFanLog2, j = i & (kFan - 1);
     const bool real = i < n;
@@ -283,6 +294,42 @@ __global__ void __launch_bounds__(256) k_build_leaves(const float4* __restrict__
 #pragma unroll
         for (int c = 0; c < V; ++c) { lo[c] = make_float4(3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f); hi[c] = make_float4(-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f); }
     }
+#if WB_POINT_HALF
+    if (i < stride0) {
+        // the point as the half-precision point rounds see it (padding points: +inf, they fail every test) and how far the rounding moved it
+        constexpr int HV = half_chunks(V);
+        float d2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < HV; ++k) {
+            __half2 h[4];
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int ch = 2 * k + half;
+                float e[4] = {0.f, 0.f, 0.f, 0.f};
+                if (ch < V) {
+                    const float4 p = real ? lo[ch] : make_float4(kPadCoord, kPadCoord, kPadCoord, kPadCoord);
+                    e[0] = p.x - qp->centre[4 * ch]; e[1] = p.y - qp->centre[4 * ch + 1];
+                    e[2] = p.z - qp->centre[4 * ch + 2]; e[3] = p.w - qp->centre[4 * ch + 3];
+                }
+                h[2 * half] = __floats2half2_rn(e[0], e[1]);
+                h[2 * half + 1] = __floats2half2_rn(e[2], e[3]);
+                const float2 b0 = __half22float2(h[2 * half]), b1 = __half22float2(h[2 * half + 1]);
+                d2 = fmaf(e[0] - b0.x, e[0] - b0.x, d2); d2 = fmaf(e[1] - b0.y, e[1] - b0.y, d2);
+                d2 = fmaf(e[2] - b1.x, e[2] - b1.x, d2); d2 = fmaf(e[3] - b1.y, e[3] - b1.y, d2);
+            }
+            float4 packed;
+            packed.x = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h[0]));
+            packed.y = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h[1]));
+            packed.z = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h[2]));
+            packed.w = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h[3]));
+            ptsH[(int64_t)k * stride0 + i] = packed;
+        }
+        float delta = real ? sqrtf(d2) * 1.001f * half_margin_root(V) : 0.f;
+        if (!(delta >= 0.f)) delta = __int_as_float(0x7f800000);          // beyond the half range: every query keeps this point
+        const float iwp = real ? b : 1.f;
+        pmeta[i] = make_float4(iwp, __frcp_ru(iwp), delta, 0.f);
+    }
+#endif
 #pragma unroll
     for (int o = kFan / 2; o > 0; o >>= 1) {
 #pragma unroll
@@ -484,9 +531,8 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
     constexpr int WARPS = repulse_warps(V), STACK = 56 * kMaxLevels + 72;   // LIFO bound: <= 56 leftovers per level + one push of 64
     constexpr int HV = half_chunks(V);
     constexpr int QROW = V + 1 + (HALF ? HV : 0), BLK = HALF ? half_block_float4s(V) : block_float4s(V);
-    // relative slack of the half-precision sum of squares: (4 HV + 2) roundings of 2^-11 each, doubled
-    // (the threshold is scaled by its square root before it is squared; a first-order expansion rounded up)
-    constexpr float kHalfMarginRoot = 1.f + (float)(4 * HV + 6) * 4.9e-4f + 1.0e-6f;
+    // relative slack of the half-precision sum of squares, applied to the threshold before it is squared
+    constexpr float kHalfMarginRoot = half_margin_root(V);
     constexpr uint32_t kRefMask = 0x07ffffffu;   // low 27 bits of an entry: block (stack) or leaf (leaf queue); high 5 bits: query lane
     // dynamic shared memory (repulse_smem_bytes): per warp
     //   query rows [32][QROW]: V coordinate chunks + {iw, sorted position + 1, threshold factor, |delta|} (+ HV chunks of 8 halves: q - centre)
@@ -587,23 +633,64 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
         r.qq = entry >> 27;
         r.idx = active ? (int)(entry & kRefMask) * kFan + c : 0;
         const float4* qrow = myQ + r.qq * QROW;
-        float4 pu[V], qv[V];
+        if constexpr (HALF && WB_POINT_HALF) {
+            // half-precision prefilter: |p - q| >= |p_h - q_h| (1 - eps) - |delta_q| - |delta_p|; survivors are tested exactly in resolveHit
+            float4 ph[HV], qh[HV];
 #pragma unroll
-        for (int k = 0; k < V; ++k) pu[k] = __ldg(t.lo[0] + (int64_t)k * t.stride[0] + r.idx);
-        const float iwu = __ldg(t.bound[0] + r.idx);
+            for (int k = 0; k < HV; ++k) ph[k] = __ldg(t.ptsH + (int64_t)k * t.stride[0] + r.idx);
+            const float4 pm = __ldg(t.pmeta + r.idx);
 #pragma unroll
-        for (int k = 0; k < V; ++k) qv[k] = qrow[k];
-        const float4 qm = qrow[V];
-        r.ws = qm.x * iwu;
-        r.d2 = point_dist2<V>(qv, pu);
-        r.hit = active && (uint32_t)r.idx >= __float_as_uint(qm.y) && r.d2 * r.ws * r.ws <= fp.pruneL2;   // idx > qpos
-        return r;
+            for (int k = 0; k < HV; ++k) qh[k] = qrow[V + 1 + k];
+            const float4 qm = qrow[V];
+            const __half2 zero2 = __float2half2_rn(0.f);
+            __half2 acc0 = zero2, acc1 = zero2;
+#pragma unroll
+            for (int k = 0; k < HV; ++k) {
+                const float pw[4] = {ph[k].x, ph[k].y, ph[k].z, ph[k].w}, qw[4] = {qh[k].x, qh[k].y, qh[k].z, qh[k].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const __half2 e = __hsub2(*reinterpret_cast<const __half2*>(&pw[i]), *reinterpret_cast<const __half2*>(&qw[i]));
+                    if (i & 1) acc1 = __hfma2(e, e, acc1); else acc0 = __hfma2(e, e, acc0);
+                }
+            }
+            const __half2 acc = __hadd2(acc0, acc1);
+            const float sum = __half2float(__hadd(__low2half(acc), __high2half(acc)));
+            const float thr = fmaf(qm.z, pm.y, qm.w + pm.z);
+            const float lim = thr * thr;
+            r.ws = qm.x * pm.x;
+            r.d2 = -1.f;                                       // computed exactly by resolveHit
+            // NaN sums (inf - inf: both beyond the half range) must not prune: !(sum > lim)
+            r.hit = active && (uint32_t)r.idx >= __float_as_uint(qm.y) && (!(sum > lim) || lim >= 6.0e4f);   // idx > qpos
+            return r;
+        } else {
+            float4 pu[V], qv[V];
+#pragma unroll
+            for (int k = 0; k < V; ++k) pu[k] = __ldg(t.lo[0] + (int64_t)k * t.stride[0] + r.idx);
+            const float iwu = __ldg(t.bound[0] + r.idx);
+#pragma unroll
+            for (int k = 0; k < V; ++k) qv[k] = qrow[k];
+            const float4 qm = qrow[V];
+            r.ws = qm.x * iwu;
+            r.d2 = point_dist2<V>(qv, pu);
+            r.hit = active && (uint32_t)r.idx >= __float_as_uint(qm.y) && r.d2 * r.ws * r.ws <= fp.pruneL2;   // idx > qpos
+            return r;
+        }
     };
     // A hit is resolved by the lane that found it: exact predicate, neighbour filter, then the term goes to the rows of both
     // vertices (hits are rare - a handful per query - so this branch is cold).
     auto resolveHit = [&](const PointSlot& r) {
         if (!r.hit) return;
-        const float dist = sqrtf(r.d2), ws = r.ws;
+        float d2 = r.d2;
+        if constexpr (HALF && WB_POINT_HALF) {                 // the exact squared distance, same operation order as the fp32 point round
+            const float4* qrow = myQ + r.qq * QROW;
+            float4 pu[V], qv[V];
+#pragma unroll
+            for (int k = 0; k < V; ++k) pu[k] = __ldg(t.lo[0] + (int64_t)k * t.stride[0] + r.idx);
+#pragma unroll
+            for (int k = 0; k < V; ++k) qv[k] = qrow[k];
+            d2 = point_dist2<V>(qv, pu);
+        }
+        const float dist = sqrtf(d2), ws = r.ws;
         if (dist > 0.f && !(dist * ws <= L)) return;         // exact predicate; dist <= 0 is the coincident case
         const float4* qrow = myQ + r.qq * QROW;
         const int u = __ldg(t.ids + r.idx);

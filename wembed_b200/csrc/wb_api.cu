@@ -117,6 +117,7 @@ struct wb_embedder {
     float* momentPartials = nullptr;
     wb::QuantParams* quant = nullptr;
     float4* blkH = nullptr;               // half-precision copy of the array-of-blocks tree (box rounds of k_repulse_pairs)
+    float4 *ptsH = nullptr, *pmeta = nullptr;   // WB_POINT_HALF: half-precision copy of the sorted points + per-point record
     float halfSigmaLimit = 0.f;           // layouts with a larger per-dimension sd walk the fp32 boxes (k_quant_params)
     int halfMode = -1;                    // WB_HALF_BOXES: 0 never, 1 always, unset: by the layout
     float4* lvlLo[wb::kMaxLevels] = {};
@@ -187,7 +188,7 @@ void free_all(wb_embedder* h) {
     auto F = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
     F(h->rowPtr); F(h->col); F(h->x); F(h->xNew); F(h->mom1); F(h->mom2); F(h->forceRep); F(h->force);
     F(h->iw); F(h->invOrder); F(h->edgeWs); F(h->mtScratch); F(h->chunkCounter); F(h->hubVertex); F(h->hubSlot); F(h->hubForce); F(h->heavyVertex); F(h->heavySlot); F(h->keysIn); F(h->keysOut); F(h->valsIn); F(h->valsOut);
-    F(h->cubTemp); F(h->momentPartials); F(h->quant); F(h->ids); F(h->blk); F(h->blkH);
+    F(h->cubTemp); F(h->momentPartials); F(h->quant); F(h->ids); F(h->blk); F(h->blkH); F(h->ptsH); F(h->pmeta);
     for (int l = 0; l < wb::kMaxLevels; ++l) { F(h->lvlLo[l]); if (l > 0) F(h->lvlHi[l]); F(h->lvlBound[l]); }
     F(h->partialsForce); F(h->partialsRep); F(h->partialsObs); F(h->sumsAll); F(h->gathered); F(h->localSums);
     if (h->comm) { nccl().commDestroy(h->comm); h->comm = nullptr; }
@@ -323,6 +324,14 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
         WB_CUDA(cudaMemsetAsync(h->blkH, 0, h4 * sizeof(float4), h->stream));
         t.blkH = h->blkH;
         t.quant = h->quant;
+#if WB_POINT_HALF
+        h->ptsH = dalloc<float4>((size_t)wb::half_chunks(V) * t.stride[0]);
+        h->pmeta = dalloc<float4>(t.stride[0]);
+        WB_CUDA(cudaMemsetAsync(h->ptsH, 0, sizeof(float4) * wb::half_chunks(V) * t.stride[0], h->stream));
+        WB_CUDA(cudaMemsetAsync(h->pmeta, 0, sizeof(float4) * t.stride[0], h->stream));
+#endif
+        t.ptsH = h->ptsH;
+        t.pmeta = h->pmeta;
         // the walk's per-warp queries + stacks exceed the 48 KB static limit for the wider rows
         WB_DISPATCH_V(V, WB_CUDA(cudaFuncSetAttribute(wb::k_repulse_pairs<V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wb::repulse_smem_bytes(V, false)));
                          WB_CUDA(cudaFuncSetAttribute(wb::k_repulse_pairs<V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wb::repulse_smem_bytes(V, true))));
@@ -371,7 +380,7 @@ void enqueue_index(wb_embedder* h, const float* pointBound) {
     const wb::TreeView& t = h->tree;
     WB_DISPATCH_V(V, wb::k_build_leaves<V><<<div_up(t.stride[0], 256), 256, 0, s>>>(
                          h->x, pointBound, h->valsOut, n, h->lvlLo[0], t.stride[0], h->lvlBound[0], h->ids, h->invOrder, h->lvlLo[1], h->lvlHi[1],
-                         h->lvlBound[1], t.stride[1], h->blk, t.blockOff[1], h->blkH, h->quant));
+                         h->lvlBound[1], t.stride[1], h->blk, t.blockOff[1], h->blkH, h->quant, h->ptsH, h->pmeta));
     for (int l = 2; l <= t.numLevels; ++l) {
         WB_DISPATCH_V(V, wb::k_build_level<V><<<div_up((int64_t)t.count[l] * kFan, 256), 256, 0, s>>>(
                              h->lvlLo[l - 1], h->lvlHi[l - 1], h->lvlBound[l - 1], t.count[l - 1], t.stride[l - 1], h->lvlLo[l], h->lvlHi[l],
