@@ -101,6 +101,9 @@ void wb_options_default(wb_options* o);
  * ascending, no self loops, symmetric - the invariants of Graph, Graph.cpp:87-150),
  * allocates positions / weights / force / Adam moments.  Positions start at 0 and
  * weights at 1 until wb_set_coordinates / wb_set_weights are called.
+ * Environment (read once per handle, for A/B runs and tests only - results never depend on it): WB_HALF_BOXES=0 / 1 forces the
+ * fp32 / the half-precision box format of the repulsion walk; unset, the device picks per step from the layout's spread
+ * (DESIGN.md section 3.1).
  */
 int wb_create(wb_embedder** out, int32_t n, const int32_t* row_ptr, const int32_t* col, const wb_options* opts);
 int wb_destroy(wb_embedder* h);

@@ -57,7 +57,7 @@ struct BoxMeta {
     float bound;              // min over the subtree of the pruning weight factor
     uint32_t childRef;        // level >= 2: block holding this node's children; level 1: kLeafFlag | leaf index
     uint32_t endPos;          // one past the last sorted position of the subtree
-    uint32_t pad;
+    float invBound;           // 1 / bound, rounded up (threshold factor of the half-precision box rounds)
 };
 constexpr uint32_t kLeafFlag = 0x80000000u;
 __host__ __device__ constexpr int block_float4s(int V) { return (2 * V + 1) * kFan; }
