@@ -8,7 +8,9 @@ cd "$(dirname "$0")/.."
 scripts/build_variant.sh default
 scripts/build_variant.sh staged -DWB_ATTRACT_STAGED=1
 scripts/build_variant.sh pointhalf -DWB_POINT_HALF=1
-for v in staged pointhalf; do
+scripts/build_variant.sh hitbatch -DWB_HIT_BATCH=1
+scripts/build_variant.sh both -DWB_POINT_HALF=1 -DWB_HIT_BATCH=1
+for v in staged pointhalf hitbatch both; do
   WB_LIB=$PWD/wembed_b200/lib/variants/libwb_$v.so timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 done
-timeout 300 python scripts/gpu_ab.py c3 20 60 wembed_b200/lib/variants/libwb_default.so wembed_b200/lib/variants/libwb_staged.so wembed_b200/lib/variants/libwb_pointhalf.so
+timeout 300 python scripts/gpu_ab.py c3 20 60 wembed_b200/lib/variants/libwb_default.so wembed_b200/lib/variants/libwb_staged.so wembed_b200/lib/variants/libwb_pointhalf.so wembed_b200/lib/variants/libwb_hitbatch.so wembed_b200/lib/variants/libwb_both.so

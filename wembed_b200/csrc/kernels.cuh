@@ -66,6 +66,9 @@ __host__ __device__ constexpr int half_block_float4s(int V) { return (2 * half_c
 // relative slack of a half-precision sum of squares over 8 * half_chunks(V) dimensions, as a factor on the threshold BEFORE it is
 // squared: (4 HV + 2) roundings of 2^-11 each, doubled, first-order square root rounded up
 __host__ __device__ constexpr float half_margin_root(int V) { return 1.f + (float)(4 * half_chunks(V) + 6) * 4.9e-4f + 1.0e-6f; }
+#ifndef WB_HIT_BATCH
+#define WB_HIT_BATCH 0             // 1: hits of the point rounds are resolved 32 at a time, one per lane (A/B candidate, not yet measured)
+#endif
 #ifndef WB_POINT_HALF
 #define WB_POINT_HALF 0            // 1: the point rounds prefilter in half precision too (A/B candidate, not yet measured)
 #endif
@@ -504,8 +507,9 @@ __device__ __forceinline__ void fixed_add(long long* p, long long v) {
 __host__ __device__ constexpr int repulse_warps(int V) { return V <= 4 ? 8 : 4; }
 
 // dynamic shared memory of k_repulse_pairs<V, HALF>
+constexpr int kHitBuffer = 96;            // WB_HIT_BATCH: waiting hits per warp (<= 31 left over + 64 from one point round)
 __host__ __device__ constexpr int repulse_smem_bytes(int V, bool half) {
-    return repulse_warps(V) * (32 * (V + 1 + (half ? half_chunks(V) : 0)) * 16 + (8 + 56 * kMaxLevels + 72 + 80) * 4);
+    return repulse_warps(V) * (32 * (V + 1 + (half ? half_chunks(V) : 0)) * 16 + (8 + 56 * kMaxLevels + 72 + 80) * 4 + (WB_HIT_BATCH ? kHitBuffer * 8 : 0));
 }
 
 #ifndef WB_REPULSE_MINBLOCKS
@@ -539,10 +543,15 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
     //   stack [8 + STACK]: 8 null entries below the stack (a short pop reads them and nothing passes)
     //   leaf queue [80]: leaves waiting for their point round
     extern __shared__ float4 smemRep[];
-    static_assert(repulse_smem_bytes(V, HALF) == WARPS * (32 * QROW * 16 + (8 + STACK + 80) * 4), "host and kernel disagree on the layout");
+    static_assert(repulse_smem_bytes(V, HALF) == WARPS * (32 * QROW * 16 + (8 + STACK + 80) * 4 + (WB_HIT_BATCH ? kHitBuffer * 8 : 0)),
+                  "host and kernel disagree on the layout");
     float4 (*sQ)[32][QROW] = reinterpret_cast<float4 (*)[32][QROW]>(smemRep);
     uint32_t (*sStack)[8 + STACK] = reinterpret_cast<uint32_t (*)[8 + STACK]>(smemRep + WARPS * 32 * QROW);
     uint32_t (*sLeaf)[80] = reinterpret_cast<uint32_t (*)[80]>(reinterpret_cast<uint32_t*>(smemRep + WARPS * 32 * QROW) + WARPS * (8 + STACK));
+#if WB_HIT_BATCH
+    uint2* myHit = reinterpret_cast<uint2*>(&sLeaf[WARPS][0]) + (threadIdx.x >> 5) * kHitBuffer;   // {sorted position of the partner, query lane}
+    int nHit = 0;
+#endif
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = lane & (kFan - 1), g = lane >> kFanLog2;
     // lanes that precede this one in child-major order (c, g)
     uint32_t before = 0u;
@@ -680,8 +689,8 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
     // vertices (hits are rare - a handful per query - so this branch is cold).
     auto resolveHit = [&](const PointSlot& r) {
         if (!r.hit) return;
-        float d2 = r.d2;
-        if constexpr (HALF && WB_POINT_HALF) {                 // the exact squared distance, same operation order as the fp32 point round
+        float d2 = r.d2, ws = r.ws;
+        if constexpr ((HALF && WB_POINT_HALF) || WB_HIT_BATCH) {   // the exact squared distance, same operation order as the fp32 point round
             const float4* qrow = myQ + r.qq * QROW;
             float4 pu[V], qv[V];
 #pragma unroll
@@ -689,8 +698,9 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
 #pragma unroll
             for (int k = 0; k < V; ++k) qv[k] = qrow[k];
             d2 = point_dist2<V>(qv, pu);
+            ws = qrow[V].x * __ldg(t.bound[0] + r.idx);
         }
-        const float dist = sqrtf(d2), ws = r.ws;
+        const float dist = sqrtf(d2);
         if (dist > 0.f && !(dist * ws <= L)) return;         // exact predicate; dist <= 0 is the coincident case
         const float4* qrow = myQ + r.qq * QROW;
         const int u = __ldg(t.ids + r.idx);
@@ -730,6 +740,28 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
         nPairs += 2;                                         // counted per direction, like the reference's loop over all v
     };
 
+#if WB_HIT_BATCH
+    // Hits wait in the warp's buffer and are resolved 32 at a time, one per lane, so that the neighbour filter's dependent loads
+    // of up to 32 hits overlap instead of one lane's search stalling the warp (integer rows: the order of the adds does not matter).
+    auto queueHit = [&](const PointSlot& r) {
+        const uint32_t hm = __ballot_sync(0xffffffffu, r.hit);
+        if (r.hit) myHit[nHit + __popc(hm & ltMask)] = make_uint2((uint32_t)r.idx, r.qq);
+        nHit += __popc(hm);
+    };
+    auto flushHits = [&](int keep) {                         // until at most `keep` hits are left
+        __syncwarp();
+        while (nHit > keep) {
+            const int take = min(32, nHit);
+            PointSlot r;
+            r.hit = lane < take;
+            const uint2 h = myHit[nHit - take + (r.hit ? lane : 0)];
+            r.idx = (int)h.x; r.qq = h.y; r.d2 = 0.f; r.ws = 0.f;
+            resolveHit(r);
+            nHit -= take;
+            __syncwarp();
+        }
+    };
+#endif
     for (;;) {
         int chunk = 0;
         if (lane == 0) chunk = atomicAdd(chunkCounter, 1);
@@ -799,8 +831,14 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
                 nTests += (int)activeA + (int)activeB;
                 const PointSlot a = testPoint(entryA, activeA);
                 const PointSlot b = testPoint(entryB, activeB);
+#if WB_HIT_BATCH
+                queueHit(a);
+                queueHit(b);
+                if (nHit >= 32) flushHits(31);
+#else
                 resolveHit(a);
                 resolveHit(b);
+#endif
             } else {
                 // a pop of fewer than eight pairs reads the null entries below the stack (they fail the position test)
                 const uint32_t entryA = myStack[sp - 1 - g];
@@ -828,6 +866,9 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
             }
             __syncwarp();
         }
+#if WB_HIT_BATCH
+        flushHits(0);                                         // before the next chunk overwrites the query rows
+#endif
     }
     // per-warp statistics (integers, so the order in which warps took chunks cannot change the reduced value);
     // every box slot is 8 lane tests and all 32 lanes counted it: 8 / 32 per lane
