@@ -213,8 +213,10 @@ void choose_fixed_scales(wb_embedder* h, double maxIw, double minIw) {
     h->fixLoss = scale(h->opt.edge_length / (minIw * minIw));
     // Box format of the repulsion walk (k_quant_params decides every step): half-precision boxes while the layout's largest
     // per-dimension sd is at most kHalfSpread smallest interaction radii (L / max ws); the rounding of a centred coordinate is
-    // ~sd * 2^-11, i.e. below 1 % of that radius.  WB_HALF_BOXES=0 / 1 forces one format (A/B runs, tests).
-    constexpr double kHalfSpread = 16.0;
+    // ~sd * 2^-11, i.e. ~3 % of that radius at the limit.  Simulated on the c3 layout with shortened mantissas: +3 % box tests and
+    // +7 % point tests at 55 radii (the half-precision rounds are ~26 % cheaper), +0.2 % / +0.4 % at the 3.4 radii of c3 itself.
+    // WB_HALF_BOXES=0 / 1 forces one format (A/B runs, tests).
+    constexpr double kHalfSpread = 64.0;
     if (h->halfMode < 0) {
         const char* env = std::getenv("WB_HALF_BOXES");
         h->halfMode = env ? (std::atoi(env) != 0 ? 1 : 0) : 2;
