@@ -156,3 +156,61 @@ def edge_detection_metrics(x, w, v, u, is_edge, n, m):
             if f1 > best[2]:
                 best = (float(precision), float(recall), float(f1))
     return best
+
+
+def brute_force_repulsive_pairs(x, w, row_ptr, col, L=1.0, tau=1e-5, tile=2048, device="cuda"):
+    """Index-free census of the repulsive pairs of a layout: ALL n^2 ordered pairs are tested in tiles on the GPU with plain
+    torch (a matmul-form distance in fp32 selects a generous superset, which is then re-evaluated in float64), so nothing of
+    the product's index, tree or walk is shared with it.
+
+    A pair (v, u), u not in N(v), u != v, counts when dist * ws <= L, ws = (w_v w_u)^(-1/d) (WembedEmbedder.cpp:196-201).
+    Returns (lo, hi, degree_lo, degree_hi): directed pair counts with dist * ws <= L (1 - tau) / <= L (1 + tau) - an
+    implementation that evaluates the predicate in fp32 must land between the two - and the same per vertex.
+    """
+    import torch
+    n, d = x.shape
+    dev = torch.device(device)
+    x64 = torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float64, device=dev)
+    xc = (x64 - x64.mean(0, keepdim=True)).to(torch.float32)
+    iw64 = torch.as_tensor(w ** (-1.0 / d), dtype=torch.float64, device=dev)
+    iwsq = (iw64 * iw64).to(torch.float32)
+    nb = (xc * xc).sum(1)
+    src = np.repeat(np.arange(n, dtype=np.int64), np.diff(row_ptr))
+    ekeys = torch.as_tensor(src * n + col.astype(np.int64), device=dev)       # CSR order = sorted by (src, dst)
+    lo_deg = torch.zeros(n, dtype=torch.int64, device=dev)
+    hi_deg = torch.zeros(n, dtype=torch.int64, device=dev)
+    thr = float(L * L * 1.02)
+    for a0 in range(0, n, tile):
+        a1 = min(n, a0 + tile)
+        g = xc[a0:a1] @ xc.T
+        g.mul_(-2.0).add_(nb[a0:a1, None]).add_(nb[None, :])
+        g.mul_(iwsq[a0:a1, None]).mul_(iwsq[None, :])
+        ri, cj = (g <= thr).nonzero(as_tuple=True)
+        del g
+        ri = ri + a0
+        keep = ri != cj
+        ri, cj = ri[keep], cj[keep]
+        if ri.numel() == 0:
+            continue
+        val = (x64[ri] - x64[cj]).pow(2).sum(1).sqrt() * iw64[ri] * iw64[cj]
+        key = ri * n + cj
+        pos = torch.searchsorted(ekeys, key).clamp_(max=max(ekeys.numel() - 1, 0))
+        is_nb = (ekeys[pos] == key) if ekeys.numel() else torch.zeros_like(key, dtype=torch.bool)
+        ok_lo = (~is_nb) & (val <= L * (1.0 - tau))
+        ok_hi = (~is_nb) & (val <= L * (1.0 + tau))
+        lo_deg += torch.bincount(ri[ok_lo], minlength=n)
+        hi_deg += torch.bincount(ri[ok_hi], minlength=n)
+    return int(lo_deg.sum()), int(hi_deg.sum()), lo_deg.cpu().numpy(), hi_deg.cpu().numpy()
+
+
+def near_threshold_edge_owners(x, w, row_ptr, col, L=1.0, tau=1e-5, chunk=1 << 21):
+    """Vertices owning a graph edge whose weighted length lies within tau * L of the attraction hinge (chunked numpy)."""
+    n, d = x.shape
+    iw = w ** (-1.0 / d)
+    src = np.repeat(np.arange(n, dtype=np.int64), np.diff(row_ptr))
+    flagged = np.zeros(n, bool)
+    for a in range(0, len(col), chunk):
+        s, c = src[a:a + chunk], col[a:a + chunk]
+        dist = np.sqrt(((x[s] - x[c]) ** 2).sum(1))
+        flagged[s[np.abs(dist * iw[s] * iw[c] - L) <= tau * L]] = True
+    return flagged

@@ -25,7 +25,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-ccbin", "/usr/bin/g++",
-           "-Xcompiler", "-fPIC", "-shared", "-o", OUT, SRC, "-ldl"]
+           "-Xcompiler", "-fPIC,-pthread", "-shared", "-o", OUT, SRC, "-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.run(cmd, check=True)

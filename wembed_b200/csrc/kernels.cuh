@@ -1627,19 +1627,6 @@ __global__ void k_sum_ranks(const double* __restrict__ gathered, int world, int 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Boundary conversions (coordinates cross the C ABI as row-major n x d doubles).
-__global__ void k_rows_from_double(const double* __restrict__ in, int n, int dim, int rowFloats, float* __restrict__ out) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)n * rowFloats) return;
-    const int v = (int)(i / rowFloats), k = (int)(i % rowFloats);
-    out[i] = k < dim ? (float)in[(int64_t)v * dim + k] : 0.f;
-}
-__global__ void k_rows_to_double(const float* __restrict__ in, int n, int dim, int rowFloats, double* __restrict__ out) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)n * dim) return;
-    const int v = (int)(i / dim), k = (int)(i % dim);
-    out[i] = (double)in[(int64_t)v * rowFloats + k];
-}
 template <typename T>
 __global__ void k_fill(T* p, int64_t count, T value) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -15,6 +15,7 @@
 #include <deque>
 #include <limits>
 #include <stdexcept>
+#include <thread>
 #include <vector>
 
 #include "../../include/wembed_b200.h"
@@ -142,6 +143,11 @@ struct wb_embedder {
     std::deque<PendingStep> pending;
     std::vector<PendingStep> freeSlots;
 
+    // host <-> device staging of coordinate rows (wb_set_coordinates / wb_get_coordinates): per worker thread one stream and two
+    // pinned chunks, allocated on first use and kept for the life of the handle
+    struct StageLane { cudaStream_t stream = nullptr; float* pinned[2] = {nullptr, nullptr}; cudaEvent_t done[2] = {nullptr, nullptr}; };
+    std::vector<StageLane> stageLanes;
+
     cudaEvent_t marks[8] = {};
     int64_t launches = 0;
     bool timing = false;
@@ -195,6 +201,11 @@ void free_all(wb_embedder* h) {
     for (auto& p : h->pending) { cudaEventDestroy(p.done); cudaFreeHost(p.hostSums); }
     for (auto& p : h->freeSlots) { cudaEventDestroy(p.done); cudaFreeHost(p.hostSums); }
     h->pending.clear(); h->freeSlots.clear();
+    for (auto& l : h->stageLanes) {
+        for (int b = 0; b < 2; ++b) { if (l.pinned[b]) cudaFreeHost(l.pinned[b]); if (l.done[b]) cudaEventDestroy(l.done[b]); }
+        if (l.stream) cudaStreamDestroy(l.stream);
+    }
+    h->stageLanes.clear();
     for (auto& e : h->ev) if (e) { cudaEventDestroy(e); e = nullptr; }
     for (auto& e : h->marks) if (e) { cudaEventDestroy(e); e = nullptr; }
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -550,29 +561,120 @@ void collect_step(wb_embedder* h, wb_step_stats* out) {
     if (out) *out = st;
 }
 
-void upload_rows(wb_embedder* h, const double* src, float4* dst) {
-    const int64_t count = (int64_t)h->n * h->dim;
-    if (count == 0) return;
-    double* tmp = dalloc<double>(count);
-    cudaError_t e = cudaMemcpyAsync(tmp, src, sizeof(double) * count, cudaMemcpyHostToDevice, h->stream);
-    if (e == cudaSuccess) {
-        const int64_t total = (int64_t)h->n * h->rowFloats;
-        wb::k_rows_from_double<<<div_up(total, 256), 256, 0, h->stream>>>(tmp, h->n, h->dim, h->rowFloats, reinterpret_cast<float*>(dst));
-        e = cudaStreamSynchronize(h->stream);
+// Coordinates cross the C ABI as row-major n x d doubles in caller-owned (pageable) memory; the device keeps fp32 rows padded to
+// 4V floats.  The conversion happens on the host while the rows pass through pinned chunks: a few worker threads each own a
+// contiguous share of the rows, one stream and two pinned chunks, so the host pass (read 8 B, write 4 B per value), the PCIe
+// copies (half the bytes of the double rows) and the other workers overlap.  Nothing is allocated per call.
+constexpr size_t kStageChunkFloats = (size_t)1 << 18;       // 1 MiB per pinned chunk
+
+int stage_lanes(wb_embedder* h, int64_t rows) {
+    const int64_t rowsPerChunk = std::max<int64_t>(1, (int64_t)(kStageChunkFloats / (size_t)h->rowFloats));
+    const int want = (int)std::max<int64_t>(1, std::min<int64_t>({8, (int64_t)std::max(1u, std::thread::hardware_concurrency()), (rows + rowsPerChunk - 1) / rowsPerChunk}));
+    while ((int)h->stageLanes.size() < want) {
+        wb_embedder::StageLane l;
+        WB_CUDA(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            WB_CUDA(cudaMallocHost(&l.pinned[b], kStageChunkFloats * sizeof(float)));
+            WB_CUDA(cudaEventCreateWithFlags(&l.done[b], cudaEventDisableTiming));
+        }
+        h->stageLanes.push_back(l);
     }
-    cudaFree(tmp);
-    WB_CUDA(e);
+    return want;
+}
+
+// body(lane index, first row, end row) on `lanes` threads over [0, rows); the first error wins
+template <typename Body>
+void run_lanes(wb_embedder* h, int lanes, int64_t rows, Body&& body) {
+    std::vector<cudaError_t> err(lanes, cudaSuccess);
+    auto work = [&](int t) {
+        cudaSetDevice(h->opt.device);
+        const int64_t r0 = rows * t / lanes, r1 = rows * (t + 1) / lanes;
+        err[t] = body(t, r0, r1);
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < lanes; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
+    for (cudaError_t e : err) WB_CUDA(e);
+}
+
+void upload_rows(wb_embedder* h, const double* src, float4* dst) {
+    const int64_t rows = h->n;
+    if (rows == 0) return;
+    const int dim = h->dim, rf = h->rowFloats;
+    const int64_t rowsPerChunk = std::max<int64_t>(1, (int64_t)(kStageChunkFloats / (size_t)rf));
+    WB_CUDA(cudaStreamSynchronize(h->stream));                // nothing on the main stream may still be reading or writing dst
+    const int lanes = stage_lanes(h, rows);
+    float* out = reinterpret_cast<float*>(dst);
+    run_lanes(h, lanes, rows, [&](int t, int64_t r0, int64_t r1) -> cudaError_t {
+        auto& l = h->stageLanes[t];
+        int b = 0;
+        for (int64_t r = r0; r < r1; r += rowsPerChunk, b ^= 1) {
+            const int64_t cnt = std::min(rowsPerChunk, r1 - r);
+            cudaError_t e = cudaEventSynchronize(l.done[b]);   // the copy that last used this chunk has finished
+            if (e != cudaSuccess) return e;
+            float* p = l.pinned[b];
+            const double* s = src + r * dim;
+            if (rf == dim) {
+                for (int64_t i = 0; i < cnt * dim; ++i) p[i] = (float)s[i];
+            } else {
+                for (int64_t v = 0; v < cnt; ++v) {
+                    for (int k = 0; k < dim; ++k) p[v * rf + k] = (float)s[v * dim + k];
+                    for (int k = dim; k < rf; ++k) p[v * rf + k] = 0.f;
+                }
+            }
+            e = cudaMemcpyAsync(out + r * rf, p, sizeof(float) * cnt * rf, cudaMemcpyHostToDevice, l.stream);
+            if (e != cudaSuccess) return e;
+            e = cudaEventRecord(l.done[b], l.stream);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaStreamSynchronize(l.stream);
+    });
 }
 
 void download_rows(wb_embedder* h, const float4* src, double* dst) {
-    const int64_t count = (int64_t)h->n * h->dim;
-    if (count == 0) return;
-    double* tmp = dalloc<double>(count);
-    wb::k_rows_to_double<<<div_up(count, 256), 256, 0, h->stream>>>(reinterpret_cast<const float*>(src), h->n, h->dim, h->rowFloats, tmp);
-    cudaError_t e = cudaMemcpyAsync(dst, tmp, sizeof(double) * count, cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(tmp);
-    WB_CUDA(e);
+    const int64_t rows = h->n;
+    if (rows == 0) return;
+    const int dim = h->dim, rf = h->rowFloats;
+    const int64_t rowsPerChunk = std::max<int64_t>(1, (int64_t)(kStageChunkFloats / (size_t)rf));
+    WB_CUDA(cudaStreamSynchronize(h->stream));                // the rows are final
+    const int lanes = stage_lanes(h, rows);
+    const float* in = reinterpret_cast<const float*>(src);
+    run_lanes(h, lanes, rows, [&](int t, int64_t r0, int64_t r1) -> cudaError_t {
+        auto& l = h->stageLanes[t];
+        auto convert = [&](int b, int64_t r, int64_t cnt) {
+            const float* p = l.pinned[b];
+            double* d = dst + r * dim;
+            if (rf == dim) {
+                for (int64_t i = 0; i < cnt * dim; ++i) d[i] = (double)p[i];
+            } else {
+                for (int64_t v = 0; v < cnt; ++v)
+                    for (int k = 0; k < dim; ++k) d[v * dim + k] = (double)p[v * rf + k];
+            }
+        };
+        // two chunks in flight: while chunk i is converted on the host, chunk i + 1 crosses PCIe
+        int64_t prevR = -1, prevCnt = 0;
+        int b = 0;
+        for (int64_t r = r0; r < r1; r += rowsPerChunk, b ^= 1) {
+            const int64_t cnt = std::min(rowsPerChunk, r1 - r);
+            cudaError_t e = cudaMemcpyAsync(l.pinned[b], in + r * rf, sizeof(float) * cnt * rf, cudaMemcpyDeviceToHost, l.stream);
+            if (e != cudaSuccess) return e;
+            e = cudaEventRecord(l.done[b], l.stream);
+            if (e != cudaSuccess) return e;
+            if (prevR >= 0) {
+                e = cudaEventSynchronize(l.done[b ^ 1]);
+                if (e != cudaSuccess) return e;
+                convert(b ^ 1, prevR, prevCnt);
+            }
+            prevR = r; prevCnt = cnt;
+        }
+        if (prevR >= 0) {
+            cudaError_t e = cudaEventSynchronize(l.done[b ^ 1]);
+            if (e != cudaSuccess) return e;
+            convert(b ^ 1, prevR, prevCnt);
+        }
+        return cudaSuccess;
+    });
 }
 
 template <typename F>
@@ -634,13 +736,24 @@ int wb_create(wb_embedder** out, int32_t n, const int32_t* row_ptr, const int32_
     if (n == 0) row_ptr = zeroRow;
     // the invariants of Graph (Graph.cpp:87-150): monotone offsets, rows strictly ascending, ids in range, no self loops
     if (row_ptr[0] != 0) return fail(WB_ERR_INVALID, "wb_create: row_ptr[0] != 0");
-    for (int v = 0; v < n; ++v) {
+    for (int v = 0; v < n; ++v)
         if (row_ptr[v + 1] < row_ptr[v]) return fail(WB_ERR_INVALID, "wb_create: row_ptr not monotone");
+    if (row_ptr[n] > 0 && !col) return fail(WB_ERR_INVALID, "wb_create: col is null but row_ptr[n] > 0");
+    for (int v = 0; v < n; ++v) {
         for (int e = row_ptr[v]; e < row_ptr[v + 1]; ++e) {
             if (col[e] < 0 || col[e] >= n || col[e] == v) return fail(WB_ERR_INVALID, "wb_create: neighbour id out of range or self loop");
             if (e > row_ptr[v] && col[e] <= col[e - 1]) return fail(WB_ERR_INVALID, "wb_create: rows must be strictly ascending");
         }
     }
+    // symmetric (Graph stores every undirected edge from both sides): the repulsion's neighbour filter looks at one endpoint's row only
+    for (int v = 0; v < n; ++v) {
+        for (int e = row_ptr[v]; e < row_ptr[v + 1]; ++e) {
+            const int u = col[e];
+            if (!std::binary_search(col + row_ptr[u], col + row_ptr[u + 1], v)) return fail(WB_ERR_INVALID, "wb_create: the CSR is not symmetric");
+        }
+    }
+    // the walk packs a block / leaf index into 27 bits of a stack entry (kernels.cuh: kRefMask)
+    if ((int64_t)n > ((int64_t)1 << 29)) return fail(WB_ERR_UNSUPPORTED, "wb_create: graph too large for the index (n > 2^29)");
     auto* h = new wb_embedder();
     h->n = n;
     h->dim = opts->embedding_dimension;
@@ -822,9 +935,18 @@ int wb_comm_init(wb_embedder* h, const char* id128, int32_t rank, int32_t world)
         // block -> vertex-range assignment over the owned range
         const int own = std::max(1, h->ownEnd - h->ownBegin), K = 2 + 4 * V;
         attract_grid(V, own, h->forceBlocks, h->forceVertsPerBlock);
-            h->obsBlocks = std::max(1, std::min(div_up(own, 256), 148 * 8));
+        h->obsBlocks = std::max(1, std::min(div_up(own, 256), 148 * 8));
         h->obsVertsPerBlock = std::max(256, div_up(div_up(own, h->obsBlocks), 256) * 256);
         h->obsBlocks = std::max(1, div_up(own, h->obsVertsPerBlock));
+        // the rounding of vertsPerBlock can make the sharded grids LARGER than the single-GPU ones: size the partial sums again
+        cudaFree(h->partialsForce); h->partialsForce = nullptr;
+        cudaFree(h->partialsObs); h->partialsObs = nullptr;
+        h->partialsForce = dalloc<double>((size_t)h->forceBlocks * K);
+        h->partialsObs = dalloc<double>((size_t)h->obsBlocks * 2);
+#if WB_ATTRACT_STAGED
+        cudaFree(h->mtScratch); h->mtScratch = nullptr;
+        h->mtScratch = dalloc<uint32_t>((size_t)h->forceBlocks * 8 * 624);
+#endif
         // repulsion rows: blocks of kRepBlockChunks chunks of the sorted order dealt round-robin to the ranks, each rank's rows contiguous
         const int blocksPerRank = div_up(div_up(div_up(std::max(n, 1), 32), wb::kRepBlockChunks), world);
         h->repLayout = wb::RepLayout{world, rank, blocksPerRank * wb::kRepBlockChunks * 32};
@@ -837,7 +959,6 @@ int wb_comm_init(wb_embedder* h, const char* id128, int32_t rank, int32_t world)
         h->localSums = dalloc<double>(h->sumsTotal);
         WB_CUDA(cudaMemsetAsync(h->localSums, 0, sizeof(double) * h->sumsTotal, h->stream));
         WB_CUDA(cudaStreamSynchronize(h->stream));
-        (void)K;
     });
 }
 

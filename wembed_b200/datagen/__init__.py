@@ -25,6 +25,8 @@ def lib():
         l.wbd_pairs_within.restype = C.c_int64
         l.wbd_pairs_within.argtypes = [C.c_int64, C.c_void_p, C.c_double]
         l.wbd_take_edges.argtypes = [C.c_void_p]
+        l.wbd_girg_pairs.restype = C.c_int64
+        l.wbd_girg_pairs.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int]
         l.wbd_csr_canonical.restype = C.c_int
         l.wbd_csr_canonical.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = l
@@ -35,6 +37,18 @@ def pairs_within(points: np.ndarray, radius: float) -> np.ndarray:
     """All index pairs (i < j) with ||p_i - p_j|| < radius as int32 [m, 2], lexicographic order."""
     pts = np.ascontiguousarray(points, dtype=np.float64)
     m = lib().wbd_pairs_within(len(pts), pts.ctypes.data, float(radius))
+    out = np.empty((m, 2), np.int32)
+    lib().wbd_take_edges(out.ctypes.data)
+    return out
+
+
+def girg_pairs(points: np.ndarray, weights: np.ndarray, c: float, W: float, count_only: bool = False):
+    """Threshold-GIRG edges (i < j, lexicographic) of datasets.heavy_tailed_graph, or only their number."""
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    m = lib().wbd_girg_pairs(len(pts), pts.ctypes.data, w.ctypes.data, float(c), float(W), int(count_only))
+    if count_only:
+        return int(m)
     out = np.empty((m, 2), np.int32)
     lib().wbd_take_edges(out.ctypes.data)
     return out

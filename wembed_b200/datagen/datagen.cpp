@@ -4,12 +4,14 @@
 //
 //   wbd_pairs_within   all index pairs (i < j) with ||p_i - p_j||^2 < r^2, lexicographic order
 //                      (the rule of the reference's GeometricGraphSampler.cpp:10-51, found with a cell grid instead of its O(n^2) loop)
+//   wbd_girg_pairs     threshold-GIRG edges: (i, j) with ||p_i - p_j||^2 < c^2 w_i w_j / W, lexicographic order (datasets.heavy_tailed_graph)
 //   wbd_csr_canonical  CSR of an edge list that is already unique, sorted and has src < dst (Graph.cpp:87-150 invariants)
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <vector>
+#include <omp.h>
 
 namespace {
 std::vector<int32_t> g_edges;   // result of the last wbd_pairs_within call, copied out by wbd_take_edges
@@ -68,6 +70,78 @@ int64_t wbd_pairs_within(int64_t n, const double* pts /* [n][2] */, double radiu
     g_edges.reserve(total);
     for (auto& p : part) { g_edges.insert(g_edges.end(), p.begin(), p.end()); std::vector<int32_t>().swap(p); }
     return (int64_t)(g_edges.size() / 2);
+}
+
+// Threshold GIRG-like edge rule of datasets.heavy_tailed_graph: vertices are binned into weight layers [2^k, 2^(k+1)); for every
+// layer pair (ka <= kb) the vertices of layer kb are put on a grid whose cell is the largest distance that pair of layers can
+// connect over, and every vertex of layer ka scans its 3 x 3 cells.  The predicate is evaluated exactly as the numpy code does
+// (first factor = the vertex of the lower layer, or of the lower index inside one layer).  count_only: no edges are kept.
+int64_t wbd_girg_pairs(int64_t n, const double* pts /* [n][2] */, const double* w, double c, double W, int count_only) {
+    g_edges.clear();
+    if (n <= 0) return 0;
+    std::vector<int> cls(n);
+    int maxCls = 0;
+    for (int64_t i = 0; i < n; ++i) { cls[i] = (int)std::floor(std::log2(w[i])); maxCls = std::max(maxCls, cls[i]); }
+    std::vector<std::vector<int32_t>> layer(maxCls + 1);
+    for (int64_t i = 0; i < n; ++i) layer[cls[i]].push_back((int32_t)i);
+    const int threads = 16;
+    std::vector<std::vector<int64_t>> part(threads);
+    std::vector<int64_t> counts(threads, 0);
+    const double cc = c * c;
+    for (int ka = 0; ka <= maxCls; ++ka) {
+        const std::vector<int32_t>& A = layer[ka];
+        if (A.empty()) continue;
+        for (int kb = ka; kb <= maxCls; ++kb) {
+            const std::vector<int32_t>& B = layer[kb];
+            if (B.empty()) continue;
+            const double rmax = std::min(1.5, c * std::sqrt(std::ldexp(1.0, ka + 1) * std::ldexp(1.0, kb + 1) / W));
+            // grid over the unit square (positions are uniform in [0, 1)^2), cells of side >= rmax
+            const int64_t g = std::max<int64_t>(1, std::min<int64_t>(4096, (int64_t)std::floor(1.0 / rmax)));
+            const double inv = (double)g;
+            std::vector<int64_t> start(g * g + 1, 0);
+            std::vector<int32_t> cellOf(B.size());
+            for (size_t k = 0; k < B.size(); ++k) {
+                const int64_t gx = std::min<int64_t>(g - 1, (int64_t)(pts[2 * (int64_t)B[k]] * inv)), gy = std::min<int64_t>(g - 1, (int64_t)(pts[2 * (int64_t)B[k] + 1] * inv));
+                cellOf[k] = (int32_t)(gx * g + gy);
+                ++start[cellOf[k] + 1];
+            }
+            for (int64_t q = 0; q < g * g; ++q) start[q + 1] += start[q];
+            std::vector<int32_t> member(B.size());
+            {
+                std::vector<int64_t> at(start.begin(), start.end() - 1);
+                for (size_t k = 0; k < B.size(); ++k) member[at[cellOf[k]]++] = B[k];
+            }
+            const bool same = ka == kb;
+#pragma omp parallel for schedule(dynamic, 256) num_threads(threads)
+            for (int64_t ai = 0; ai < (int64_t)A.size(); ++ai) {
+                const int t = omp_get_thread_num();
+                const int64_t i = A[ai];
+                const double xi = pts[2 * i], yi = pts[2 * i + 1], wi = w[i];
+                const int64_t gx = std::min<int64_t>(g - 1, (int64_t)(xi * inv)), gy = std::min<int64_t>(g - 1, (int64_t)(yi * inv));
+                for (int64_t x = std::max<int64_t>(0, gx - 1); x <= std::min<int64_t>(g - 1, gx + 1); ++x)
+                    for (int64_t y = std::max<int64_t>(0, gy - 1); y <= std::min<int64_t>(g - 1, gy + 1); ++y)
+                        for (int64_t k = start[x * g + y]; k < start[x * g + y + 1]; ++k) {
+                            const int64_t j = member[k];
+                            if (same && j <= i) continue;
+                            const double ex = xi - pts[2 * j], ey = yi - pts[2 * j + 1];
+                            if (ex * ex + ey * ey < cc * wi * w[j] / W) {
+                                ++counts[t];
+                                if (!count_only) part[t].push_back(i < j ? (i << 32) | j : (j << 32) | i);
+                            }
+                        }
+            }
+        }
+    }
+    int64_t total = 0;
+    for (int64_t k : counts) total += k;
+    if (count_only) return total;
+    std::vector<int64_t> keys;
+    keys.reserve((size_t)total);
+    for (auto& p : part) { keys.insert(keys.end(), p.begin(), p.end()); std::vector<int64_t>().swap(p); }
+    std::sort(keys.begin(), keys.end());
+    g_edges.resize(keys.size() * 2);
+    for (size_t e = 0; e < keys.size(); ++e) { g_edges[2 * e] = (int32_t)(keys[e] >> 32); g_edges[2 * e + 1] = (int32_t)(keys[e] & 0xffffffff); }
+    return total;
 }
 
 void wbd_take_edges(int32_t* out /* [m][2] */) {

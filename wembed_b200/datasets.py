@@ -111,13 +111,13 @@ def _pairs_between(P: np.ndarray, Q: np.ndarray, radius: float, same: bool) -> n
     return np.concatenate(out) if out else np.zeros((0, 2), np.int64)
 
 
-def heavy_tailed_graph(n: int, avg_degree: float = 20.0, beta: float = 2.5, seed: int = 42, c: float | None = None):
+def heavy_tailed_graph(n: int, avg_degree: float = 20.0, beta: float = 2.5, seed: int = 42, c: float | None = None, native: bool = True):
     """Threshold GIRG-like graph with power-law weights; returns (edges, generator weights).
 
     The expected degree, pi * c^2 * E[w] up to boundary effects, does not depend on n, so for large n the constant c
     is calibrated once on a 100k-vertex instance of the same distribution."""
     if c is None and n > 200_000:
-        c = _calibrate_c(avg_degree, beta, seed)
+        c = _calibrate_c(avg_degree, beta, seed, native)
     rng = np.random.default_rng(seed)
     w = (1.0 - rng.random(n)) ** (-1.0 / (beta - 1.0))
     pts = rng.random((n, 2))
@@ -125,7 +125,17 @@ def heavy_tailed_graph(n: int, avg_degree: float = 20.0, beta: float = 2.5, seed
     cls = np.floor(np.log2(w)).astype(np.int64)          # weight layers [2^k, 2^(k+1))
     layers = [np.flatnonzero(cls == k) for k in range(int(cls.max()) + 1)]
 
+    girg = None
+    if native:
+        try:                               # C++ helper: the same edges in the same order, ~40x faster at n = 1e6
+            from . import datagen
+            girg = datagen.girg_pairs
+        except (OSError, subprocess.CalledProcessError):
+            girg = None
+
     def build(c, count_only):
+        if girg is not None:
+            return girg(pts, w, c, W, count_only)
         parts, total = [], 0
         for ka, A in enumerate(layers):
             for kb in range(ka, len(layers)):
@@ -161,8 +171,8 @@ def heavy_tailed_graph(n: int, avg_degree: float = 20.0, beta: float = 2.5, seed
     return build(0.5 * (lo + hi), False), w
 
 
-def _calibrate_c(avg_degree, beta, seed):
-    heavy_tailed_graph(100_000, avg_degree, beta, seed)
+def _calibrate_c(avg_degree, beta, seed, native=True):
+    heavy_tailed_graph(100_000, avg_degree, beta, seed, native=native)
     return heavy_tailed_graph.last_c
 
 

@@ -32,7 +32,7 @@ def build(force: bool = False) -> str:
     from .. import build as cuda_build
     cuda_build.build()
     inc = ["-I", os.path.join(_ROOT, "include"), "-I", _HERE]
-    common = ["-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-Wl,-rpath,$ORIGIN", "-L", _LIBDIR]
+    common = ["-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-pthread", "-Wl,-rpath,$ORIGIN", "-L", _LIBDIR]
     if force or _stale(HOST_LIB):
         subprocess.run([CXX, *common, *inc, "-o", HOST_LIB, *_SRCS, "-lwembed_b200"], check=True)
     if force or _stale(PYMOD):
