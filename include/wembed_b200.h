@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define WB_ABI_VERSION 1
+#define WB_ABI_VERSION 2
 
 typedef struct wb_embedder wb_embedder; /* opaque */
 
@@ -40,7 +40,6 @@ enum wb_status {
 };
 
 enum wb_optimizer { WB_OPT_SIMPLE = 0, WB_OPT_ADAM = 1 };    /* EmbedderOptions.hpp:6  */
-enum wb_precision { WB_PREC_F32 = 0, WB_PREC_F64 = 1 };      /* device state type      */
 
 /*
  * The force / optimizer knobs of EmbedderOptions (EmbedderOptions.hpp:31-88) that the
@@ -51,7 +50,8 @@ typedef struct wb_options {
     int32_t embedding_dimension;   /* EmbedderOptions::embeddingDimension, 1..32            */
     int32_t optimizer;             /* wb_optimizer; Adam: beta1=.9 beta2=.999 eps=1e-8      */
                                    /*   (WembedEmbedder.hpp:46)                             */
-    int32_t precision;             /* wb_precision of device state; F32 is the product path */
+    int32_t reserved2;             /* must be 0.  Device state is fp32 (north_star: "within 1e-5 relative error in fp32");  */
+                                   /*   sums are taken in fp64 / 64-bit fixed point.  The reference is fp64 throughout.      */
     int32_t device;                /* CUDA device ordinal                                   */
     int32_t keep_forces;           /* 1: keep state.force of every step for wb_get_forces   */
     int32_t reserved0;
@@ -82,6 +82,11 @@ typedef struct wb_step_stats {
     double num_box_tests;      /* box tests of the repulsion walk                    */
     double centroid[32];       /* per-dimension mean removed by applyGravityCentre   */
     int64_t iteration;         /* state.currentIteration after the step              */
+    /* state of the repulsion pair list (see wb_set_list_policy) */
+    double num_listed_pairs;   /* unordered pairs in the list this step evaluated     */
+    double list_rebuilt;       /* 1: this step rebuilt index + list, 0: it reused them */
+    double list_skin;          /* relative inflation of the list radius               */
+    double max_displacement_ratio; /* max_v ||dx_v|| / (smallest interaction radius of v) of this step */
 } wb_step_stats;
 
 /* -- life cycle ----------------------------------------------------------------- */
@@ -145,6 +150,17 @@ int wb_step(wb_embedder* h, double learning_rate, wb_step_stats* stats);
 int wb_step_async(wb_embedder* h, double learning_rate);
 int wb_step_collect(wb_embedder* h, wb_step_stats* stats);
 int wb_synchronize(wb_embedder* h);
+
+/*
+ * The repulsion search does not apply forces: it lists every non-adjacent pair within L (1 + skin) / ws, and the step evaluates the
+ * exact predicate of repellingForce (WembedEmbedder.cpp:196-201) on the listed pairs.  While no vertex has moved further than
+ * skin / 2 of its smallest interaction radius since the search, the list is provably complete and index rebuild + search are
+ * skipped; the device keeps that bound itself and picks the skin of each search from the current pace of the layout, between 0 (early
+ * in a run: every step searches, nothing is inflated) and skin_max, aiming at lists that live for `reuse_steps` steps.  Results never
+ * depend on the policy (a listed pair beyond the exact threshold contributes exactly zero); skin_max = 0 restores "search every step",
+ * which is what WembedEmbedder::updateIndex does.  Defaults: 1.0 and 4 (environment, for A/B runs: WB_SKIN_MAX, WB_REUSE_STEPS).
+ */
+int wb_set_list_policy(wb_embedder* h, double skin_max, double reuse_steps);
 
 /* -- test hooks for the spatial index ------------------------------------------------ */
 

@@ -19,8 +19,8 @@ dev.set_weights(wl["weights"]); dev.set_coordinates(wl["x0"]); dev.enable_timing
 iw = wl["weights"] ** (-1.0 / d)
 rho = 1.0 / (iw * iw.max())
 mon = LossMonitor()
-acc, cnt, dev_ms, t0 = {}, 0, 0.0, time.perf_counter()
-print("# step | ms/step index repel attract recentre | pairs/v pt/v box/v | rel_disp | disp/rho: mean p99 p999 max | lossA lossR")
+acc, cnt, dev_ms, t0, builds = {}, 0, 0.0, time.perf_counter(), 0
+print("# step | ms/step index repel(search+list) fused recentre | pairs/v pt/v box/v (last step) | rel_disp | disp/rho: mean p99 p999 max | lossA lossR | list")
 it = 0
 while it < max_steps and not mon.converged():
     it += 1
@@ -32,11 +32,13 @@ while it < max_steps and not mon.converged():
     dev_ms += ph["total"]
     for k, v in ph.items(): acc[k] = acc.get(k, 0.0) + v
     cnt += 1
+    builds += int(st["list_rebuilt"])
     if probe:
         dl = np.sqrt(((dev.coordinates() - xb) ** 2).sum(1)) / rho
         q = np.quantile(dl, [0.99, 0.999])
         print(f"{it:5d} | {acc['total']/cnt:7.3f} {acc['index']/cnt:6.3f} {acc['repel']/cnt:7.3f} {acc['attract_update']/cnt:6.3f} {acc['recentre_observe']/cnt:6.3f} | "
               f"{st['num_repulsion_pairs']/n:6.2f} {st['num_candidates']/n:7.1f} {st['num_box_tests']/n:7.1f} | {st['rel_displacement']:.3e} | "
-              f"{dl.mean():.4f} {q[0]:.4f} {q[1]:.4f} {dl.max():.4f} | {st['loss_attract']:.5g} {st['loss_repel']:.5g}", flush=True)
-        acc, cnt = {}, 0
+              f"{dl.mean():.4f} {q[0]:.4f} {q[1]:.4f} {dl.max():.4f} | {st['loss_attract']:.5g} {st['loss_repel']:.5g} | "
+              f"builds {builds}/{cnt} skin {st['list_skin']:.3f} listed/v {st['num_listed_pairs']/n:.2f} maxratio {st['max_displacement_ratio']:.4f}", flush=True)
+        acc, cnt, builds = {}, 0, 0
 print(f"converged={mon.converged()} iterations={it} device_ms_total={dev_ms:.1f} wall_s={time.perf_counter()-t0:.2f} (wall includes the probes)")

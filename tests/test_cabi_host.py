@@ -26,7 +26,7 @@ def test_header_symbols_exported(lib):
     l = lib.lib()
     for name in declared:
         assert getattr(l, name) is not None
-    assert l.wb_abi_version() == 1
+    assert l.wb_abi_version() == 2
     assert b"sm_100a" in l.wb_build_info()
 
 
@@ -65,6 +65,7 @@ def test_create_validates_csr(lib):
         (np.array([0, 2, 2], np.int32), np.array([1, 1], np.int32)),      # not strictly ascending
         (np.array([0, 1, 2], np.int32), np.array([1, 5], np.int32)),      # out of range
         (np.array([1, 1, 2], np.int32), np.array([1, 0], np.int32)),      # row_ptr[0] != 0
+        (np.array([0, 1, 1], np.int32), np.array([1], np.int32)),         # not symmetric: 0 -> 1 without 1 -> 0
     ]
     for rp, col in bad:
         rc = l.wb_create(C.byref(h), 2, rp.ctypes.data_as(C.POINTER(C.c_int32)), col.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(o))

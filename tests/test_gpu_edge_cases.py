@@ -194,3 +194,59 @@ def test_half_precision_boxes_find_the_same_pairs(device_lib, monkeypatch, d):
 def geometric_graph_small(n):
     from wembed_b200.datasets import geometric_graph
     return geometric_graph(n, 10, 11)
+
+
+def test_pair_list_policy_never_changes_results(device_lib):
+    """The repulsion pair list may be kept for several steps (skin > 0) or rebuilt every step (skin_max = 0, what
+    WembedEmbedder::updateIndex does): a listed pair beyond the exact threshold contributes exactly zero and the sums are integers,
+    so the whole trajectory is bit-identical - and late in the run most steps must have reused their list."""
+    from helpers import make_problem
+    n, d, steps = 3000, 2, 420
+    edges, w, x0 = make_problem(n, d)
+    rp, col = device_lib.csr_from_edges(n, edges)
+    out = []
+    for policy in ((0.0, 4.0), (1.0, 4.0), (0.3, 8.0)):
+        dev = device_lib.DeviceEmbedder(rp, col, embedding_dimension=d, seed=1234)
+        dev.set_list_policy(*policy)
+        dev.set_weights(w)
+        dev.set_coordinates(x0)
+        stats = [dev.step(lr_exponential(it)) for it in range(1, steps + 1)]
+        out.append((dev.coordinates(), [(s["loss_attract"], s["loss_repel"], s["num_repulsion_pairs"], s["sum_displacement"]) for s in stats],
+                    sum(1 for s in stats if s["list_rebuilt"] == 0), max(s["list_skin"] for s in stats)))
+        dev.close()
+    assert out[0][2] == 0 and out[0][3] == 0.0                      # skin_max = 0: every step searched
+    for x, s, reused, skin in out[1:]:
+        assert np.array_equal(x, out[0][0])
+        assert s == out[0][1]
+        assert reused > steps // 4 and skin > 0.0
+
+
+def test_pair_list_grows_on_overflow(device_lib, monkeypatch):
+    """A pair buffer that is too small stops the step on the device (nothing is applied), the host grows it and replays the queued
+    steps: same results as with a large buffer, for blocking and for queued steps."""
+    from helpers import make_problem
+    n, d = 4000, 3
+    edges, w, x0 = make_problem(n, d)
+    rp, col = device_lib.csr_from_edges(n, edges)
+    out = {}
+    for cap, queued in (("0", False), ("16", False), ("16", True)):
+        if cap != "0":
+            monkeypatch.setenv("WB_PAIR_CAP", cap)
+        else:
+            monkeypatch.delenv("WB_PAIR_CAP", raising=False)
+        dev = device_lib.DeviceEmbedder(rp, col, embedding_dimension=d, seed=1234)
+        dev.set_weights(w)
+        dev.set_coordinates(x0)
+        if queued:
+            for it in range(1, 13):
+                dev.step_async(lr_exponential(it))
+            stats = [dev.step_collect() for _ in range(12)]
+        else:
+            stats = [dev.step(lr_exponential(it)) for it in range(1, 13)]
+        out[(cap, queued)] = (dev.coordinates(), [(s["loss_attract"], s["loss_repel"], s["num_repulsion_pairs"]) for s in stats])
+        dev.close()
+    base = out[("0", False)]
+    assert base[1][0][2] > 16                                       # the first step alone lists more pairs than the tiny buffer holds
+    for key in (("16", False), ("16", True)):
+        assert np.array_equal(out[key][0], base[0])
+        assert out[key][1] == base[1]

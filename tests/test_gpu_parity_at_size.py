@@ -43,7 +43,7 @@ def _one_step_against_port(device_lib, edges, n, d, w, rp, col, x, max_flagged_f
     np.testing.assert_allclose(st["loss_repel"], cs["loss_repel"], rtol=1e-4, atol=1e-6)
     assert lo <= st["num_repulsion_pairs"] <= hi, (lo, st["num_repulsion_pairs"], hi)
     assert lo <= cs["num_rep_pairs"] <= hi, (lo, cs["num_rep_pairs"], hi)
-    assert hi - lo <= 1e-4 * max(hi, 1) + 8
+    assert hi - lo <= 4e-4 * max(hi, 1) + 8             # the shell |dist ws - L| <= 1e-5 L holds ~2 * 1e-5 * d of all pairs
     out = dict(pairs=st["num_repulsion_pairs"], lo=lo, hi=hi, flagged=int(flagged.sum()), unstable=float(tracker.unstable.mean()),
                force_err=float(np.abs(cpu.forces() - dev.forces())[~flagged].max() / np.abs(cpu.forces()).max()))
     cpu.close()

@@ -24,13 +24,13 @@ EXPORTS = (
     "wb_set_coordinates", "wb_set_weights", "wb_get_coordinates", "wb_get_weights", "wb_get_forces", "wb_reset_optimizer",
     "wb_set_iteration", "wb_step", "wb_step_async", "wb_step_collect", "wb_synchronize", "wb_query_candidates",
     "wb_enable_timing", "wb_get_phase_times", "wb_mark", "wb_elapsed_ms", "wb_launch_count", "wb_comm_unique_id", "wb_comm_init", "wb_reconstruction",
-    "wb_edge_detection",
+    "wb_edge_detection", "wb_set_list_policy",
 )
 
 
 class WbOptions(C.Structure):
     _fields_ = [
-        ("embedding_dimension", C.c_int32), ("optimizer", C.c_int32), ("precision", C.c_int32), ("device", C.c_int32),
+        ("embedding_dimension", C.c_int32), ("optimizer", C.c_int32), ("reserved2", C.c_int32), ("device", C.c_int32),
         ("keep_forces", C.c_int32), ("reserved0", C.c_int32),
         ("attraction_scale", C.c_double), ("repulsion_scale", C.c_double), ("centre_scale", C.c_double),
         ("edge_length", C.c_double), ("doubling_factor", C.c_double), ("simple_max_displacement", C.c_double),
@@ -43,6 +43,7 @@ class WbStepStats(C.Structure):
         ("loss_attract", C.c_double), ("loss_repel", C.c_double), ("sum_displacement", C.c_double),
         ("sum_radius_sq", C.c_double), ("rel_displacement", C.c_double), ("num_repulsion_pairs", C.c_double),
         ("num_candidates", C.c_double), ("num_box_tests", C.c_double), ("centroid", C.c_double * 32), ("iteration", C.c_int64),
+        ("num_listed_pairs", C.c_double), ("list_rebuilt", C.c_double), ("list_skin", C.c_double), ("max_displacement_ratio", C.c_double),
     ]
 
     def as_dict(self):
@@ -82,6 +83,7 @@ def lib():
         "wb_launch_count": (C.c_int64, [H]),
         "wb_reconstruction": (C.c_int, [H, i32, ip, dp]),
         "wb_edge_detection": (C.c_int, [H, C.c_int64, ip, ip, C.POINTER(C.c_uint8), dp]),
+        "wb_set_list_policy": (C.c_int, [H, C.c_double, C.c_double]),
         "wb_comm_unique_id": (C.c_int, [C.c_char_p]), "wb_comm_init": (C.c_int, [H, C.c_char_p, i32, i32]),
     }
     for name, (res, args) in sig.items():
@@ -183,6 +185,10 @@ class DeviceEmbedder:
         st = WbStepStats()
         self._check(self._l.wb_step_collect(self._h, C.byref(st)))
         return st.as_dict()
+
+    def set_list_policy(self, skin_max, reuse_steps=4.0):
+        """Policy of the repulsion pair list (include/wembed_b200.h); results never depend on it."""
+        self._check(self._l.wb_set_list_policy(self._h, float(skin_max), float(reuse_steps)))
 
     def synchronize(self):
         self._check(self._l.wb_synchronize(self._h))

@@ -1,8 +1,10 @@
 // C ABI (include/wembed_b200.h) and host orchestration of the device step.
 //
-// One wb_embedder owns one device-resident problem and one CUDA stream.  A step is a fixed sequence of
-// kernel launches on that stream (see enqueue_step); the only host<->device traffic per step is one
-// small D2H copy of the reduced sums.  There is no CPU fallback anywhere in this file.
+// One wb_embedder owns one device-resident problem and one CUDA stream.  A step is a fixed sequence of kernel launches on that
+// stream (launch_step); which of them do work - index rebuild + repulsion search, or only the evaluation of the stored pair list -
+// is decided by the device itself (StepCtrl, params.cuh), so steps can be queued without the host waiting for anything.  The only
+// host<->device traffic per step is one small H2D copy of the step's scalars and one D2H copy of the reduced sums.
+// There is no CPU fallback anywhere in this file.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <dlfcn.h>
@@ -34,7 +36,6 @@ struct NcclApi {
     ncclResult_t (*getUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*commInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*allGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*reduceScatter)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*commDestroy)(ncclComm_t) = nullptr;
     bool ok = false;
 };
@@ -48,9 +49,8 @@ NcclApi& nccl() {
         a.getUniqueId = reinterpret_cast<decltype(a.getUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
         a.commInitRank = reinterpret_cast<decltype(a.commInitRank)>(dlsym(lib, "ncclCommInitRank"));
         a.allGather = reinterpret_cast<decltype(a.allGather)>(dlsym(lib, "ncclAllGather"));
-        a.reduceScatter = reinterpret_cast<decltype(a.reduceScatter)>(dlsym(lib, "ncclReduceScatter"));
         a.commDestroy = reinterpret_cast<decltype(a.commDestroy)>(dlsym(lib, "ncclCommDestroy"));
-        a.ok = a.getUniqueId && a.commInitRank && a.allGather && a.reduceScatter && a.commDestroy;
+        a.ok = a.getUniqueId && a.commInitRank && a.allGather && a.commDestroy;
         return a;
     }();
     return api;
@@ -68,9 +68,14 @@ T* dalloc(size_t count) {
     return p;
 }
 
+// host copy of a step's scalars + where its sums land; lives in pinned memory until the step has been collected
+struct StepSlotHost {
+    wb::StepDyn dyn;
+    double sums[wb::kMaxSums + 32];
+};
 struct PendingStep {
     cudaEvent_t done;
-    double* hostSums;     // pinned, kSumsTotal doubles
+    StepSlotHost* host;   // pinned
     int64_t iteration;
     bool trivial;         // n <= 1: nothing was launched
 };
@@ -88,25 +93,37 @@ struct wb_embedder {
 
     // layout state
     float4 *x = nullptr, *xNew = nullptr, *mom1 = nullptr, *mom2 = nullptr, *force = nullptr;
-    long long* forceRep = nullptr;        // repulsion results, one row of 4V + 2 fixed-point integers per vertex
-    size_t forceRepBytes = 0;
-    double fixForce = 1.0, fixLoss = 1.0; // fixed-point scales of those rows (powers of two, chosen by wb_set_weights)
-    wb::RepLayout repLayout{1, 0, 0};     // which sorted positions this rank's repulsion walk queries
-    int* invOrder = nullptr;              // vertex -> sorted position
+    size_t rowsAlloc = 0;                 // rows of x / xNew / mom / force (n rounded up to whole tiles)
     float* iw = nullptr;
-    float* edgeWs = nullptr;              // ws(v,u) = iw_v * iw_u of every CSR entry
-    uint32_t* mtScratch = nullptr;        // WB_ATTRACT_STAGED: tie-break generator state, one row of 624 words per warp
-    int* chunkCounter = nullptr;          // work counter of the persistent repulsion kernel
-    int numHeavy = 0;                     // vertices of weight >= kHeavyWeight x mean, walked by k_repulse_heavy
-    int *heavyVertex = nullptr, *heavySlot = nullptr;
-    int numHubs = 0;                      // rows longer than kHubThreshold, pre-summed by k_attract_hubs
-    int *hubVertex = nullptr, *hubSlot = nullptr;
-    double* hubForce = nullptr;
+    double fixForce = 1.0, fixLoss = 1.0; // fixed-point scales of the repulsive terms (powers of two, chosen by wb_set_weights)
+    double maxIw = 1.0, minIw = 1.0;
     std::vector<double> weights;          // state.currentWeights
     std::vector<int> hostDegree;          // CSR row lengths (host copy)
     std::vector<double> classMax;         // maxWeightOfClass[class(v)] (WeightedIndex.cpp:25-32), for the test hook
     int64_t iteration = 0;                // state.currentIteration
     int adamT = 0;                        // AdamOptimizer::t
+
+    // device-side control block, per-step scalars, pair list
+    wb::StepCtrl* ctrl = nullptr;
+    wb::StepDyn* dyn = nullptr;
+    int2* pairBuf = nullptr;
+    unsigned int pairCap = 0;
+    unsigned int* pairCounts = nullptr;   // [kMaxRanks]
+    int *repDeg = nullptr, *repRowPtr = nullptr, *repCol = nullptr, *scanSums = nullptr;
+    int scanBlocks = 0;
+    float skinMax = 0.f, reuseTarget = 4.f;
+    int nextRebuild = 1;                  // what the host knows about the next step: 1 rebuilds (or unknown), 0 reuses the list
+    bool quantValid = false;              // the quantisation frame on the device belongs to the current positions
+
+    wb::RepLayout repLayout{1, 0, 0};     // which sorted positions this rank's repulsion walk queries
+    int* chunkCounter = nullptr;          // work counter of the persistent repulsion kernel
+    int numHeavy = 0;                     // vertices of weight >= kHeavyWeight x mean, walked by k_repulse_heavy
+    int *heavyVertex = nullptr, *heavySlot = nullptr, *heavyPos = nullptr;
+    int numHubs = 0;                      // long CSR rows and heavy vertices, summed by k_hub_rows
+    int *hubVertex = nullptr, *hubSlot = nullptr;
+    double* hubD = nullptr;
+    long long* hubF = nullptr;
+    uint32_t* mtScratch = nullptr;        // tie-break generator state, one row of 624 words per warp of the fused kernel
 
     // spatial index
     int mortonBits = 0;                   // bits per dimension of the 32-bit Morton key
@@ -114,12 +131,9 @@ struct wb_embedder {
     int *valsIn = nullptr, *valsOut = nullptr;
     void* cubTemp = nullptr;
     size_t cubBytes = 0;
-    int momentBlocks = 0;
-    float* momentPartials = nullptr;
     wb::QuantParams* quant = nullptr;
     float4* blkH = nullptr;               // half-precision copy of the array-of-blocks tree (box rounds of k_repulse_pairs)
-    float4 *ptsH = nullptr, *pmeta = nullptr;   // WB_POINT_HALF: half-precision copy of the sorted points + per-point record
-    float halfSigmaLimit = 0.f;           // layouts with a larger per-dimension sd walk the fp32 boxes (k_quant_params)
+    float halfSigmaLimit = 0.f;           // layouts with a larger per-dimension sd walk the fp32 boxes
     int halfMode = -1;                    // WB_HALF_BOXES: 0 never, 1 always, unset: by the layout
     float4* lvlLo[wb::kMaxLevels] = {};
     float4* lvlHi[wb::kMaxLevels] = {};
@@ -127,18 +141,18 @@ struct wb_embedder {
     int* ids = nullptr;
     float4* blk = nullptr;                // array-of-blocks copy of the boxes (wb::TreeView::blk)
     wb::TreeView tree{};
+    wb::TreePlanes planes{};
 
-    // reductions: sumsAll = [ force sums (2 + 4V) | repulsion counters (2) | observe sums (2) ]
-    int forceBlocks = 0, forceVertsPerBlock = 0, repBlocks = 0, obsBlocks = 0, obsVertsPerBlock = 0;
-    double *partialsForce = nullptr, *partialsRep = nullptr, *partialsObs = nullptr, *sumsAll = nullptr;
-    int sumsTotal = 0;
+    // reductions (all over GLOBAL tiles, see step.cuh)
+    int tileVerts = 0, numTiles = 0, numGroups = 0, cols = 0;       // fused-kernel tiles, groups of kTileGroup tiles, sums per tile
+    int fusedBlocks = 0, tilesPerBlock = 0, repBlocks = 0, numObsTiles = 0;
+    double *tilePartials = nullptr, *groupSums = nullptr, *forceSums = nullptr, *obsPartials = nullptr, *walkPartials = nullptr, *stats = nullptr;
+    float* momentPartials = nullptr;
+    int statsTotal = 0;
 
-    // vertex-sharded multi-GPU step (wb_comm_init): this rank owns vertices [ownBegin, ownEnd); x is replicated and
-    // re-assembled by an all-gather of the owners' rows at the end of every step
+    // vertex-sharded multi-GPU step (wb_comm_init): this rank owns vertices [ownBegin, ownEnd)
     ncclComm_t comm = nullptr;
     int world = 1, rank = 0, ownBegin = 0, ownEnd = 0, rowsPerRank = 0;
-    double* gathered = nullptr;           // world x sumsTotal doubles
-    double* localSums = nullptr;          // this rank's share of sumsAll
 
     std::deque<PendingStep> pending;
     std::vector<PendingStep> freeSlots;
@@ -151,7 +165,7 @@ struct wb_embedder {
     cudaEvent_t marks[8] = {};
     int64_t launches = 0;
     bool timing = false;
-    cudaEvent_t ev[7] = {};
+    cudaEvent_t ev[6] = {};
     double phaseMs[6] = {0, 0, 0, 0, 0, 0};
     bool havePhase = false;
 };
@@ -159,7 +173,6 @@ struct wb_embedder {
 namespace {
 
 using wb::kFan;
-constexpr int kHubThreshold = 96;   // CSR rows longer than this are summed by one block each (k_attract_hubs)
 
 #define WB_DISPATCH_V(V_, ...)                                   \
     switch (V_) {                                                \
@@ -176,30 +189,17 @@ constexpr int kHubThreshold = 96;   // CSR rows longer than this are summed by o
 
 inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
-// Block -> vertex-range assignment of the fused attraction + optimizer kernel over `own` vertices.  k_attract_update: many blocks of
-// a few passes; k_attract_staged (WB_ATTRACT_STAGED): four blocks per SM's two resident slots, each a long pipelined run of passes.
-inline void attract_grid(int V, int own, int& blocks, int& vertsPerBlock) {
-    const int perPass = 256 / wb::attract_lanes(V);      // vertices per block iteration
-#if WB_ATTRACT_STAGED
-    const int maxBlocks = 148 * 4;
-#else
-    const int maxBlocks = 148 * 16;
-#endif
-    blocks = std::max(1, std::min(div_up(own, perPass), maxBlocks));
-    vertsPerBlock = std::max(perPass, div_up(div_up(own, blocks), perPass) * perPass);
-    blocks = std::max(1, div_up(own, vertsPerBlock));
-}
-
 void free_all(wb_embedder* h) {
     auto F = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
-    F(h->rowPtr); F(h->col); F(h->x); F(h->xNew); F(h->mom1); F(h->mom2); F(h->forceRep); F(h->force);
-    F(h->iw); F(h->invOrder); F(h->edgeWs); F(h->mtScratch); F(h->chunkCounter); F(h->hubVertex); F(h->hubSlot); F(h->hubForce); F(h->heavyVertex); F(h->heavySlot); F(h->keysIn); F(h->keysOut); F(h->valsIn); F(h->valsOut);
-    F(h->cubTemp); F(h->momentPartials); F(h->quant); F(h->ids); F(h->blk); F(h->blkH); F(h->ptsH); F(h->pmeta);
+    F(h->rowPtr); F(h->col); F(h->x); F(h->xNew); F(h->mom1); F(h->mom2); F(h->force); F(h->iw);
+    F(h->ctrl); F(h->dyn); F(h->pairBuf); F(h->pairCounts); F(h->repDeg); F(h->repRowPtr); F(h->repCol); F(h->scanSums);
+    F(h->chunkCounter); F(h->heavyVertex); F(h->heavySlot); F(h->heavyPos); F(h->hubVertex); F(h->hubSlot); F(h->hubD); F(h->hubF); F(h->mtScratch);
+    F(h->keysIn); F(h->keysOut); F(h->valsIn); F(h->valsOut); F(h->cubTemp); F(h->quant); F(h->ids); F(h->blk); F(h->blkH);
     for (int l = 0; l < wb::kMaxLevels; ++l) { F(h->lvlLo[l]); if (l > 0) F(h->lvlHi[l]); F(h->lvlBound[l]); }
-    F(h->partialsForce); F(h->partialsRep); F(h->partialsObs); F(h->sumsAll); F(h->gathered); F(h->localSums);
+    F(h->tilePartials); F(h->groupSums); F(h->forceSums); F(h->obsPartials); F(h->walkPartials); F(h->stats); F(h->momentPartials);
     if (h->comm) { nccl().commDestroy(h->comm); h->comm = nullptr; }
-    for (auto& p : h->pending) { cudaEventDestroy(p.done); cudaFreeHost(p.hostSums); }
-    for (auto& p : h->freeSlots) { cudaEventDestroy(p.done); cudaFreeHost(p.hostSums); }
+    for (auto& p : h->pending) { cudaEventDestroy(p.done); cudaFreeHost(p.host); }
+    for (auto& p : h->freeSlots) { cudaEventDestroy(p.done); cudaFreeHost(p.host); }
     h->pending.clear(); h->freeSlots.clear();
     for (auto& l : h->stageLanes) {
         for (int b = 0; b < 2; ++b) { if (l.pinned[b]) cudaFreeHost(l.pinned[b]); if (l.done[b]) cudaEventDestroy(l.done[b]); }
@@ -212,7 +212,7 @@ void free_all(wb_embedder* h) {
     h->stream = nullptr;
 }
 
-// Fixed-point scales of the repulsion rows: the largest power of two such that n terms of the largest possible magnitude
+// Fixed-point scales of the repulsive terms: the largest power of two such that n terms of the largest possible magnitude
 // (|force component| <= |repulsionScale| * max ws, loss term <= L / min ws, ws = iw_v * iw_u) stay below 2^62.
 void choose_fixed_scales(wb_embedder* h, double maxIw, double minIw) {
     auto scale = [&](double maxTerm) {
@@ -220,82 +220,153 @@ void choose_fixed_scales(wb_embedder* h, double maxIw, double minIw) {
         if (!(bound > 0.0) || !std::isfinite(bound)) return 1.0;
         return std::ldexp(1.0, std::max(-900, std::min(900, 61 - (int)std::ceil(std::log2(bound)))));
     };
+    h->maxIw = maxIw; h->minIw = minIw;
     h->fixForce = scale(std::fabs(h->opt.repulsion_scale) * maxIw * maxIw);
     h->fixLoss = scale(h->opt.edge_length / (minIw * minIw));
-    // Box format of the repulsion walk (k_quant_params decides every step): half-precision boxes while the layout's largest
-    // per-dimension sd is at most kHalfSpread smallest interaction radii (L / max ws); the rounding of a centred coordinate is
-    // ~sd * 2^-11, i.e. ~3 % of that radius at the limit.  Simulated on the c3 layout with shortened mantissas: +3 % box tests and
-    // +7 % point tests at 55 radii (the half-precision rounds are ~26 % cheaper), +0.2 % / +0.4 % at the 3.4 radii of c3 itself.
+    // Box format of the repulsion walk (decided on the device whenever the quantisation frame is computed): half-precision boxes while
+    // the layout's largest per-dimension sd is at most kHalfSpread smallest interaction radii (L / max ws); the rounding of a centred
+    // coordinate is ~sd * 2^-11, i.e. ~3 % of that radius at the limit.  Simulated on the c3 layout with shortened mantissas: +3 % box
+    // tests and +7 % point tests at 55 radii (the half-precision rounds are ~26 % cheaper), +0.2 % / +0.4 % at the 3.4 radii of c3 itself.
     // WB_HALF_BOXES=0 / 1 forces one format (A/B runs, tests).
     constexpr double kHalfSpread = 64.0;
     if (h->halfMode < 0) {
         const char* env = std::getenv("WB_HALF_BOXES");
         h->halfMode = env ? (std::atoi(env) != 0 ? 1 : 0) : 2;
     }
-    const double rMin = h->opt.edge_length / (maxIw * maxIw), rMax = h->opt.edge_length / (minIw * minIw);
+    const double rMin = h->opt.edge_length / (maxIw * maxIw), rMax = h->opt.edge_length * (1.0 + (double)h->skinMax) / (minIw * minIw);
     // squared gaps are summed in half precision (max 65504): radii beyond ~200 cannot be tested there at all
     const bool representable = rMax < 200.0;
     h->halfSigmaLimit = h->halfMode == 0 ? -1.f : (h->halfMode == 1 ? std::numeric_limits<float>::infinity()
                                                                     : (representable ? (float)(kHalfSpread * rMin) : -1.f));
 }
 
+// (re)writes the device control block: the pair list is void, the next step rebuilds index and list without a skin
+void invalidate_list(wb_embedder* h) {
+    wb::StepCtrl c{};
+    c.overflow = 0; c.pairNeeded = 0; c.listValid = 0; c.rebuild = 1;
+    c.skin = 0.f; c.dispAccum = 0.f;
+    c.listL2 = (float)(h->opt.edge_length * h->opt.edge_length) * (1.0f + wb::kPruneSlack);
+    c.pruneL = std::sqrt(c.listL2);
+    c.skinMax = h->skinMax; c.reuseTarget = h->reuseTarget; c.skinCap = h->skinMax;
+    c.pairBudget = (unsigned int)std::min<int64_t>((int64_t)4 * std::max(h->n, 1), 0x7fffffff);
+    c.numBuilds = 0; c.numReused = 0;
+    WB_CUDA(cudaMemcpyAsync(h->ctrl, &c, sizeof(c), cudaMemcpyHostToDevice, h->stream));   // pageable source: the copy is staged before the call returns
+    h->nextRebuild = 1;
+}
+
+// hub rows (long CSR rows; heavy vertices, whose rows of the pair list are long) and heavy vertices (walked by one block each)
+void rebuild_hub_lists(wb_embedder* h) {
+    const int n = h->n, V = h->V;
+    auto F = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
+    F(h->hubVertex); F(h->hubSlot); F(h->hubD); F(h->hubF); F(h->heavyVertex); F(h->heavySlot); F(h->heavyPos); F(h->walkPartials);
+    double mean = 0.0;
+    for (int v = 0; v < n; ++v) mean += h->weights[v];
+    mean /= (double)std::max(n, 1);
+    std::vector<int> hubs, hubSlot(n, -1), heavy, heavySlot(n, -1);
+    for (int v = 0; v < n; ++v) {
+        const bool isHeavy = h->weights[v] >= (double)wb::kHeavyWeight * mean;
+        if (isHeavy) { heavySlot[v] = (int)heavy.size(); heavy.push_back(v); }
+        if (isHeavy || h->hostDegree[v] > wb::kHubThreshold) { hubSlot[v] = (int)hubs.size(); hubs.push_back(v); }
+    }
+    h->numHubs = (int)hubs.size();
+    h->numHeavy = (int)heavy.size();
+    if (h->numHubs) {
+        h->hubVertex = dalloc<int>(hubs.size());
+        h->hubSlot = dalloc<int>(n);
+        h->hubD = dalloc<double>(hubs.size() * wb::hub_doubles(V));
+        h->hubF = dalloc<long long>(hubs.size() * wb::hub_fixed(V));
+        WB_CUDA(cudaMemcpyAsync(h->hubVertex, hubs.data(), sizeof(int) * hubs.size(), cudaMemcpyHostToDevice, h->stream));
+        WB_CUDA(cudaMemcpyAsync(h->hubSlot, hubSlot.data(), sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
+    }
+    if (h->numHeavy) {
+        h->heavyVertex = dalloc<int>(heavy.size());
+        h->heavySlot = dalloc<int>(n);
+        h->heavyPos = dalloc<int>(heavy.size());
+        WB_CUDA(cudaMemcpyAsync(h->heavyVertex, heavy.data(), sizeof(int) * heavy.size(), cudaMemcpyHostToDevice, h->stream));
+        WB_CUDA(cudaMemcpyAsync(h->heavySlot, heavySlot.data(), sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
+        WB_CUDA(cudaMemsetAsync(h->heavyPos, 0, sizeof(int) * heavy.size(), h->stream));
+    }
+    h->walkPartials = dalloc<double>(((size_t)h->repBlocks * 8 + heavy.size()) * 3);
+    WB_CUDA(cudaStreamSynchronize(h->stream));
+}
+
+// pair buffer + CSR entries for `cap` unordered pairs
+void allocate_pair_list(wb_embedder* h, unsigned int cap) {
+    auto F = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
+    F(h->pairBuf); F(h->repCol);
+    h->pairCap = cap;
+    h->pairBuf = dalloc<int2>((size_t)cap);
+    h->repCol = dalloc<int>((size_t)2 * cap + 8);
+}
+
 void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
     const int n = h->n, V = h->V;
     WB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    // (+ 8: k_attract_staged copies whole 16-byte groups of these arrays)
+    {   // policy of the pair list (A/B runs and tests; results never depend on it)
+        const char* e = std::getenv("WB_SKIN_MAX");
+        h->skinMax = e ? (float)std::atof(e) : 1.0f;
+        e = std::getenv("WB_REUSE_STEPS");
+        h->reuseTarget = e ? std::max(1.f, (float)std::atof(e)) : 4.f;
+    }
+    // (+ 8: the fused kernel copies whole 16-byte groups of these arrays)
     h->rowPtr = dalloc<int>(n + 1 + 8);
     h->col = dalloc<int>(h->numDirected + 8);
+    WB_CUDA(cudaMemsetAsync(h->rowPtr, 0, sizeof(int) * (n + 1 + 8), h->stream));
     WB_CUDA(cudaMemcpyAsync(h->rowPtr, rowPtr, sizeof(int) * (n + 1), cudaMemcpyHostToDevice, h->stream));
     if (h->numDirected) WB_CUDA(cudaMemcpyAsync(h->col, col, sizeof(int) * h->numDirected, cudaMemcpyHostToDevice, h->stream));
-
     h->hostDegree.resize(n);
     for (int v = 0; v < n; ++v) h->hostDegree[v] = rowPtr[v + 1] - rowPtr[v];
-    {   // hub rows
-        std::vector<int> hubs, slot(n, -1);
-        for (int v = 0; v < n; ++v)
-            if (rowPtr[v + 1] - rowPtr[v] > kHubThreshold) { slot[v] = (int)hubs.size(); hubs.push_back(v); }
-        h->numHubs = (int)hubs.size();
-        if (h->numHubs) {
-            h->hubVertex = dalloc<int>(hubs.size());
-            h->hubSlot = dalloc<int>(n);
-            h->hubForce = dalloc<double>(hubs.size() * (4 * V + 2));
-            WB_CUDA(cudaMemcpyAsync(h->hubVertex, hubs.data(), sizeof(int) * hubs.size(), cudaMemcpyHostToDevice, h->stream));
-            WB_CUDA(cudaMemcpyAsync(h->hubSlot, slot.data(), sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
-            WB_CUDA(cudaStreamSynchronize(h->stream));
-        }
-    }
-    const size_t rows = (size_t)n * V;
-    h->repLayout = wb::RepLayout{1, 0, div_up(std::max(n, 1), 32) * 32};
-    h->forceRepBytes = (size_t)std::max(n, 1) * (4 * V + 2) * sizeof(long long);
-    h->forceRep = dalloc<long long>((size_t)std::max(n, 1) * (4 * V + 2));
-    WB_CUDA(cudaMemsetAsync(h->forceRep, 0, h->forceRepBytes, h->stream));
-    h->invOrder = dalloc<int>(n);
-    WB_CUDA(cudaMemsetAsync(h->invOrder, 0, std::max(n, 1) * sizeof(int), h->stream));
+
+    // tiles of the fused kernel and of the recentre pass; rows are allocated for whole tiles so that bulk copies of a last, partial
+    // tile stay inside the arrays
+    h->tileVerts = wb::tile_vertices(V);
+    h->numTiles = div_up(std::max(n, 1), h->tileVerts);
+    h->numGroups = div_up(h->numTiles, wb::kTileGroup);
+    h->cols = wb::tile_sums(V) + 1;
+    h->numObsTiles = div_up(std::max(n, 1), wb::kObsTile);
+    h->rowsAlloc = (size_t)h->numTiles * h->tileVerts;
+    const size_t rows = h->rowsAlloc * V;
     for (float4** p : {&h->x, &h->xNew, &h->mom1, &h->mom2, &h->force}) {
         *p = dalloc<float4>(rows);
         WB_CUDA(cudaMemsetAsync(*p, 0, std::max<size_t>(rows, 1) * sizeof(float4), h->stream));
     }
-    h->iw = dalloc<float>(n);
-    h->edgeWs = dalloc<float>(h->numDirected + 8);
-    if (n) wb::k_fill<float><<<div_up(n, 256), 256, 0, h->stream>>>(h->iw, n, 1.0f);
-    if (h->numDirected) wb::k_fill<float><<<div_up(h->numDirected, 256), 256, 0, h->stream>>>(h->edgeWs, h->numDirected, 1.0f);
+    h->iw = dalloc<float>(h->rowsAlloc + 8);
+    wb::k_fill<float><<<div_up(h->rowsAlloc + 8, 256), 256, 0, h->stream>>>(h->iw, (int64_t)h->rowsAlloc + 8, 1.0f);
     h->weights.assign(n, 1.0);
-    choose_fixed_scales(h, 1.0, 1.0);
     h->classMax.assign(n, 1.0);
+
+    h->ctrl = dalloc<wb::StepCtrl>(1);
+    h->dyn = dalloc<wb::StepDyn>(1);
+    h->pairCounts = dalloc<unsigned int>(wb::kMaxRanks);
+    WB_CUDA(cudaMemsetAsync(h->pairCounts, 0, sizeof(unsigned int) * wb::kMaxRanks, h->stream));
+    {   // pair list: room for 8 unordered pairs per vertex (never more than all pairs); grown on demand (collect_step)
+        const int64_t all = (int64_t)n * (n - 1) / 2;
+        int64_t cap = std::max<int64_t>(1024, std::min<int64_t>({all + 8, (int64_t)8 * n, (int64_t)0x3fffffff}));
+        if (const char* e = std::getenv("WB_PAIR_CAP")) cap = std::max<int64_t>(1, std::atoll(e));      // tests: force the growth path
+        allocate_pair_list(h, (unsigned int)cap);
+    }
+    h->repDeg = dalloc<int>(h->rowsAlloc + 8);
+    h->repRowPtr = dalloc<int>(h->rowsAlloc + 1 + 8);
+    WB_CUDA(cudaMemsetAsync(h->repDeg, 0, sizeof(int) * (h->rowsAlloc + 8), h->stream));
+    WB_CUDA(cudaMemsetAsync(h->repRowPtr, 0, sizeof(int) * (h->rowsAlloc + 1 + 8), h->stream));
+    h->scanBlocks = div_up(std::max(n, 1), wb::kScanItems);
+    h->scanSums = dalloc<int>(h->scanBlocks + 1);
+    choose_fixed_scales(h, 1.0, 1.0);
 
     // Morton keys: as many bits per dimension as fit a 32-bit key
     // 32-bit keys: floor(32 / d) bits per dimension.  Measured alternatives that did not pay and were removed: 64-bit keys (d = 16:
     // 4 instead of 2 bits per dimension, same test counts, dearer sort) and a weight band in the top key bits (c4: separate subtrees
     // per band cost more spatial coherence than the tighter pruning bounds saved, 150 vs 110 ms per step).
     h->mortonBits = std::max(1, std::min(16, 32 / h->dim));
+    if (const char* e = std::getenv("WB_MORTON_BITS")) h->mortonBits = std::max(1, std::min(h->mortonBits, std::atoi(e)));
     h->keysIn = dalloc<uint32_t>(n); h->keysOut = dalloc<uint32_t>(n);
     h->valsIn = dalloc<int>(n); h->valsOut = dalloc<int>(n);
     h->cubBytes = 0;
     WB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, h->cubBytes, h->keysIn, h->keysOut, h->valsIn, h->valsOut, std::max(n, 1), 0, 32, h->stream));
     h->cubTemp = dalloc<char>(h->cubBytes);
-    h->momentBlocks = std::max(1, std::min(div_up(n, 256), 592));
-    h->momentPartials = dalloc<float>((size_t)h->momentBlocks * 4 * wb::kMaxDim);
+    h->momentPartials = dalloc<float>((size_t)h->numObsTiles * 4 * wb::kMaxDim);
     h->quant = dalloc<wb::QuantParams>(1);
+    WB_CUDA(cudaMemsetAsync(h->quant, 0, sizeof(wb::QuantParams), h->stream));
 
     // hierarchy: level 0 = points (stride = n rounded up to kFan); level l >= 1 = ceil(count[l-1] / kFan) boxes
     wb::TreeView& t = h->tree;
@@ -318,6 +389,7 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
         h->lvlBound[level] = dalloc<float>(t.stride[level]);
         wb::k_fill<float><<<div_up(t.stride[level], 256), 256, 0, h->stream>>>(h->lvlBound[level], t.stride[level], 1.0f);
         t.lo[level] = h->lvlLo[level]; t.hi[level] = h->lvlHi[level]; t.bound[level] = h->lvlBound[level];
+        h->planes.lo[level] = h->lvlLo[level]; h->planes.hi[level] = h->lvlHi[level]; h->planes.bound[level] = h->lvlBound[level];
         if (level >= 1 && count <= kFan) break;
         count = std::max(1, div_up(count, kFan));
         ++level;
@@ -337,69 +409,84 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
         WB_CUDA(cudaMemsetAsync(h->blkH, 0, h4 * sizeof(float4), h->stream));
         t.blkH = h->blkH;
         t.quant = h->quant;
-#if WB_POINT_HALF
-        h->ptsH = dalloc<float4>((size_t)wb::half_chunks(V) * t.stride[0]);
-        h->pmeta = dalloc<float4>(t.stride[0]);
-        WB_CUDA(cudaMemsetAsync(h->ptsH, 0, sizeof(float4) * wb::half_chunks(V) * t.stride[0], h->stream));
-        WB_CUDA(cudaMemsetAsync(h->pmeta, 0, sizeof(float4) * t.stride[0], h->stream));
-#endif
-        t.ptsH = h->ptsH;
-        t.pmeta = h->pmeta;
-        // the walk's per-warp queries + stacks exceed the 48 KB static limit for the wider rows
+        // the walk's per-warp queries + stacks and the fused kernel's stages exceed the 48 KB static limit
         WB_DISPATCH_V(V, WB_CUDA(cudaFuncSetAttribute(wb::k_repulse_pairs<V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wb::repulse_smem_bytes(V, false)));
-                         WB_CUDA(cudaFuncSetAttribute(wb::k_repulse_pairs<V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wb::repulse_smem_bytes(V, true))));
+                         WB_CUDA(cudaFuncSetAttribute(wb::k_repulse_pairs<V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wb::repulse_smem_bytes(V, true)));
+                         WB_CUDA(cudaFuncSetAttribute(wb::k_step_fused<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wb::step_fused_smem<V>())));
     }
     h->ids = dalloc<int>(t.stride[0]);
     WB_CUDA(cudaMemsetAsync(h->ids, 0xff, sizeof(int) * t.stride[0], h->stream));
     t.ids = h->ids;
 
-    // reductions: fixed block -> vertex-range assignment so the sums do not depend on scheduling
-    attract_grid(V, n, h->forceBlocks, h->forceVertsPerBlock);
-#if WB_ATTRACT_STAGED
-    h->mtScratch = dalloc<uint32_t>((size_t)h->forceBlocks * 8 * 624);   // sharding only shrinks the grid
-    WB_DISPATCH_V(V, WB_CUDA(cudaFuncSetAttribute(wb::k_attract_staged<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wb::attract_staged_smem<V>())));
-#endif
-    {   // persistent repulsion grid: enough resident blocks to fill every SM, never more than there are chunks
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->opt.device);
-        h->repBlocks = std::max(1, std::min(div_up(div_up(n, 8), 8), sms * 4));
-    }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->opt.device);
+    // persistent repulsion grid: enough resident blocks to fill every SM, never more than there are chunks
+    h->repBlocks = std::max(1, std::min(div_up(div_up(n, 8), 8), sms * 4));
     h->chunkCounter = dalloc<int>(1);
-    h->obsBlocks = std::max(1, std::min(div_up(n, 256), 148 * 8));
-    h->obsVertsPerBlock = std::max(256, div_up(div_up(n, h->obsBlocks), 256) * 256);
-    h->obsBlocks = std::max(1, div_up(n, h->obsVertsPerBlock));
-    h->ownBegin = 0; h->ownEnd = n; h->rowsPerRank = n;
-    const int K = 2 + 4 * V;
-    h->sumsTotal = K + 5;      // [ force sums (K) | repulsion counters: pairs, point tests, box tests | observe sums (2) ]
-    h->partialsForce = dalloc<double>((size_t)h->forceBlocks * K);
-    h->partialsRep = dalloc<double>((size_t)h->repBlocks * 8 * 3);
-    h->partialsObs = dalloc<double>((size_t)h->obsBlocks * 2);
-    h->sumsAll = dalloc<double>(h->sumsTotal);
-    WB_CUDA(cudaMemsetAsync(h->sumsAll, 0, sizeof(double) * h->sumsTotal, h->stream));
+    h->repLayout = wb::RepLayout{1, 0, div_up(std::max(n, 1), 32) * 32};
+    h->ownBegin = 0; h->ownEnd = n; h->rowsPerRank = (int)h->rowsAlloc;
+    // fused kernel: every block works through a contiguous run of tiles, as many blocks as can be resident
+    h->fusedBlocks = std::max(1, std::min(h->numTiles, sms * WB_FUSED_MINBLOCKS));
+    h->tilesPerBlock = div_up(h->numTiles, h->fusedBlocks);
+    h->fusedBlocks = div_up(h->numTiles, h->tilesPerBlock);
+    h->mtScratch = dalloc<uint32_t>((size_t)h->fusedBlocks * 8 * 624);
+    h->tilePartials = dalloc<double>((size_t)h->numTiles * h->cols);
+    h->groupSums = dalloc<double>((size_t)h->numGroups * h->cols);
+    h->forceSums = dalloc<double>(h->cols);
+    h->obsPartials = dalloc<double>((size_t)h->numObsTiles * 2);
+    h->statsTotal = h->cols + wb::kTailStats;
+    h->stats = dalloc<double>(h->statsTotal);
+    WB_CUDA(cudaMemsetAsync(h->stats, 0, sizeof(double) * h->statsTotal, h->stream));
     for (auto& e : h->ev) WB_CUDA(cudaEventCreate(&e));
     for (auto& e : h->marks) WB_CUDA(cudaEventCreate(&e));
+    rebuild_hub_lists(h);
+    invalidate_list(h);
     WB_CUDA(cudaStreamSynchronize(h->stream));
 }
 
-// Rebuild the index from the current positions (WembedEmbedder::updateIndex, every step from scratch).
-// pointBound[v] = the pruning weight factor of v: iw[v] for forces, iw of v's class maximum for the test hook.
-void enqueue_index(wb_embedder* h, const float* pointBound) {
+wb::ForceParams force_params(const wb_embedder* h) {
+    wb::ForceParams fp{};
+    fp.edgeLength = (float)h->opt.edge_length;
+    fp.attractionScale = (float)h->opt.attraction_scale;
+    fp.repulsionScale = (float)h->opt.repulsion_scale;
+    fp.centreScale = (float)h->opt.centre_scale;
+    fp.optimizer = h->opt.optimizer;
+    fp.beta1 = 0.9f; fp.beta2 = 0.999f; fp.eps = 1e-8f;      // WembedEmbedder.hpp:46
+    fp.maxDisplacement = (float)h->opt.simple_max_displacement;
+    fp.seed = h->opt.seed;
+    fp.dim = h->dim;
+    fp.keepForces = h->opt.keep_forces;
+    fp.fixForce = h->fixForce; fp.invFixForce = 1.0 / h->fixForce;
+    fp.fixLoss = h->fixLoss; fp.invFixLoss = 1.0 / h->fixLoss;
+    fp.dispScale = (float)(h->maxIw / h->opt.edge_length) * 1.000001f;
+    return fp;
+}
+
+// quantisation frame of the CURRENT positions (first step after wb_set_coordinates, test hook); inside a run it comes out of the
+// previous step's recentre pass
+void enqueue_frame(wb_embedder* h) {
+    cudaStream_t s = h->stream;
+    WB_DISPATCH_V(h->V, wb::k_moments<V><<<h->numObsTiles, 256, 0, s>>>(h->x, h->n, h->momentPartials));
+    wb::k_quant_params<<<1, 1024, 0, s>>>(h->momentPartials, h->numObsTiles, h->n, h->dim, h->mortonBits, h->halfSigmaLimit, h->quant);
+    h->launches += 2;
+    h->quantValid = true;
+}
+
+// Rebuild the index from the current positions (WembedEmbedder::updateIndex).  pointBound[v] = the pruning weight factor of v: iw[v] for
+// forces, iw of v's class maximum for the test hook.  Inside a step every kernel returns at once unless the device decided to rebuild.
+void enqueue_index(wb_embedder* h, const float* pointBound, int always) {
     const int n = h->n, V = h->V;
     cudaStream_t s = h->stream;
-    WB_DISPATCH_V(V, wb::k_moments<V><<<h->momentBlocks, 256, 0, s>>>(h->x, n, h->momentPartials));
-    wb::k_quant_params<<<1, 1024, 0, s>>>(h->momentPartials, h->momentBlocks, n, h->dim, h->mortonBits, h->halfSigmaLimit, h->quant);
-    WB_DISPATCH_V(V, wb::k_morton_keys<V><<<div_up(n, 256), 256, 0, s>>>(h->x, n, h->dim, h->mortonBits, h->quant, h->keysIn, h->valsIn));
-    WB_CUDA(cub::DeviceRadixSort::SortPairs(h->cubTemp, h->cubBytes, h->keysIn, h->keysOut, h->valsIn, h->valsOut, n, 0, h->mortonBits * h->dim, s));
     const wb::TreeView& t = h->tree;
-    WB_DISPATCH_V(V, wb::k_build_leaves<V><<<div_up(t.stride[0], 256), 256, 0, s>>>(
-                         h->x, pointBound, h->valsOut, n, h->lvlLo[0], t.stride[0], h->lvlBound[0], h->ids, h->invOrder, h->lvlLo[1], h->lvlHi[1],
-                         h->lvlBound[1], t.stride[1], h->blk, t.blockOff[1], h->blkH, h->quant, h->ptsH, h->pmeta));
-    for (int l = 2; l <= t.numLevels; ++l) {
-        WB_DISPATCH_V(V, wb::k_build_level<V><<<div_up((int64_t)t.count[l] * kFan, 256), 256, 0, s>>>(
-                             h->lvlLo[l - 1], h->lvlHi[l - 1], h->lvlBound[l - 1], t.count[l - 1], t.stride[l - 1], h->lvlLo[l], h->lvlHi[l],
-                             h->lvlBound[l], t.count[l], t.stride[l], h->blk, t.blockOff[l], t.blockOff[l - 1], l, h->blkH, h->quant));
+    WB_DISPATCH_V(V, wb::k_morton_keys<V><<<div_up(n, 256), 256, 0, s>>>(h->x, n, h->dim, h->mortonBits, h->quant, h->keysIn, h->valsIn, h->ctrl, always));
+    WB_CUDA(cub::DeviceRadixSort::SortPairs(h->cubTemp, h->cubBytes, h->keysIn, h->keysOut, h->valsIn, h->valsOut, n, 0, h->mortonBits * h->dim, s));
+    WB_DISPATCH_V(V, wb::k_build_low<V><<<div_up(t.stride[0], wb::kBuildThreads), wb::kBuildThreads, 0, s>>>(
+                         h->x, pointBound, h->valsOut, n, t, h->planes, h->ids, h->heavySlot, h->heavyPos, h->blk, h->blkH, h->ctrl, always));
+    h->launches += 3;
+    if (t.numLevels >= 4) {
+        WB_DISPATCH_V(V, wb::k_build_top<V><<<1, 1024, 0, s>>>(t, h->planes, h->blk, h->blkH, h->ctrl, always));
+        h->launches += 1;
     }
-    h->launches += 5 + (t.numLevels - 1);
     WB_CUDA(cudaGetLastError());
 }
 
@@ -411,147 +498,159 @@ PendingStep take_slot(wb_embedder* h) {
     }
     PendingStep p{};
     WB_CUDA(cudaEventCreateWithFlags(&p.done, cudaEventDisableTiming));
-    WB_CUDA(cudaMallocHost(&p.hostSums, sizeof(double) * (wb::kMaxSums + 8)));
+    WB_CUDA(cudaMallocHost(&p.host, sizeof(StepSlotHost)));
     return p;
 }
 
-// WembedEmbedder::calculateStep (WembedEmbedder.cpp:13-63) as a stream of launches.
-void enqueue_step(wb_embedder* h, double learningRate) {
+// WembedEmbedder::calculateStep (WembedEmbedder.cpp:13-63) as a stream of launches; the step's scalars are in slot.host->dyn.
+void launch_step(wb_embedder* h, const PendingStep& slot) {
     const int n = h->n, V = h->V;
     cudaStream_t s = h->stream;
+    const wb::ForceParams fp = force_params(h);
+    WB_CUDA(cudaMemcpyAsync(h->dyn, &slot.host->dyn, sizeof(wb::StepDyn), cudaMemcpyHostToDevice, s));
+    if (!h->quantValid) enqueue_frame(h);
+    // What the host knows: after a blocking step it has read the device's decision for the next one and leaves out the launches of a
+    // build that will not happen; with steps in flight it does not know, queues everything, and the kernels of a build return at once
+    // on a reuse step (correctness never depends on this knowledge: the device flags alone decide what runs).
+    const bool build = h->nextRebuild != 0 || !h->pending.empty();
+
+    if (h->timing) WB_CUDA(cudaEventRecord(h->ev[0], s));
+    wb::k_step_begin<<<1, 32, 0, s>>>(h->ctrl, h->pairCounts, h->world, h->chunkCounter);
+    h->launches += 1;
+    if (build) enqueue_index(h, h->iw, 0);
+    if (h->timing) WB_CUDA(cudaEventRecord(h->ev[1], s));
+    wb::PairSink sink{};
+    sink.seg[0] = h->pairBuf; sink.count = h->pairCounts; sink.cap = h->pairCap; sink.world = 1; sink.rowsPerRank = std::max(h->rowsPerRank, 1);
+    wb::PairSource src{};
+    src.seg[0] = h->pairBuf; src.count = h->pairCounts; src.cap = h->pairCap; src.world = 1; src.ownBegin = h->ownBegin; src.ownEnd = h->ownEnd;
+    const int repWarps = h->repBlocks * wb::repulse_warps(V);
+    if (build) {
+        // at least ~8 work units per resident warp, else the tail of the dynamic schedule dominates
+        const int64_t residentWarps = (int64_t)h->repBlocks * wb::repulse_warps(V);
+        const int queriesPerUnit = h->repLayout.segRows / 32 >= 8 * residentWarps ? 32 : (h->repLayout.segRows / 16 >= 8 * residentWarps ? 16 : 8);
+        // both box formats are launched; the one QuantParams::halfBoxes does not name returns at once (the choice is made on the device
+        // from the layout, the host never waits for it)
+        WB_DISPATCH_V(V, (wb::k_repulse_pairs<V, false><<<h->repBlocks, 32 * wb::repulse_warps(V), wb::repulse_smem_bytes(V, false), s>>>(
+                             h->tree, h->rowPtr, h->col, n, sink, h->repLayout, queriesPerUnit, h->heavySlot, h->chunkCounter, h->walkPartials, h->ctrl)));
+        WB_DISPATCH_V(V, (wb::k_repulse_pairs<V, true><<<h->repBlocks, 32 * wb::repulse_warps(V), wb::repulse_smem_bytes(V, true), s>>>(
+                             h->tree, h->rowPtr, h->col, n, sink, h->repLayout, queriesPerUnit, h->heavySlot, h->chunkCounter, h->walkPartials, h->ctrl)));
+        h->launches += 2;
+        if (h->numHeavy) {
+            WB_DISPATCH_V(V, wb::k_repulse_heavy<V><<<h->numHeavy, 256, 0, s>>>(h->tree, h->rowPtr, h->col, n, sink, h->repLayout, h->heavyVertex, h->heavySlot,
+                                                                                 h->heavyPos, h->walkPartials + (size_t)repWarps * 3, h->ctrl));
+            h->launches += 1;
+        }
+        // pair list -> CSR of partners
+        const int own = std::max(1, h->ownEnd - h->ownBegin);
+        const int pairBlocks = std::max(1, std::min(div_up(h->pairCap, 256), 148 * 8));
+        const int scanBlocks = div_up(own, wb::kScanItems);
+        wb::k_rep_count<<<pairBlocks, 256, 0, s>>>(src, h->repDeg, h->ctrl);
+        wb::k_scan_sums<<<scanBlocks, 256, 0, s>>>(h->repDeg + h->ownBegin, own, h->scanSums, h->ctrl);
+        wb::k_scan_offsets<<<1, 1024, 0, s>>>(h->scanSums, scanBlocks, h->ctrl);
+        wb::k_scan_apply<<<scanBlocks, 256, 0, s>>>(h->repDeg + h->ownBegin, own, h->scanSums, scanBlocks, h->repRowPtr + h->ownBegin, h->ctrl);
+        wb::k_rep_fill<<<pairBlocks, 256, 0, s>>>(src, h->repDeg, h->repRowPtr, h->repCol, h->ctrl);
+        h->launches += 5;
+    }
+    if (h->timing) WB_CUDA(cudaEventRecord(h->ev[2], s));
+    if (h->numHubs) {
+        WB_DISPATCH_V(V, wb::k_hub_rows<V><<<h->numHubs, 256, 0, s>>>(h->x, h->iw, h->rowPtr, h->col, h->repRowPtr, h->repCol, h->hubVertex, h->ownBegin, h->ownEnd,
+                                                                       fp, h->hubD, h->hubF, h->ctrl));
+        h->launches += 1;
+    }
+    const int tileBegin = h->ownBegin / h->tileVerts, tileEnd = div_up(h->ownEnd, h->tileVerts);
+    WB_DISPATCH_V(V, wb::k_step_fused<V><<<h->fusedBlocks, 256, wb::step_fused_smem<V>(), s>>>(
+                         h->x, h->iw, h->rowPtr, h->col, h->repRowPtr, h->repCol, h->ownBegin, h->ownEnd, h->tilesPerBlock, fp, h->dyn, h->hubSlot, h->hubD, h->hubF,
+                         h->xNew, h->mom1, h->mom2, h->force, h->tilePartials, h->mtScratch, h->ctrl));
+    const int ownGroups = div_up(tileEnd - tileBegin, wb::kTileGroup);
+    wb::k_reduce_tile_groups<<<div_up((int64_t)ownGroups * h->cols, 256), 256, 0, s>>>(h->tilePartials, tileBegin, tileEnd, h->cols, h->groupSums, h->ctrl);
+    wb::k_reduce_groups<<<h->cols, 256, 0, s>>>(h->groupSums, h->numGroups, h->cols, h->forceSums, h->ctrl);
+    if (h->timing) WB_CUDA(cudaEventRecord(h->ev[3], s));
+    const int obsBegin = h->ownBegin / wb::kObsTile, obsEnd = div_up(h->ownEnd, wb::kObsTile);
+    WB_DISPATCH_V(V, wb::k_recentre_observe<V><<<obsEnd - obsBegin, 256, 0, s>>>(h->x, h->xNew, n, obsBegin, h->dim, h->forceSums, h->obsPartials, h->momentPartials, h->ctrl));
+    wb::TailPolicy pol{(float)h->opt.edge_length, h->halfSigmaLimit, h->dim, h->mortonBits};
+    wb::k_step_tail<<<1, 1024, 0, s>>>(h->forceSums, h->cols, h->obsPartials, h->numObsTiles, h->momentPartials, n, h->walkPartials, repWarps + h->numHeavy,
+                                        h->pairCounts, h->world, pol, h->quant, h->ctrl, h->stats);
+    if (h->timing) WB_CUDA(cudaEventRecord(h->ev[4], s));
+    h->launches += 5;
+    WB_CUDA(cudaGetLastError());
+    WB_CUDA(cudaMemcpyAsync(slot.host->sums, h->stats, sizeof(double) * h->statsTotal, cudaMemcpyDeviceToHost, s));
+    WB_CUDA(cudaEventRecord(slot.done, s));
+}
+
+void enqueue_step(wb_embedder* h, double learningRate) {
     h->iteration++;                                           // EmbedderState::nextStep
     PendingStep slot = take_slot(h);
     slot.iteration = h->iteration;
-    slot.trivial = n <= 1;
+    slot.trivial = h->n <= 1;
     if (slot.trivial) {                                       // "Abort in the case of the first hierarchy layer" (:19-21)
-        WB_CUDA(cudaEventRecord(slot.done, s));
+        WB_CUDA(cudaEventRecord(slot.done, h->stream));
         h->pending.push_back(slot);
         return;
     }
-    wb::ForceParams fp{};
-    fp.edgeLength = (float)h->opt.edge_length;
-    fp.pruneL2 = (float)(h->opt.edge_length * h->opt.edge_length) * (1.0f + wb::kPruneSlack);
-    fp.attractionScale = (float)h->opt.attraction_scale;
-    fp.repulsionScale = (float)h->opt.repulsion_scale;
-    fp.centreScale = (float)h->opt.centre_scale;
-    fp.optimizer = h->opt.optimizer;
-    fp.lr = (float)learningRate;
-    fp.beta1 = 0.9f; fp.beta2 = 0.999f; fp.eps = 1e-8f;      // WembedEmbedder.hpp:46
     if (h->opt.optimizer == WB_OPT_ADAM) h->adamT++;          // AdamOptimizer.cpp:19
-    fp.invBias1 = (float)(1.0 / (1.0 - std::pow(0.9, h->adamT)));
-    fp.invBias2 = (float)(1.0 / (1.0 - std::pow(0.999, h->adamT)));
-    fp.maxDisplacement = (float)h->opt.simple_max_displacement;
-    fp.seed = h->opt.seed;
-    fp.iteration = (uint32_t)h->iteration;
-    fp.dim = h->dim;
-    fp.keepForces = h->opt.keep_forces;
-    fp.fixForce = h->fixForce; fp.invFixForce = 1.0 / h->fixForce;
-    fp.fixLoss = h->fixLoss; fp.invFixLoss = 1.0 / h->fixLoss;
-    const int K = 2 + 4 * V;
-
-    const bool sharded = h->world > 1;
-    double* sums = sharded ? h->localSums : h->sumsAll;      // a sharded step reduces locally first, then across ranks
-
-    if (h->timing) WB_CUDA(cudaEventRecord(h->ev[0], s));
-    enqueue_index(h, h->iw);
-    if (h->timing) WB_CUDA(cudaEventRecord(h->ev[1], s));
-    // at least ~8 work units per resident warp, else the tail of the dynamic schedule dominates
-    const int64_t residentWarps = (int64_t)h->repBlocks * wb::repulse_warps(V);
-    const int queriesPerUnit = h->repLayout.segRows / 32 >= 8 * residentWarps ? 32 : (h->repLayout.segRows / 16 >= 8 * residentWarps ? 16 : 8);
-    WB_CUDA(cudaMemsetAsync(h->chunkCounter, 0, sizeof(int), s));
-    WB_CUDA(cudaMemsetAsync(h->forceRep, 0, h->forceRepBytes, s));      // EmbedderState::nextStep zeroes the forces
-    // both box formats are launched; the one QuantParams::halfBoxes does not name returns at once (the choice is made on the device
-    // from this step's layout, the host never waits for it)
-    WB_DISPATCH_V(V, (wb::k_repulse_pairs<V, false><<<h->repBlocks, 32 * wb::repulse_warps(V), wb::repulse_smem_bytes(V, false), s>>>(
-                         h->tree, h->rowPtr, h->col, n, fp, h->forceRep, h->repLayout, queriesPerUnit, h->heavySlot, h->chunkCounter, h->partialsRep)));
-    WB_DISPATCH_V(V, (wb::k_repulse_pairs<V, true><<<h->repBlocks, 32 * wb::repulse_warps(V), wb::repulse_smem_bytes(V, true), s>>>(
-                         h->tree, h->rowPtr, h->col, n, fp, h->forceRep, h->repLayout, queriesPerUnit, h->heavySlot, h->chunkCounter, h->partialsRep)));
-    h->launches += 1;
-    const int repWarps = h->repBlocks * wb::repulse_warps(V);
-    if (h->numHeavy) {
-        WB_DISPATCH_V(V, wb::k_repulse_heavy<V><<<h->numHeavy, 256, 0, s>>>(h->tree, h->rowPtr, h->col, n, fp, h->forceRep, h->repLayout, h->heavyVertex,
-                                                                             h->heavySlot, h->invOrder, h->partialsRep + (size_t)repWarps * 3));
-        h->launches += 1;
-    }
-    if (h->timing) WB_CUDA(cudaEventRecord(h->ev[5], s));
-    if (sharded) {
-        // every rank found the pairs of its own queries and added each pair's term to both rows; a rank needs the totals of the
-        // vertices it owns only: integer reduce-scatter over the ranks, in place (exact, so the result does not depend on the ring)
-        const size_t seg = (size_t)h->rowsPerRank * (4 * V + 2);
-        if (nccl().reduceScatter(h->forceRep, h->forceRep + (size_t)h->rank * seg, seg, ncclInt64, ncclSum, h->comm, s) != ncclSuccess)
-            throw std::runtime_error("ncclReduceScatter (repulsion rows) failed");
-        h->launches += 1;
-    }
-    wb::k_reduce_partials<<<3, 256, 0, s>>>(h->partialsRep, repWarps + h->numHeavy, 3, sums + K);
-    if (h->timing) WB_CUDA(cudaEventRecord(h->ev[2], s));
-    if (h->numHubs) {
-        WB_DISPATCH_V(V, wb::k_attract_hubs<V><<<h->numHubs, 256, 0, s>>>(h->x, h->edgeWs, h->rowPtr, h->col, h->hubVertex, fp, h->hubForce));
-        h->launches += 1;
-    }
-#if WB_ATTRACT_STAGED
-    WB_DISPATCH_V(V, wb::k_attract_staged<V><<<h->forceBlocks, 256, wb::attract_staged_smem<V>(), s>>>(
-                         h->x, h->edgeWs, h->rowPtr, h->col, h->ownBegin, h->ownEnd, h->forceVertsPerBlock, fp, h->forceRep,
-                         h->hubSlot, h->hubForce, h->xNew, h->mom1, h->mom2, h->force, h->partialsForce, h->mtScratch));
-#else
-    WB_DISPATCH_V(V, wb::k_attract_update<V><<<h->forceBlocks, 256, 0, s>>>(
-                         h->x, h->edgeWs, h->rowPtr, h->col, h->ownBegin, h->ownEnd, h->forceVertsPerBlock, fp, h->forceRep,
-                         h->hubSlot, h->hubForce, h->xNew, h->mom1, h->mom2, h->force, h->partialsForce));
-#endif
-    wb::k_reduce_partials<<<K, 256, 0, s>>>(h->partialsForce, h->forceBlocks, K, sums);
-    if (sharded) {   // {lossA, lossR, sum xnew[k], pairs, tests}: all-gather, then every rank adds in rank order
-        if (nccl().allGather(sums, h->gathered, K + 3, ncclDouble, h->comm, s) != ncclSuccess) throw std::runtime_error("ncclAllGather (force sums) failed");
-        wb::k_sum_ranks<<<1, 256, 0, s>>>(h->gathered, h->world, K + 3, h->sumsAll);
-    }
-    if (h->timing) WB_CUDA(cudaEventRecord(h->ev[3], s));
-    WB_DISPATCH_V(V, wb::k_recentre_observe<V><<<h->obsBlocks, 256, 0, s>>>(h->x, h->xNew, n, h->ownBegin, h->ownEnd, h->obsVertsPerBlock, h->dim,
-                                                                              h->sumsAll, h->partialsObs));
-    wb::k_reduce_partials<<<2, 256, 0, s>>>(h->partialsObs, h->obsBlocks, 2, sums + K + 3);
-    if (sharded) {
-        if (nccl().allGather(sums + K + 3, h->gathered, 2, ncclDouble, h->comm, s) != ncclSuccess) throw std::runtime_error("ncclAllGather (observe sums) failed");
-        wb::k_sum_ranks<<<1, 256, 0, s>>>(h->gathered, h->world, 2, h->sumsAll + K + 3);
-        // publish the owners' updated rows: x is replicated again for the next step's index build and gathers
-        const size_t rowFloats = (size_t)h->rowsPerRank * h->rowFloats;
-        float* xf = reinterpret_cast<float*>(h->x);
-        if (nccl().allGather(xf + (size_t)h->rank * rowFloats, xf, rowFloats, ncclFloat, h->comm, s) != ncclSuccess)
-            throw std::runtime_error("ncclAllGather (coordinates) failed");
-        h->launches += 2;
-    }
-    if (h->timing) WB_CUDA(cudaEventRecord(h->ev[4], s));
-    h->launches += 6;
-    WB_CUDA(cudaGetLastError());
-    WB_CUDA(cudaMemcpyAsync(slot.hostSums, h->sumsAll, sizeof(double) * h->sumsTotal, cudaMemcpyDeviceToHost, s));
-    WB_CUDA(cudaEventRecord(slot.done, s));
+    slot.host->dyn.lr = (float)learningRate;
+    slot.host->dyn.invBias1 = (float)(1.0 / (1.0 - std::pow(0.9, h->adamT)));
+    slot.host->dyn.invBias2 = (float)(1.0 / (1.0 - std::pow(0.999, h->adamT)));
+    slot.host->dyn.iteration = (uint32_t)h->iteration;
+    launch_step(h, slot);
     h->pending.push_back(slot);
+    h->nextRebuild = 1;                                       // unknown until this step has been collected
+}
+
+// The pair buffer was too small for a build (StepCtrl::overflow): every kernel of that step and of all later ones returned at once, so
+// the device state is that of the step before.  Grow the buffer and run the pending steps again, with the scalars they were queued with.
+void recover_from_overflow(wb_embedder* h, double needed) {
+    WB_CUDA(cudaStreamSynchronize(h->stream));
+    const double want = std::max(2.0 * needed, 2.0 * (double)h->pairCap);
+    if (want > 1.0e9) throw std::runtime_error("repulsion pair list exceeds 1e9 pairs");
+    allocate_pair_list(h, (unsigned int)want);
+    invalidate_list(h);
+    std::deque<PendingStep> again;
+    again.swap(h->pending);
+    for (const PendingStep& p : again) {
+        launch_step(h, p);
+        h->pending.push_back(p);
+    }
+    h->nextRebuild = 1;
 }
 
 void collect_step(wb_embedder* h, wb_step_stats* out) {
     PendingStep slot = h->pending.front();
+    const int cols = h->cols;
+    for (;;) {
+        WB_CUDA(cudaEventSynchronize(slot.done));
+        if (slot.trivial || slot.host->sums[cols + 8] == 0.0) break;
+        recover_from_overflow(h, slot.host->sums[cols + 9]);
+    }
     h->pending.pop_front();
-    WB_CUDA(cudaEventSynchronize(slot.done));
     wb_step_stats st;
     std::memset(&st, 0, sizeof(st));
     st.iteration = slot.iteration;
     if (!slot.trivial) {
-        const int K = 2 + 4 * h->V;
-        const double* s = slot.hostSums;
+        const double* s = slot.host->sums;
         st.loss_attract = s[0];
         st.loss_repel = s[1];
-        for (int k = 0; k < h->dim; ++k) st.centroid[k] = s[2 + k] / (double)h->n;
-        st.num_repulsion_pairs = s[K];
-        st.num_candidates = s[K + 1];
-        st.num_box_tests = s[K + 2];
-        st.sum_displacement = s[K + 3];
-        st.sum_radius_sq = s[K + 4];
+        st.num_repulsion_pairs = s[2];
+        for (int k = 0; k < h->dim; ++k) st.centroid[k] = s[3 + k] / (double)h->n;
+        st.max_displacement_ratio = s[cols - 1];
+        st.num_listed_pairs = s[cols + 0];
+        st.num_candidates = s[cols + 1];
+        st.num_box_tests = s[cols + 2];
+        st.sum_displacement = s[cols + 3];
+        st.sum_radius_sq = s[cols + 4];
+        st.list_rebuilt = s[cols + 5];
+        st.list_skin = s[cols + 6];
         const double invN = 1.0 / (double)h->n;                              // observeDisplacement (:341-350)
         const double radius = std::sqrt(st.sum_radius_sq * invN);
         st.rel_displacement = radius > 0.0 ? (st.sum_displacement * invN) / radius : 0.0;
+        if (h->pending.empty()) h->nextRebuild = s[cols + 7] != 0.0 ? 1 : 0;
         if (h->timing && h->pending.empty()) {
-            // events: 0 start | 1 index built | 2 repulsion done | 3 attraction+optimizer done | 4 recentred
+            // events: 0 start | 1 index built | 2 pair list built | 3 forces + optimizer done | 4 recentred
             float ms;
             WB_CUDA(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1])); h->phaseMs[0] = ms;
             WB_CUDA(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3])); h->phaseMs[1] = ms;
             WB_CUDA(cudaEventElapsedTime(&ms, h->ev[1], h->ev[2])); h->phaseMs[2] = ms;
-            WB_CUDA(cudaEventElapsedTime(&ms, h->ev[5], h->ev[2])); h->phaseMs[3] = ms;   // slot 3: all-gather of the repulsion rows (0 on one GPU); the optimizer itself is fused into slot 1
+            h->phaseMs[3] = 0.0;
             WB_CUDA(cudaEventElapsedTime(&ms, h->ev[3], h->ev[4])); h->phaseMs[4] = ms;
             WB_CUDA(cudaEventElapsedTime(&ms, h->ev[0], h->ev[4])); h->phaseMs[5] = ms;
             h->havePhase = true;
@@ -699,7 +798,7 @@ extern "C" {
 int wb_abi_version(void) { return WB_ABI_VERSION; }
 
 const char* wb_build_info(void) {
-    return "wembed_b200 sm_100a fp32 | index: morton-sorted 8-ary box hierarchy | cuda " WB_STRINGIFY(CUDART_VERSION);
+    return "wembed_b200 sm_100a fp32 | index: morton-sorted 8-ary box hierarchy | repulsion: pair list + fused pull kernel (cp.async.bulk staged) | cuda " WB_STRINGIFY(CUDART_VERSION);
 }
 
 const char* wb_last_error(void) { return g_lastError.c_str(); }
@@ -714,7 +813,6 @@ void wb_options_default(wb_options* o) {
     std::memset(o, 0, sizeof(*o));
     o->embedding_dimension = 4;          // EmbedderOptions.hpp:32
     o->optimizer = WB_OPT_ADAM;          // :49
-    o->precision = WB_PREC_F32;
     o->device = 0;
     o->keep_forces = 0;
     o->attraction_scale = 1.0;           // :40
@@ -730,11 +828,10 @@ int wb_create(wb_embedder** out, int32_t n, const int32_t* row_ptr, const int32_
     if (!out || !opts || n < 0 || (n > 0 && !row_ptr)) return fail(WB_ERR_INVALID, "wb_create: bad arguments");
     if (opts->embedding_dimension < 1 || opts->embedding_dimension > wb::kMaxDim)
         return fail(WB_ERR_UNSUPPORTED, "wb_create: embedding_dimension must be in 1..32");
-    if (opts->precision != WB_PREC_F32) return fail(WB_ERR_UNSUPPORTED, "wb_create: only WB_PREC_F32 device state is implemented");
     if (wb_device_count() <= opts->device) return fail(WB_ERR_NO_DEVICE, "wb_create: no CUDA device (there is no CPU fallback)");
     static const int32_t zeroRow[1] = {0};
     if (n == 0) row_ptr = zeroRow;
-    // the invariants of Graph (Graph.cpp:87-150): monotone offsets, rows strictly ascending, ids in range, no self loops
+    // the invariants of Graph (Graph.cpp:87-150): monotone offsets, rows strictly ascending, ids in range, no self loops, symmetric
     if (row_ptr[0] != 0) return fail(WB_ERR_INVALID, "wb_create: row_ptr[0] != 0");
     for (int v = 0; v < n; ++v)
         if (row_ptr[v + 1] < row_ptr[v]) return fail(WB_ERR_INVALID, "wb_create: row_ptr not monotone");
@@ -752,7 +849,7 @@ int wb_create(wb_embedder** out, int32_t n, const int32_t* row_ptr, const int32_
             if (!std::binary_search(col + row_ptr[u], col + row_ptr[u + 1], v)) return fail(WB_ERR_INVALID, "wb_create: the CSR is not symmetric");
         }
     }
-    // the walk packs a block / leaf index into 27 bits of a stack entry (kernels.cuh: kRefMask)
+    // the walk packs a block / leaf index into 27 bits of a stack entry (walk.cuh: kRefMask)
     if ((int64_t)n > ((int64_t)1 << 29)) return fail(WB_ERR_UNSUPPORTED, "wb_create: graph too large for the index (n > 2^29)");
     auto* h = new wb_embedder();
     h->n = n;
@@ -779,7 +876,12 @@ int wb_destroy(wb_embedder* h) {
 int wb_set_coordinates(wb_embedder* h, const double* coords) {
     if (h && h->n > 0 && !coords) return fail(WB_ERR_INVALID, "wb_set_coordinates: null buffer");
     if (h && !h->pending.empty()) return fail(WB_ERR_INVALID, "wb_set_coordinates: collect the asynchronous steps first");
-    return guarded(h, [&] { upload_rows(h, coords, h->x); });
+    return guarded(h, [&] {
+        upload_rows(h, coords, h->x);
+        h->quantValid = false;               // the frame on the device belongs to the old layout
+        invalidate_list(h);
+        WB_CUDA(cudaStreamSynchronize(h->stream));
+    });
 }
 
 int wb_set_weights(wb_embedder* h, const double* weights) {
@@ -795,31 +897,11 @@ int wb_set_weights(wb_embedder* h, const double* weights) {
         std::vector<float> iw(n);
         for (int v = 0; v < n; ++v) iw[v] = (float)(1.0 / std::pow(weights[v], 1.0 / (double)h->dim));
         WB_CUDA(cudaMemcpyAsync(h->iw, iw.data(), sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
-        wb::k_edge_weights<<<div_up(n, 256), 256, 0, h->stream>>>(h->rowPtr, h->col, h->iw, n, h->edgeWs);
         WB_CUDA(cudaStreamSynchronize(h->stream));
         const double minW = *std::min_element(h->weights.begin(), h->weights.end());
         const double maxW = *std::max_element(h->weights.begin(), h->weights.end());
         choose_fixed_scales(h, *std::max_element(iw.begin(), iw.end()), *std::min_element(iw.begin(), iw.end()));
-        {   // heavy vertices: weight >= kHeavyWeight x the mean weight (their repulsion is walked by one block each)
-            double mean = 0.0;
-            for (int v = 0; v < n; ++v) mean += weights[v];
-            mean /= (double)n;
-            std::vector<int> heavy, slot(n, -1);
-            for (int v = 0; v < n; ++v)
-                if (weights[v] >= (double)wb::kHeavyWeight * mean) { slot[v] = (int)heavy.size(); heavy.push_back(v); }
-            if (h->heavyVertex) { cudaFree(h->heavyVertex); h->heavyVertex = nullptr; }
-            if (h->heavySlot) { cudaFree(h->heavySlot); h->heavySlot = nullptr; }
-            if (h->partialsRep) { cudaFree(h->partialsRep); h->partialsRep = nullptr; }
-            h->numHeavy = (int)heavy.size();
-            h->partialsRep = dalloc<double>(((size_t)h->repBlocks * 8 + heavy.size()) * 3);
-            if (h->numHeavy) {
-                h->heavyVertex = dalloc<int>(heavy.size());
-                h->heavySlot = dalloc<int>(n);
-                WB_CUDA(cudaMemcpyAsync(h->heavyVertex, heavy.data(), sizeof(int) * heavy.size(), cudaMemcpyHostToDevice, h->stream));
-                WB_CUDA(cudaMemcpyAsync(h->heavySlot, slot.data(), sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
-                WB_CUDA(cudaStreamSynchronize(h->stream));
-            }
-        }
+        rebuild_hub_lists(h);
         // weight classes (WeightedIndex::getDoublingWeightBuckets + updateIndices, WeightedIndex.cpp:51-63, 18-32)
         std::vector<double> buckets;
         if (h->opt.doubling_factor > 1.0)
@@ -828,6 +910,9 @@ int wb_set_weights(wb_embedder* h, const double* weights) {
         classMaxOf.push_back(maxW);
         for (int v = 0; v < n; ++v)
             h->classMax[v] = classMaxOf[std::upper_bound(buckets.begin(), buckets.end(), h->weights[v]) - buckets.begin()];
+        h->quantValid = false;               // halfSigmaLimit may have changed
+        invalidate_list(h);
+        WB_CUDA(cudaStreamSynchronize(h->stream));
     });
 }
 
@@ -849,7 +934,7 @@ int wb_get_forces(wb_embedder* h, double* forces) {
 
 int wb_reset_optimizer(wb_embedder* h) {
     return guarded(h, [&] {
-        const size_t bytes = (size_t)h->n * h->V * sizeof(float4);
+        const size_t bytes = h->rowsAlloc * h->V * sizeof(float4);
         if (bytes) { WB_CUDA(cudaMemsetAsync(h->mom1, 0, bytes, h->stream)); WB_CUDA(cudaMemsetAsync(h->mom2, 0, bytes, h->stream)); }
         WB_CUDA(cudaStreamSynchronize(h->stream));
         h->adamT = 0;
@@ -895,6 +980,19 @@ int wb_get_phase_times(wb_embedder* h, double* ms6) {
     return WB_OK;
 }
 
+int wb_set_list_policy(wb_embedder* h, double skin_max, double reuse_steps) {
+    if (h && !h->pending.empty()) return fail(WB_ERR_INVALID, "wb_set_list_policy: collect the asynchronous steps first");
+    if (h && (!(skin_max >= 0.0) || skin_max > 4.0 || !(reuse_steps >= 1.0))) return fail(WB_ERR_INVALID, "wb_set_list_policy: skin_max in [0, 4], reuse_steps >= 1");
+    return guarded(h, [&] {
+        h->skinMax = (float)skin_max;
+        h->reuseTarget = (float)reuse_steps;
+        choose_fixed_scales(h, h->maxIw, h->minIw);      // halfSigmaLimit depends on the largest list radius
+        h->quantValid = false;
+        invalidate_list(h);
+        WB_CUDA(cudaStreamSynchronize(h->stream));
+    });
+}
+
 int wb_comm_unique_id(char* id128) {
     if (!id128) return fail(WB_ERR_INVALID, "wb_comm_unique_id: null buffer");
     static_assert(sizeof(ncclUniqueId) <= 128, "ncclUniqueId does not fit the ABI buffer");
@@ -908,58 +1006,8 @@ int wb_comm_unique_id(char* id128) {
 
 int wb_comm_init(wb_embedder* h, const char* id128, int32_t rank, int32_t world) {
     if (h && (!id128 || world < 1 || rank < 0 || rank >= world)) return fail(WB_ERR_INVALID, "wb_comm_init: bad arguments");
-    if (h && h->comm) return fail(WB_ERR_INVALID, "wb_comm_init: already initialised");
-    if (h && !h->pending.empty()) return fail(WB_ERR_INVALID, "wb_comm_init: steps in flight");
-    return guarded(h, [&] {
-        if (world == 1) return;
-        ncclUniqueId id;
-        std::memcpy(&id, id128, sizeof(id));
-        if (!nccl().ok) throw std::runtime_error("libnccl.so.2 could not be loaded");
-        if (nccl().commInitRank(&h->comm, world, id, rank) != ncclSuccess) throw std::runtime_error("ncclCommInitRank failed");
-        const int n = h->n, V = h->V;
-        h->world = world;
-        h->rank = rank;
-        h->rowsPerRank = div_up(std::max(n, 1), world);
-        h->ownBegin = std::min(n, rank * h->rowsPerRank);
-        h->ownEnd = std::min(n, h->ownBegin + h->rowsPerRank);
-        // x / xNew need world * rowsPerRank rows so the in-place all-gather has equal chunks
-        const size_t rows = (size_t)n * V, padded = (size_t)h->rowsPerRank * world * V;
-        for (float4** p : {&h->x, &h->xNew}) {
-            float4* q = dalloc<float4>(padded);
-            WB_CUDA(cudaMemsetAsync(q, 0, std::max<size_t>(padded, 1) * sizeof(float4), h->stream));
-            if (rows) WB_CUDA(cudaMemcpyAsync(q, *p, rows * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
-            WB_CUDA(cudaStreamSynchronize(h->stream));
-            cudaFree(*p);
-            *p = q;
-        }
-        // block -> vertex-range assignment over the owned range
-        const int own = std::max(1, h->ownEnd - h->ownBegin), K = 2 + 4 * V;
-        attract_grid(V, own, h->forceBlocks, h->forceVertsPerBlock);
-        h->obsBlocks = std::max(1, std::min(div_up(own, 256), 148 * 8));
-        h->obsVertsPerBlock = std::max(256, div_up(div_up(own, h->obsBlocks), 256) * 256);
-        h->obsBlocks = std::max(1, div_up(own, h->obsVertsPerBlock));
-        // the rounding of vertsPerBlock can make the sharded grids LARGER than the single-GPU ones: size the partial sums again
-        cudaFree(h->partialsForce); h->partialsForce = nullptr;
-        cudaFree(h->partialsObs); h->partialsObs = nullptr;
-        h->partialsForce = dalloc<double>((size_t)h->forceBlocks * K);
-        h->partialsObs = dalloc<double>((size_t)h->obsBlocks * 2);
-#if WB_ATTRACT_STAGED
-        cudaFree(h->mtScratch); h->mtScratch = nullptr;
-        h->mtScratch = dalloc<uint32_t>((size_t)h->forceBlocks * 8 * 624);
-#endif
-        // repulsion rows: blocks of kRepBlockChunks chunks of the sorted order dealt round-robin to the ranks, each rank's rows contiguous
-        const int blocksPerRank = div_up(div_up(div_up(std::max(n, 1), 32), wb::kRepBlockChunks), world);
-        h->repLayout = wb::RepLayout{world, rank, blocksPerRank * wb::kRepBlockChunks * 32};
-        // equal segments of rowsPerRank rows for the in-place reduce-scatter
-        cudaFree(h->forceRep);
-        h->forceRepBytes = (size_t)h->rowsPerRank * world * (4 * V + 2) * sizeof(long long);
-        h->forceRep = dalloc<long long>((size_t)h->rowsPerRank * world * (4 * V + 2));
-        WB_CUDA(cudaMemsetAsync(h->forceRep, 0, h->forceRepBytes, h->stream));
-        h->gathered = dalloc<double>((size_t)world * h->sumsTotal);
-        h->localSums = dalloc<double>(h->sumsTotal);
-        WB_CUDA(cudaMemsetAsync(h->localSums, 0, sizeof(double) * h->sumsTotal, h->stream));
-        WB_CUDA(cudaStreamSynchronize(h->stream));
-    });
+    if (h && world > 1) return fail(WB_ERR_UNSUPPORTED, "wb_comm_init: the sharded step is being rebuilt");
+    return WB_OK;
 }
 
 int wb_reconstruction(wb_embedder* h, int32_t count, const int32_t* nodes, double* out2) {
@@ -1108,7 +1156,8 @@ int wb_query_candidates(wb_embedder* h, int32_t nq, const int32_t* queries, int6
             WB_CUDA(cudaMemcpyAsync(dClassMax, h->classMax.data(), sizeof(double) * n, cudaMemcpyHostToDevice, s));
             WB_CUDA(cudaMemcpyAsync(dQueries, queries, sizeof(int) * nq, cudaMemcpyHostToDevice, s));
             WB_CUDA(cudaMemsetAsync(dCursor, 0, sizeof(int) * nq, s));
-            enqueue_index(h, dIwClass);
+            enqueue_frame(h);
+            enqueue_index(h, dIwClass, 1);
             const float pruneL2 = (float)(h->opt.edge_length * h->opt.edge_length) * (1.0f + wb::kPruneSlack);
             const int blocks = div_up((int64_t)nq * kFan, 256);
             WB_DISPATCH_V(h->V, wb::k_candidates<V><<<blocks, 256, 0, s>>>(h->tree, h->x, dW, dClassMax, h->dim, h->opt.edge_length, pruneL2, h->iw,
@@ -1130,6 +1179,8 @@ int wb_query_candidates(wb_embedder* h, int32_t nq, const int32_t* queries, int6
             }
         } catch (...) { cleanup(); throw; }
         cleanup();
+        invalidate_list(h);                  // the tree now carries the class bounds: the next step builds its own
+        WB_CUDA(cudaStreamSynchronize(h->stream));
     });
     return g != WB_OK ? g : rc;
 }
