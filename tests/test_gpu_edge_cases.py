@@ -210,7 +210,8 @@ def test_pair_list_policy_never_changes_results(device_lib):
         dev.set_list_policy(*policy)
         dev.set_weights(w)
         dev.set_coordinates(x0)
-        stats = [dev.step(lr_exponential(it)) for it in range(1, steps + 1)]
+        # (a faster cooling than the default 0.995, so the layout settles - and lists start to live - within the test's steps)
+        stats = [dev.step(lr_exponential(it, cooling=0.97)) for it in range(1, steps + 1)]
         out.append((dev.coordinates(), [(s["loss_attract"], s["loss_repel"], s["num_repulsion_pairs"], s["sum_displacement"]) for s in stats],
                     sum(1 for s in stats if s["list_rebuilt"] == 0), max(s["list_skin"] for s in stats)))
         dev.close()

@@ -78,7 +78,7 @@ __device__ __forceinline__ void store_block_node(float4* __restrict__ blk, float
 
 // ---------------------------------------------------------------------------------------------
 // Per-dimension min / max / sum / sum of squares of a layout (fixed-order reduction); partial layout [tile][4][kMaxDim] floats.
-// Inside a step these partials come out of k_recentre_observe; this kernel serves the first step after wb_set_coordinates and the
+// Inside a step the moments come out of k_recentre_observe (a sample of the tiles); this kernel serves the first step after wb_set_coordinates and the
 // test hook.  One block per tile of kObsTile vertices, like the recentre pass.
 constexpr int kObsTile = 1024;
 
@@ -139,13 +139,14 @@ struct QuantScratch {
     double sS1[32][kMaxDim], sS2[32][kMaxDim];
     float sSd[kMaxDim];
 };
-__device__ __forceinline__ void quant_from_partials(const float* __restrict__ partial, int numTiles, int n, int dim, int bits,
+// partial layout: [row][4][kMaxDim] floats = {min, max, sum, sum of squares} over `count` vertices in all
+__device__ __forceinline__ void quant_from_partials(const float* __restrict__ partial, int numRows, int count, int dim, int bits,
                                                     float halfSigmaLimit, QuantParams* __restrict__ qp, QuantScratch& sc) {
-    // thread (k, j) = (dimension, slice): slice j folds tiles j, j+32, .. in order; the 32 slices are combined in slice order
+    // thread (k, j) = (dimension, slice): slice j folds rows j, j+32, .. in order; the 32 slices are combined in slice order
     const int k = threadIdx.x & 31, j = threadIdx.x >> 5;
     float mn = 3.0e38f, mx = -3.0e38f; double s1 = 0.0, s2 = 0.0;
     if (k < dim) {
-        for (int b = j; b < numTiles; b += 32) {
+        for (int b = j; b < numRows; b += 32) {
             const float* p = partial + (int64_t)b * 4 * kMaxDim;
             mn = fminf(mn, p[k]); mx = fmaxf(mx, p[kMaxDim + k]); s1 += p[2 * kMaxDim + k]; s2 += p[3 * kMaxDim + k];
         }
@@ -156,8 +157,8 @@ __device__ __forceinline__ void quant_from_partials(const float* __restrict__ pa
         float sd = 0.f;
         if (k < dim) {
             for (int t = 1; t < 32; ++t) { mn = fminf(mn, sc.sMin[t][k]); mx = fmaxf(mx, sc.sMax[t][k]); s1 += sc.sS1[t][k]; s2 += sc.sS2[t][k]; }
-            const double mean = s1 / n;
-            const double var = fmax(0.0, s2 / n - mean * mean);
+            const double mean = s1 / count;
+            const double var = fmax(0.0, s2 / count - mean * mean);
             sd = (float)sqrt(var);
             float lo = fmaxf(mn, (float)mean - 4.f * sd), hi = fminf(mx, (float)mean + 4.f * sd);
             if (!(hi > lo)) hi = lo + 1.f;

@@ -132,68 +132,45 @@ __global__ void __launch_bounds__(256) k_rep_fill(const PairSource src, int* __r
     if (blockIdx.x == 0 && threadIdx.x == 0) { ctrl->listValid = 1; ctrl->dispAccum = 0.f; ctrl->numBuilds += 1; }
 }
 
+// rows of the pair list -> ascending partner order (the list is appended to by whoever finds a pair first, so the order inside a
+// row is arbitrary; sorting it makes the floating-point sum of a vertex' repulsive terms a fixed-order sum).  One thread per vertex,
+// insertion sort in place: rows have a handful of entries.  Hub rows (summed in fixed point by k_hub_rows) are left alone.
+__global__ void __launch_bounds__(256) k_rep_sort_rows(const int* __restrict__ repRowPtr, int* __restrict__ repCol, int ownBegin, int ownEnd,
+                                                       const int* __restrict__ hubSlot, const StepCtrl* __restrict__ ctrl) {
+    if (build_skipped(ctrl, 0)) return;
+    const int v = ownBegin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= ownEnd || (hubSlot && hubSlot[v] >= 0)) return;
+    const int b = repRowPtr[v], e = repRowPtr[v + 1];
+    for (int i = b + 1; i < e; ++i) {
+        const int key = repCol[i];
+        int j = i - 1;
+        while (j >= b && repCol[j] > key) { repCol[j + 1] = repCol[j]; --j; }
+        repCol[j + 1] = key;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Fused step kernel.
 //
 // Layout of the work: G = V (rounded up to a power of two) lanes share one vertex and lane c owns float4 chunk c of every row it
 // touches - its own row, the partners' rows, the force, the Adam moments.  For one partner the G lanes read its row with ONE
 // coalesced access (16 B per lane), add their partial squared distances with log2(G) shuffles and each accumulates its own four
-// force components; nothing has to be reduced at the end and every lane is busy in the optimizer epilogue.  A vertex first walks
-// its CSR row (attractionForce, :140-172), then its row of the repulsion pair list (repellingForce, :174-210).
+// force components; nothing has to be reduced at the end and every lane is busy in the optimizer epilogue.
+// A vertex walks ONE list of partners: its CSR row (attractionForce, :140-172) followed by its row of the repulsion pair list
+// (repellingForce, :174-210).  Both kinds of pair share the arithmetic - distance, pair weight ws = iw_v iw_u, the hinge at
+// dist ws = L - and differ in the side of the hinge they act on and in the sign of the force, so the loop body is branch-free.
+// Terms are fp32; the four terms of a batch are added in fp32 and the batch sum goes into an fp64 accumulator, in list order (rows of
+// the pair list are sorted), so the sums are reproducible bit for bit.
+// Per-pair arithmetic uses the single-instruction special functions (rsqrt.approx, rcp.approx: relative error <= 2^-22, the size of
+// the fp32 rounding of the terms themselves); one-dimensional embeddings take an IEEE path with exact +-1 unit vectors.
 //
-// Memory: a block works through a contiguous run of tiles of 256 / G vertices.  Everything that is read exactly once - the tile's
-// rows of x, m, v, its windows of both row-pointer arrays and of iw, and the entries of both of its CSR rows - is brought to shared
-// memory by bulk asynchronous copies (cp.async.bulk, completion on an mbarrier) one tile ahead of the warps, so the only loads that
-// occupy registers and scoreboard slots are the gathers of partner rows and partner weights (L2-resident: x is 4nd bytes).
-// Sums: attraction in double (terms are fp32); repulsion in 64-bit fixed point, because the pair list is unordered and integer
-// addition does not care.  Every tile emits {lossA, lossR, pairs, sum xNew[k], max displacement ratio} for the tile reducer; tiles
-// are global (tile i = vertices [i VPB, (i+1) VPB)), so the reduced values do not depend on the grid or on the number of GPUs.
+// A block owns a fixed, GLOBAL run of `vertsPerBlock` consecutive vertices (a multiple of the 256 / G vertices of one pass) and emits
+// one row of sums: {lossA, lossR, active pairs, list entries, sum xNew[k]} in double and the largest displacement ratio.
 __host__ __device__ constexpr int attract_lanes(int V) { return V <= 1 ? 1 : (V <= 2 ? 2 : (V <= 4 ? 4 : 8)); }
-__host__ __device__ constexpr int tile_vertices(int V) { return 256 / attract_lanes(V); }
-__host__ __device__ constexpr int tile_sums(int V) { return 3 + 4 * V; }          // + one max column behind them
-constexpr int kStageEdges = 2048;         // CSR entries staged per tile (c3: ~1 280 per 128 vertices); the rest is read from global memory
-constexpr int kStageRep = 1024;           // pair-list entries staged per tile
+__host__ __device__ constexpr int pass_vertices(int V) { return 256 / attract_lanes(V); }
+__host__ __device__ constexpr int block_sums(int V) { return 4 + 4 * V; }         // doubles per block row; + one max column behind them
 constexpr int kHubThreshold = 96;         // CSR rows longer than this are summed by one block each (k_hub_rows)
-
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WB_WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WB_DONE_%=;\n"
-        "bra WB_WAIT_%=;\n"
-        "WB_DONE_%=:\n"
-        "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
-}
-// global -> shared bulk copy (bytes: multiple of 16, both addresses 16-byte aligned); completion is counted on `bar`
-__device__ __forceinline__ void bulk_copy(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)), "l"(src),
-                 "r"(bytes), "r"(smem_addr(bar))
-                 : "memory");
-}
-
-template <int V>
-struct StepStage {                        // one tile of one block
-    static constexpr int G = attract_lanes(V), VPB = 256 / G;
-    float4 x[VPB * V], m[VPB * V], s[VPB * V];
-    int col[kStageEdges + 8];
-    int rcol[kStageRep + 8];
-    int rowPtr[VPB + 8];
-    int rrowPtr[VPB + 8];
-    float iw[VPB + 8];
-};
-template <int V>
-constexpr size_t step_fused_smem() {
-    return 2 * sizeof(StepStage<V>) + 2 * sizeof(uint64_t) + 8 * (4 * V) * sizeof(double) + 2 * 8 * (tile_sums(V) + 1) * sizeof(double);
-}
+constexpr uint32_t kRepFlag = 0x80000000u;
 
 // per-hub record written by k_hub_rows: [attraction force (4V) | lossA | coincident partners | active pairs] as doubles and
 // [repulsion force (4V) | lossR] as fixed-point integers
@@ -210,116 +187,70 @@ __device__ __forceinline__ float chunk_dist2(float4 a, float4 b) {
 }
 
 #ifndef WB_FUSED_MINBLOCKS
-#define WB_FUSED_MINBLOCKS 3
+#define WB_FUSED_MINBLOCKS 4
 #endif
 template <int V>
 __global__ void __launch_bounds__(256, WB_FUSED_MINBLOCKS)
 k_step_fused(const float4* __restrict__ x, const float* __restrict__ iw, const int* __restrict__ rowPtr, const int* __restrict__ col,
-             const int* __restrict__ repRowPtr, const int* __restrict__ repCol, int rangeBegin, int rangeEnd, int tilesPerBlock,
+             const int* __restrict__ repRowPtr, const int* __restrict__ repCol, int rangeBegin, int rangeEnd, int vertsPerBlock,
              const ForceParams fp, const StepDyn* __restrict__ dynp, const int* __restrict__ hubSlot, const double* __restrict__ hubD,
              const long long* __restrict__ hubF, float4* __restrict__ xNew, float4* __restrict__ mom1, float4* __restrict__ mom2,
-             float4* __restrict__ forceOut, double* __restrict__ tilePartials, uint32_t* __restrict__ mtScratch,
-             const StepCtrl* __restrict__ ctrl) {
+             float4* __restrict__ forceOut, double* __restrict__ blockPartials /* [block][K + 1] */, const StepCtrl* __restrict__ ctrl) {
     if (ctrl->overflow != 0) return;
-    using Stage = StepStage<V>;
-    constexpr int G = Stage::G, VPW = 32 / G, VPB = Stage::VPB, K = tile_sums(V), B = 4;
-    extern __shared__ __align__(128) unsigned char smemStep[];
-    Stage* stage = reinterpret_cast<Stage*>(smemStep);                                 // [2]
-    uint64_t* full = reinterpret_cast<uint64_t*>(smemStep + 2 * sizeof(Stage));        // [2]
-    double (*unitBuf)[4 * V] = reinterpret_cast<double (*)[4 * V]>(full + 2);          // [8]
-    double (*redBuf)[8][K + 1] = reinterpret_cast<double (*)[8][K + 1]>(unitBuf + 8);  // [2][8][K + 1], by tile parity
+    constexpr int G = attract_lanes(V), VPW = 32 / G, VPB = 8 * VPW, K = block_sums(V), B = 4;
+    __shared__ uint32_t mtState[8][624];
+    __shared__ double unitBuf[8][VPW][4 * V];
+    __shared__ double redBuf[8][K + 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = lane % G, gi = lane / G;
     const bool chunkLane = c < V;                                  // lanes G > V (V = 3, 5, 6, 7) only take part in the shuffles
-    const int vBegin = rangeBegin + blockIdx.x * tilesPerBlock * VPB;      // rangeBegin is a multiple of VPB
-    const int vEnd = min(rangeEnd, vBegin + tilesPerBlock * VPB);
-    const int passes = vBegin < vEnd ? (vEnd - vBegin + VPB - 1) / VPB : 0;
+    const int vBegin = rangeBegin + blockIdx.x * vertsPerBlock;     // rangeBegin and vertsPerBlock are multiples of VPB
+    const int vEnd = min(rangeEnd, vBegin + vertsPerBlock);
     const float L = fp.edgeLength;
     const StepDyn dyn = *dynp;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4* xc = x + c;
+    double sumLossA = 0.0, sumLossR = 0.0, sumX[4] = {0.0, 0.0, 0.0, 0.0};
+    int sumPairs = 0, sumEntries = 0;
+    float maxMove = 0.f;
 
-    // producer state (thread 0 only): bounds of both CSR rows of the tile to be copied next
-    int nextLo = 0, nextHi = 0, nextRLo = 0, nextRHi = 0;
-    auto passBounds = [&](int p, int& lo, int& hi, int& rlo, int& rhi) {
-        const int v0 = vBegin + p * VPB, v1 = min(v0 + VPB, vEnd);
-        lo = __ldg(rowPtr + v0); hi = __ldg(rowPtr + v1);
-        rlo = repRowPtr[v0]; rhi = repRowPtr[v1];
-    };
-    auto issue = [&](int p, int lo, int hi, int rlo, int rhi) {      // bulk copies of tile p into stage p & 1
-        Stage& st = stage[p & 1];
-        uint64_t* bar = full + (p & 1);
-        const int v0 = vBegin + p * VPB, rows = min(VPB, vEnd - v0);
-        const uint32_t rowBytes = (uint32_t)rows * V * 16u;
-        const uint32_t rpBytes = (uint32_t)((rows + 1 + 3) & ~3) * 4u;          // v0 is a multiple of 4: the windows start aligned
-        const uint32_t iwBytes = (uint32_t)((rows + 3) & ~3) * 4u;
-        const int e0 = lo & ~3, r0 = rlo & ~3;                                  // entries from an aligned entry
-        const uint32_t edgeBytes = (uint32_t)((max(min(hi - e0, kStageEdges + 4), 0) + 3) & ~3) * 4u;
-        const uint32_t repBytes = (uint32_t)((max(min(rhi - r0, kStageRep + 4), 0) + 3) & ~3) * 4u;
-        mbar_expect_tx(bar, 3u * rowBytes + 2u * rpBytes + iwBytes + edgeBytes + repBytes);
-        bulk_copy(st.x, x + (int64_t)v0 * V, rowBytes, bar);
-        bulk_copy(st.m, mom1 + (int64_t)v0 * V, rowBytes, bar);
-        bulk_copy(st.s, mom2 + (int64_t)v0 * V, rowBytes, bar);
-        bulk_copy(st.rowPtr, rowPtr + v0, rpBytes, bar);
-        bulk_copy(st.rrowPtr, repRowPtr + v0, rpBytes, bar);
-        bulk_copy(st.iw, iw + v0, iwBytes, bar);
-        if (edgeBytes) bulk_copy(st.col, col + e0, edgeBytes, bar);
-        if (repBytes) bulk_copy(st.rcol, repCol + r0, repBytes, bar);
-    };
-    if (threadIdx.x == 0) {
-        mbar_init(full, 1);
-        mbar_init(full + 1, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && passes > 0) {
-        int lo, hi, rlo, rhi;
-        passBounds(0, lo, hi, rlo, rhi);
-        issue(0, lo, hi, rlo, rhi);
-        if (passes > 1) passBounds(1, nextLo, nextHi, nextRLo, nextRHi);
-    }
-
-    for (int p = 0; p < passes; ++p) {
-        // every warp has left stage (p + 1) & 1 (barrier at the end of tile p - 1): refill it, and fetch the bounds after that
-        if (threadIdx.x == 0 && p + 1 < passes) {
-            issue(p + 1, nextLo, nextHi, nextRLo, nextRHi);
-            if (p + 2 < passes) passBounds(p + 2, nextLo, nextHi, nextRLo, nextRHi);
-        }
-        mbar_wait(full + (p & 1), (uint32_t)(p >> 1) & 1u);
-        const Stage& st = stage[p & 1];
-        const int v0 = vBegin + p * VPB;
-        const int slot = warp * VPW + gi, v = v0 + slot;
+    for (int vBase = vBegin; vBase < vEnd; vBase += VPB) {
+        const int v = vBase + warp * VPW + gi;
         const bool valid = v < vEnd;
-        const int e0 = st.rowPtr[0] & ~3, r0 = st.rrowPtr[0] & ~3;             // global index of staged entry 0 of either row
+        const int64_t at = (int64_t)v * V + c;
         float4 xv = zero4;
         float iwv = 1.f;
-        double acc[4] = {0.0, 0.0, 0.0, 0.0}, loss = 0.0;
-        int nCoincident = 0, nPairs = 0, e = 0, end = 0, re = 0, rend = 0, hub = -1;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0}, lossA = 0.0, lossR = 0.0;
+        int nCoincident = 0, nPairs = 0, e = 0, lenA = 0, re = 0, total = 0, hub = -1;
         if (valid) {
-            if (chunkLane) xv = st.x[slot * V + c];
-            iwv = st.iw[slot];
+            if (chunkLane) xv = __ldg(x + at);
+            iwv = __ldg(iw + v);
             hub = hubSlot ? __ldg(hubSlot + v) : -1;
-            if (hub < 0) { e = st.rowPtr[slot]; end = st.rowPtr[slot + 1]; re = st.rrowPtr[slot]; rend = st.rrowPtr[slot + 1]; }
+            e = __ldg(rowPtr + v); re = repRowPtr[v];
+            const int lenR = repRowPtr[v + 1] - re;
+            sumEntries += c == 0 ? lenR : 0;
+            if (hub < 0) { lenA = __ldg(rowPtr + v + 1) - e; total = lenA + lenR; }
         }
-        // ---- attraction over the CSR row (neighbours ascending, B rows in flight).  All G lanes of a vertex walk the same entries;
-        // the groups of a warp have different row lengths and the shuffles need every lane, so the warp iterates to the longest row.
-        int len = end - e;
+        // all G lanes of a vertex walk the same entries; the groups of a warp have different list lengths and the shuffles need every
+        // lane, so the warp iterates to the longest list of its groups (hub rows are pre-summed)
+        int len = total;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
-        for (int i = 0; i < len; i += B) {
-            bool has[B];
+        for (int i = 0; i < len; i += B) {                         // B partners in flight
+            bool has[B], isRep[B];
             int u[B];
-            float wsE[B], dd[B];
+            float ws[B], dd[B];
             float4 r[B];
 #pragma unroll
             for (int j = 0; j < B; ++j) {
-                const int idx = e + i + j, at = idx - e0;
-                has[j] = idx < end;
-                u[j] = has[j] ? (at < kStageEdges + 4 ? st.col[at] : __ldg(col + idx)) : 0;
+                const int idx = i + j;
+                has[j] = idx < total;
+                isRep[j] = idx >= lenA;
+                u[j] = has[j] ? (isRep[j] ? repCol[re + idx - lenA] : __ldg(col + e + idx)) : 0;
             }
 #pragma unroll
             for (int j = 0; j < B; ++j) r[j] = (has[j] && chunkLane) ? __ldg(xc + (int64_t)u[j] * V) : xv;
 #pragma unroll
-            for (int j = 0; j < B; ++j) wsE[j] = has[j] ? iwv * __ldg(iw + u[j]) : 0.f;
+            for (int j = 0; j < B; ++j) ws[j] = has[j] ? iwv * __ldg(iw + u[j]) : 0.f;
 #pragma unroll
             for (int j = 0; j < B; ++j) dd[j] = chunkLane ? chunk_dist2(r[j], xv) : 0.f;
 #pragma unroll
@@ -327,118 +258,80 @@ k_step_fused(const float4* __restrict__ x, const float* __restrict__ iw, const i
 #pragma unroll
                 for (int j = 0; j < B; ++j) dd[j] += __shfl_xor_sync(0xffffffffu, dd[j], o);
             }
-            // the terms of a batch are added in fp32 (their sum carries the same relative error as each term), the batch
-            // sum goes into the double accumulator: one conversion + one DADD per component per batch
-            float bx = 0.f, by = 0.f, bz = 0.f, bw = 0.f, bl = 0.f;
+            float bx = 0.f, by = 0.f, bz = 0.f, bw = 0.f, blA = 0.f, blR = 0.f;
             if (V > 1 || fp.dim > 1) {
-                // Branch-free pair arithmetic with single-instruction rsqrt / rcp (relative error <= 2^-22, the size of the fp32
-                // rounding of the terms themselves).  Squared distances below FLT_MIN are neither coincident (that is d2 == 0
-                // exactly, as with sqrtf) nor can they exceed the edge length: they contribute nothing and stay away from the
-                // flush-to-zero rsqrt.
 #pragma unroll
                 for (int j = 0; j < B; ++j) {
-                    const float inv = rsqrt_approx(dd[j]);
+                    // squared distances below FLT_MIN (dist < 1.1e-19) stay away from the flush-to-zero rsqrt: such a pair is inside
+                    // the hinge for certain; its direction is kept and dist is taken as d2 / 1.1e-19 (a repulsive pair that close but
+                    // not coincident - coordinates would have to be ~1e-19 themselves - gets a force scaled down accordingly)
+                    const float inv = rsqrt_approx(fmaxf(dd[j], kFltMin));
                     const float dist = dd[j] * inv;
-                    nCoincident += (int)(has[j] && dd[j] == 0.f);                        // :150-155, resolved below
-                    const bool act = has[j] && dd[j] >= kFltMin && dist * wsE[j] > L;     // :163-168
-                    const float sc = act ? fp.attractionScale * wsE[j] * inv : 0.f;
+                    const bool inside = dist * ws[j] <= L;                              // the hinge (:163, :196)
+                    nCoincident += (int)(has[j] && dd[j] == 0.f);                       // :150-155, :183-188, resolved below
+                    nPairs += (int)(has[j] && isRep[j] && inside);
+                    const bool act = has[j] && dd[j] > 0.f && (isRep[j] ? inside : !inside);
+                    const float sc = act ? (isRep[j] ? -fp.repulsionScale : fp.attractionScale) * ws[j] * inv : 0.f;
                     bx = fmaf(sc, r[j].x - xv.x, bx); by = fmaf(sc, r[j].y - xv.y, by);
                     bz = fmaf(sc, r[j].z - xv.z, bz); bw = fmaf(sc, r[j].w - xv.w, bw);
-                    bl += act ? fmaf(-L, rcp_approx(wsE[j]), dist) : 0.f;
+                    const float over = fmaf(-L, rcp_approx(ws[j]), dist);               // dist - L / ws
+                    blA += (act && !isRep[j]) ? over : 0.f;
+                    blR += (act && isRep[j]) ? -over : 0.f;
                 }
             } else {                                            // one dimension: exact +-1 unit vectors (VectorOperations.hpp:19-24), IEEE arithmetic
 #pragma unroll
                 for (int j = 0; j < B; ++j) {
                     if (!has[j]) continue;
                     const float dist = sqrtf(dd[j]);
-                    if (dist <= 0.f) { ++nCoincident; continue; }
-                    if (dist * wsE[j] > L) {
-                        bx += copysignf(fp.attractionScale * wsE[j], r[j].x - xv.x);
-                        bl += dist - L / wsE[j];
+                    if (dist <= 0.f) { ++nCoincident; nPairs += (int)isRep[j]; continue; }
+                    const bool inside = dist * ws[j] <= L;
+                    if (isRep[j]) {
+                        if (!inside) continue;
+                        ++nPairs;
+                        bx += copysignf(fp.repulsionScale * ws[j], xv.x - r[j].x);
+                        blR += L / ws[j] - dist;
+                    } else if (!inside) {
+                        bx += copysignf(fp.attractionScale * ws[j], r[j].x - xv.x);
+                        blA += dist - L / ws[j];
                     }
                 }
             }
             acc[0] += (double)bx; acc[1] += (double)by; acc[2] += (double)bz; acc[3] += (double)bw;
-            loss += (double)bl;
-        }
-        // ---- repulsion over the vertex' row of the pair list (unordered; exact predicate of repellingForce, :183-201)
-        long long rep[4] = {0ll, 0ll, 0ll, 0ll}, lossR = 0ll;
-        int rlen = rend - re;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) rlen = max(rlen, __shfl_xor_sync(0xffffffffu, rlen, o));
-        for (int i = 0; i < rlen; i += 2) {
-            bool has[2];
-            int u[2];
-            float iwu[2], dd[2];
-            float4 r[2];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int idx = re + i + j, at = idx - r0;
-                has[j] = idx < rend;
-                u[j] = has[j] ? (at < kStageRep + 4 ? st.rcol[at] : repCol[idx]) : 0;
-            }
-#pragma unroll
-            for (int j = 0; j < 2; ++j) r[j] = (has[j] && chunkLane) ? __ldg(xc + (int64_t)u[j] * V) : xv;
-#pragma unroll
-            for (int j = 0; j < 2; ++j) iwu[j] = has[j] ? __ldg(iw + u[j]) : 1.f;
-#pragma unroll
-            for (int j = 0; j < 2; ++j) dd[j] = chunkLane ? chunk_dist2(xv, r[j]) : 0.f;
-#pragma unroll
-            for (int o = G / 2; o > 0; o >>= 1) {
-#pragma unroll
-                for (int j = 0; j < 2; ++j) dd[j] += __shfl_xor_sync(0xffffffffu, dd[j], o);
-            }
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                if (!has[j]) continue;
-                const float dist = sqrtf(dd[j]), ws = iwv * iwu[j];
-                if (dist <= 0.f) { ++nCoincident; ++nPairs; continue; }          // :183-188
-                if (!(dist * ws <= L)) continue;                                 // :196 (listed with a skin: most entries end here)
-                ++nPairs;
-                if (fp.dim == 1) {
-                    rep[0] += to_fixed(copysignf(fp.repulsionScale * ws, xv.x - r[j].x), fp.fixForce);
-                } else {
-                    const float sc = fp.repulsionScale * ws / dist;
-                    rep[0] += to_fixed(sc * (xv.x - r[j].x), fp.fixForce); rep[1] += to_fixed(sc * (xv.y - r[j].y), fp.fixForce);
-                    rep[2] += to_fixed(sc * (xv.z - r[j].z), fp.fixForce); rep[3] += to_fixed(sc * (xv.w - r[j].w), fp.fixForce);
-                }
-                lossR += to_fixed(L / ws - dist, fp.fixLoss);
-            }
+            lossA += (double)blA; lossR += (double)blR;
         }
         if (valid && hub >= 0) {                               // hub rows were summed by k_hub_rows
             const double* hd = hubD + (int64_t)hub * hub_doubles(V);
             const long long* hf = hubF + (int64_t)hub * hub_fixed(V);
             if (chunkLane) {
-                acc[0] = hd[4 * c]; acc[1] = hd[4 * c + 1]; acc[2] = hd[4 * c + 2]; acc[3] = hd[4 * c + 3];
-                rep[0] = hf[4 * c]; rep[1] = hf[4 * c + 1]; rep[2] = hf[4 * c + 2]; rep[3] = hf[4 * c + 3];
+                acc[0] = hd[4 * c] + (double)hf[4 * c] * fp.invFixForce; acc[1] = hd[4 * c + 1] + (double)hf[4 * c + 1] * fp.invFixForce;
+                acc[2] = hd[4 * c + 2] + (double)hf[4 * c + 2] * fp.invFixForce; acc[3] = hd[4 * c + 3] + (double)hf[4 * c + 3] * fp.invFixForce;
             }
-            loss = hd[4 * V];
+            lossA = hd[4 * V];
             nCoincident = (int)hd[4 * V + 1];
             nPairs = (int)hd[4 * V + 2];
-            lossR = hf[4 * V];
+            lossR = (double)hf[4 * V] * fp.invFixLoss;
         }
-        // coincident partners: every one of them adds the same unit vector (generator re-created per pair, :150-155, :183-188)
+        // coincident partners: every one of them adds the same unit vector (generator re-created per pair, :150-155, :183-188).
+        // The generator state (624 words) lives in per-warp shared memory; the rare vertices that need it take turns.
         uint32_t todo = __ballot_sync(0xffffffffu, nCoincident > 0 && c == 0);
-        while (todo) {                                          // one vertex at a time; the generator state lives in global scratch
-            const int l = __ffs(todo) - 1;
-            todo &= todo - 1u;
-            if (lane == l)
-                random_unit_vector(mtScratch + ((size_t)blockIdx.x * 8 + warp) * 624, fp.seed, (uint32_t)v, dyn.iteration, fp.dim, unitBuf[warp]);
-            __syncwarp();
-            if (lane / G == l / G && chunkLane) {
+        if (todo) {
+            uint32_t rest = todo;
+            while (rest) {
+                const int l = __ffs(rest) - 1;
+                rest &= rest - 1u;
+                if (lane == l) random_unit_vector(mtState[warp], fp.seed, (uint32_t)v, dyn.iteration, fp.dim, unitBuf[warp][gi]);
+                __syncwarp();
+            }
+            if (nCoincident > 0 && chunkLane) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                    if (4 * c + i < fp.dim) acc[i] += nCoincident * unitBuf[warp][4 * c + i];
+                    if (4 * c + i < fp.dim) acc[i] += nCoincident * unitBuf[warp][gi][4 * c + i];
             }
             __syncwarp();
         }
-        // ---- optimizer epilogue and the tile's sums
-        double sumX[4] = {0.0, 0.0, 0.0, 0.0}, sumLossA = 0.0, sumLossR = 0.0, sumPairs = 0.0;
-        float maxMove = 0.f, disp2 = 0.f;
+        float disp2 = 0.f;
         if (valid && chunkLane) {
-            const int64_t at = (int64_t)v * V + c;
-            float4 f = make_float4((float)(acc[0] + (double)rep[0] * fp.invFixForce), (float)(acc[1] + (double)rep[1] * fp.invFixForce),
-                                   (float)(acc[2] + (double)rep[2] * fp.invFixForce), (float)(acc[3] + (double)rep[3] * fp.invFixForce));
+            float4 f = make_float4((float)acc[0], (float)acc[1], (float)acc[2], (float)acc[3]);
             if (fp.centreScale != 0.f) {                   // :296-301
                 f.x = fmaf(-fp.centreScale, xv.x, f.x); f.y = fmaf(-fp.centreScale, xv.y, f.y);
                 f.z = fmaf(-fp.centreScale, xv.z, f.z); f.w = fmaf(-fp.centreScale, xv.w, f.w);
@@ -446,7 +339,7 @@ k_step_fused(const float4* __restrict__ x, const float* __restrict__ iw, const i
             if (fp.keepForces) forceOut[at] = f;
             float4 xn;
             if (fp.optimizer == 1) {
-                const float4 m = st.m[slot * V + c], s = st.s[slot * V + c];
+                const float4 m = mom1[at], s = mom2[at];
                 const float fe[4] = {f.x, f.y, f.z, f.w};
                 float me[4] = {m.x, m.y, m.z, m.w}, se[4] = {s.x, s.y, s.z, s.w};
                 float xe[4] = {xv.x, xv.y, xv.z, xv.w};
@@ -468,40 +361,43 @@ k_step_fused(const float4* __restrict__ x, const float* __restrict__ iw, const i
                 xn.w = xv.w + fminf(fmaxf(f.w, -cap), cap) * dyn.lr;
             }
             xNew[at] = xn;
-            sumX[0] = (double)xn.x; sumX[1] = (double)xn.y; sumX[2] = (double)xn.z; sumX[3] = (double)xn.w;
+            sumX[0] += (double)xn.x; sumX[1] += (double)xn.y; sumX[2] += (double)xn.z; sumX[3] += (double)xn.w;
             disp2 = chunk_dist2(xn, xv);
         }
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) disp2 += __shfl_xor_sync(0xffffffffu, disp2, o);
         if (valid && c == 0) {
-            sumLossA = loss;
-            sumLossR = (double)lossR * fp.invFixLoss;
-            sumPairs = (double)nPairs;
+            sumLossA += lossA;
+            sumLossR += lossR;
+            sumPairs += nPairs;
             // how far the vertex moved, in units of its smallest possible interaction radius (StepCtrl)
-            maxMove = sqrtf(disp2) * iwv * fp.dispScale;
+            maxMove = fmaxf(maxMove, sqrtf(disp2) * iwv * fp.dispScale);
         }
-        // fixed-order tile reduction: lanes that own the same chunk add up (xor offsets G, 2G, ..), then the 8 warps in order
+    }
+    // fixed-order block reduction: lanes that own the same chunk combine (xor offsets G, 2G, ..), then the 8 warps in order
+    double dPairs = (double)sumPairs, dEntries = (double)sumEntries;
 #pragma unroll
-        for (int o = G; o < 32; o <<= 1) {
-            sumLossA += __shfl_xor_sync(0xffffffffu, sumLossA, o);
-            sumLossR += __shfl_xor_sync(0xffffffffu, sumLossR, o);
-            sumPairs += __shfl_xor_sync(0xffffffffu, sumPairs, o);
-            maxMove = fmaxf(maxMove, __shfl_xor_sync(0xffffffffu, maxMove, o));
+    for (int o = G; o < 32; o <<= 1) {
+        sumLossA += __shfl_xor_sync(0xffffffffu, sumLossA, o);
+        sumLossR += __shfl_xor_sync(0xffffffffu, sumLossR, o);
+        dPairs += __shfl_xor_sync(0xffffffffu, dPairs, o);
+        dEntries += __shfl_xor_sync(0xffffffffu, dEntries, o);
+        maxMove = fmaxf(maxMove, __shfl_xor_sync(0xffffffffu, maxMove, o));
 #pragma unroll
-            for (int i = 0; i < 4; ++i) sumX[i] += __shfl_xor_sync(0xffffffffu, sumX[i], o);
-        }
-        if (lane == 0) { redBuf[p & 1][warp][0] = sumLossA; redBuf[p & 1][warp][1] = sumLossR; redBuf[p & 1][warp][2] = sumPairs; redBuf[p & 1][warp][K] = (double)maxMove; }
-        if (lane < G && chunkLane) {
+        for (int i = 0; i < 4; ++i) sumX[i] += __shfl_xor_sync(0xffffffffu, sumX[i], o);
+    }
+    if (lane == 0) { redBuf[warp][0] = sumLossA; redBuf[warp][1] = sumLossR; redBuf[warp][2] = dPairs; redBuf[warp][3] = dEntries; redBuf[warp][K] = (double)maxMove; }
+    if (lane < G && chunkLane) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) redBuf[p & 1][warp][3 + 4 * c + i] = sumX[i];
-        }
-        __syncthreads();                                        // stage p & 1 may be refilled (tile p + 2) from here on
-        if (threadIdx.x <= K) {
-            double sacc = redBuf[p & 1][0][threadIdx.x];
-            if (threadIdx.x < K) { for (int w = 1; w < 8; ++w) sacc += redBuf[p & 1][w][threadIdx.x]; }
-            else { for (int w = 1; w < 8; ++w) sacc = fmax(sacc, redBuf[p & 1][w][threadIdx.x]); }
-            tilePartials[(int64_t)(v0 / VPB) * (K + 1) + threadIdx.x] = sacc;
-        }
+        for (int i = 0; i < 4; ++i) redBuf[warp][4 + 4 * c + i] = sumX[i];
+    }
+    __syncthreads();
+    const int blockRow = vBegin / vertsPerBlock;                    // GLOBAL row: block ranges tile the vertex range from vertex 0
+    if (threadIdx.x <= K) {
+        double sacc = redBuf[0][threadIdx.x];
+        if (threadIdx.x < K) { for (int w = 1; w < 8; ++w) sacc += redBuf[w][threadIdx.x]; }
+        else { for (int w = 1; w < 8; ++w) sacc = fmax(sacc, redBuf[w][threadIdx.x]); }
+        blockPartials[(int64_t)blockRow * (K + 1) + threadIdx.x] = sacc;
     }
 }
 
@@ -586,34 +482,18 @@ __global__ void __launch_bounds__(256) k_hub_rows(const float4* __restrict__ x, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Deterministic reduction of the tile sums (util::deterministicSum's role, ParallelReduce.hpp:18-37): tiles are grouped 64 by 64 in
-// GLOBAL tile order; a group is summed sequentially, thread t of the reducing block adds the groups t, t + 256, .. in order, and
-// the 256 thread sums are combined by a fixed tree.  Neither the grid of the step kernel nor the number of GPUs (whole groups per
-// rank, the group sums are exchanged) can change a bit of the result.  Column K (the last) is a maximum.
-constexpr int kTileGroup = 64;
-__global__ void __launch_bounds__(256) k_reduce_tile_groups(const double* __restrict__ tilePartials, int tileBegin, int tileEnd, int cols,
-                                                            double* __restrict__ groupSums, const StepCtrl* __restrict__ ctrl) {
-    if (ctrl->overflow != 0) return;
-    // one thread per (group, column)
-    const int numGroups = (tileEnd - tileBegin + kTileGroup - 1) / kTileGroup;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)numGroups * cols) return;
-    const int g = (int)(i / cols), k = (int)(i % cols);
-    const int t0 = tileBegin + g * kTileGroup, t1 = min(tileEnd, t0 + kTileGroup);
-    double s = tilePartials[(int64_t)t0 * cols + k];
-    if (k == cols - 1) { for (int t = t0 + 1; t < t1; ++t) s = fmax(s, tilePartials[(int64_t)t * cols + k]); }
-    else { for (int t = t0 + 1; t < t1; ++t) s += tilePartials[(int64_t)t * cols + k]; }
-    groupSums[(int64_t)(tileBegin / kTileGroup + g) * cols + k] = s;
-}
-// block k reduces column k of the group sums
-__global__ void __launch_bounds__(256) k_reduce_groups(const double* __restrict__ groupSums, int numGroups, int cols, double* __restrict__ out,
-                                                       const StepCtrl* __restrict__ ctrl) {
+// Deterministic reduction of the per-block sums (util::deterministicSum's role, ParallelReduce.hpp:18-37): block rows are GLOBAL
+// (row i = vertices [i S, (i + 1) S), S fixed by n alone), thread t of the reducing block adds the rows t, t + 256, .. in order and
+// the 256 thread sums are combined by a fixed tree.  Neither scheduling nor the number of GPUs (whole rows per rank; the rows are
+// exchanged) can change a bit of the result.  Block k reduces column k; the last column is a maximum.
+__global__ void __launch_bounds__(256) k_reduce_rows(const double* __restrict__ rowSums, int numRows, int cols, double* __restrict__ out,
+                                                     const StepCtrl* __restrict__ ctrl) {
     if (ctrl->overflow != 0) return;
     __shared__ double sm[256];
     const int k = blockIdx.x;
     const bool isMax = k == cols - 1;
     double s = 0.0;
-    for (int g = threadIdx.x; g < numGroups; g += 256) { const double v = groupSums[(int64_t)g * cols + k]; s = isMax ? fmax(s, v) : s + v; }
+    for (int g = threadIdx.x; g < numRows; g += 256) { const double v = rowSums[(int64_t)g * cols + k]; s = isMax ? fmax(s, v) : s + v; }
     sm[threadIdx.x] = s;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
@@ -624,27 +504,26 @@ __global__ void __launch_bounds__(256) k_reduce_groups(const double* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
-// applyGravityCentre + observeDisplacement (WembedEmbedder.cpp:303-352): x = xnew - centroid, the sums of ||x - xprev|| and ||x||^2,
-// and - because this pass streams the final layout anyway - the per-dimension moments the next index build takes its quantisation
-// frame from.  One block per tile of kObsTile vertices (global tiles: the partial sums do not depend on the grid or on the number
-// of GPUs).  forceSums = output of k_reduce_groups ({lossA, lossR, pairs, sum xnew[k], max displacement}).
+// applyGravityCentre + observeDisplacement (WembedEmbedder.cpp:303-352): x = xnew - centroid and the sums of ||x - xprev|| and
+// ||x||^2.  One block per tile of kObsTile vertices (global tiles: the partial sums do not depend on the grid or on the number of
+// GPUs).  forceSums = output of k_reduce_rows ({lossA, lossR, pairs, list entries, sum xnew[k], max displacement}).
+// Every momentStride-th tile also takes the per-dimension moments of the final layout: the next index build derives its
+// quantisation frame from that sample (only locality depends on the frame, and a fixed 1-in-8 sample of the tiles pins it as well as
+// all of them while costing an eighth).
 template <int V>
 __global__ void __launch_bounds__(256) k_recentre_observe(float4* __restrict__ x, const float4* __restrict__ xNew, int n, int tileBegin, int dim,
                                                           const double* __restrict__ forceSums, double* __restrict__ obsPartials /* [tile][2] */,
-                                                          float* __restrict__ momentPartials /* [tile][4][kMaxDim] */,
+                                                          int momentStride, float* __restrict__ momentPartials /* [tile / stride][4][kMaxDim] */,
                                                           const StepCtrl* __restrict__ ctrl) {
     if (ctrl->overflow != 0) return;
     __shared__ double redBuf[8 * 2];
     __shared__ float smMom[8][4][4 * V];
     float cen[4 * V];
 #pragma unroll
-    for (int k = 0; k < 4 * V; ++k) cen[k] = (k < dim) ? (float)(forceSums[3 + k] / (double)n) : 0.f;
+    for (int k = 0; k < 4 * V; ++k) cen[k] = (k < dim) ? (float)(forceSums[4 + k] / (double)n) : 0.f;
     const int tile = tileBegin + blockIdx.x;
     const int vEnd = min(n, (tile + 1) * kObsTile);
     double sums[2] = {0.0, 0.0};
-    float mn[4 * V], mx[4 * V], s1[4 * V], s2[4 * V];
-#pragma unroll
-    for (int k = 0; k < 4 * V; ++k) { mn[k] = 3.0e38f; mx[k] = -3.0e38f; s1[k] = 0.f; s2[k] = 0.f; }
     for (int v = tile * kObsTile + threadIdx.x; v < vEnd; v += 256) {
         float disp2 = 0.f, rad2 = 0.f;
 #pragma unroll
@@ -656,7 +535,21 @@ __global__ void __launch_bounds__(256) k_recentre_observe(float4* __restrict__ x
             disp2 = fmaf(r.x - o.x, r.x - o.x, disp2); disp2 = fmaf(r.y - o.y, r.y - o.y, disp2);
             disp2 = fmaf(r.z - o.z, r.z - o.z, disp2); disp2 = fmaf(r.w - o.w, r.w - o.w, disp2);
             rad2 = fmaf(r.x, r.x, rad2); rad2 = fmaf(r.y, r.y, rad2); rad2 = fmaf(r.z, r.z, rad2); rad2 = fmaf(r.w, r.w, rad2);
-            const float e[4] = {r.x, r.y, r.z, r.w};
+        }
+        sums[0] += (double)sqrtf(disp2);
+        sums[1] += (double)rad2;
+    }
+    block_sum<2, 256>(sums, redBuf, obsPartials + (int64_t)tile * 2);
+    if (tile % momentStride != 0) return;
+    // second pass over the tile's (L1 / L2-resident) rows for the moments
+    float mn[4 * V], mx[4 * V], s1[4 * V], s2[4 * V];
+#pragma unroll
+    for (int k = 0; k < 4 * V; ++k) { mn[k] = 3.0e38f; mx[k] = -3.0e38f; s1[k] = 0.f; s2[k] = 0.f; }
+    for (int v = tile * kObsTile + threadIdx.x; v < vEnd; v += 256) {
+#pragma unroll
+        for (int c = 0; c < V; ++c) {
+            const float4 p = x[(int64_t)v * V + c];
+            const float e[4] = {p.x, p.y, p.z, p.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int k = 4 * c + i;
@@ -664,26 +557,23 @@ __global__ void __launch_bounds__(256) k_recentre_observe(float4* __restrict__ x
                 s1[k] += e[i]; s2[k] = fmaf(e[i], e[i], s2[k]);
             }
         }
-        sums[0] += (double)sqrtf(disp2);
-        sums[1] += (double)rad2;
     }
-    block_sum<2, 256>(sums, redBuf, obsPartials + (int64_t)tile * 2);
-    moments_block_reduce<V>(mn, mx, s1, s2, smMom, momentPartials + (int64_t)tile * 4 * kMaxDim);
+    moments_block_reduce<V>(mn, mx, s1, s2, smMom, momentPartials + (int64_t)(tile / momentStride) * 4 * kMaxDim);
 }
 
 // ---------------------------------------------------------------------------------------------
 // Last kernel of a step (one block): the observation sums, the quantisation frame of the next index build, the device's decision
 // about the next step (rebuild the pair list or reuse it, and with which skin) and the record the host reads back.
 //
-// stats layout (doubles): [0] lossA [1] lossR [2] active pairs [3 .. 3+4V) sum xnew [K] max displacement ratio of this step |
-//   then kTailStats values: listed pairs, point tests, box tests, sum displacement, sum radius^2, rebuilt (this step), skin of the
-//   current list, next step rebuilds, overflow, pairs needed
+// stats layout (doubles): [0] lossA [1] lossR [2] active pairs [3] list entries [4 .. 4+4V) sum xnew [K] max displacement ratio of this
+//   step | then kTailStats values: listed pairs, point tests, box tests, sum displacement, sum radius^2, rebuilt (this step), skin of
+//   the current list, next step rebuilds, overflow, pairs needed
 constexpr int kTailStats = 10;
 struct TailPolicy { float edgeLength; float halfSigmaLimit; int dim; int mortonBits; };
 
 __global__ void __launch_bounds__(1024) k_step_tail(const double* __restrict__ forceSums, int cols, const double* __restrict__ obsPartials, int numObsTiles,
-                                                    const float* __restrict__ momentPartials, int n, const double* __restrict__ walkPartials, int walkRows,
-                                                    const unsigned int* __restrict__ pairCounts, int world, const TailPolicy pol, QuantParams* __restrict__ qp,
+                                                    const float* __restrict__ momentPartials, int numMomentTiles, int momentCount, int n,
+                                                    const double* __restrict__ walkPartials, int walkRows, const TailPolicy pol, QuantParams* __restrict__ qp,
                                                     StepCtrl* ctrl, double* __restrict__ stats) {
     __shared__ QuantScratch sc;
     __shared__ double sm[1024];
@@ -708,16 +598,16 @@ __global__ void __launch_bounds__(1024) k_step_tail(const double* __restrict__ f
         if (threadIdx.x == 0) res[col] = sm[0];
         __syncthreads();
     }
-    quant_from_partials(momentPartials, numObsTiles, n, pol.dim, pol.mortonBits, pol.halfSigmaLimit, qp, sc);
+    // frame of the final layout, from the sample of tiles the recentre pass took moments of (momentCount vertices)
+    quant_from_partials(momentPartials, numMomentTiles, momentCount, pol.dim, pol.mortonBits, pol.halfSigmaLimit, qp, sc);
     if (threadIdx.x == 0) {
         const float r = (float)forceSums[cols - 1];                // largest displacement of this step, in smallest interaction radii
         float accum = rebuilt ? r : ctrl->dispAccum + r;           // a list built this step saw the positions BEFORE the step's move
         const float skin = ctrl->skin;
         const bool reuse = ctrl->listValid != 0 && skin > 0.f && accum <= 0.5f * skin * 0.999f && isfinite(accum);
-        unsigned int listed = 0u;
-        for (int s = 0; s < world; ++s) listed += pairCounts[s];
+        const double listed = 0.5 * forceSums[3];                  // every listed pair is an entry in both vertices' rows
         for (int k = 0; k < cols; ++k) stats[k] = forceSums[k];
-        stats[cols + 0] = (double)listed;
+        stats[cols + 0] = listed;
         stats[cols + 1] = res[3]; stats[cols + 2] = res[4];
         stats[cols + 3] = res[0]; stats[cols + 4] = res[1];
         stats[cols + 5] = rebuilt ? 1.0 : 0.0;
@@ -731,11 +621,13 @@ __global__ void __launch_bounds__(1024) k_step_tail(const double* __restrict__ f
             // one step would outrun the largest allowed skin (then inflating the radius only costs)
             // (a build whose inflated radius listed more pairs than the budget lowers the ceiling; it recovers slowly)
             float cap = ctrl->skinCap;
-            if (rebuilt && skin > 0.f && listed > ctrl->pairBudget) cap = fmaxf(0.02f, 0.75f * skin);
+            if (rebuilt && skin > 0.f && listed > (double)ctrl->pairBudget) cap = fmaxf(0.02f, 0.75f * skin);
             else cap = fminf(ctrl->skinMax, cap * 1.1f);
             ctrl->skinCap = cap;
+            // a skin pays only if the list then lives for reuseTarget steps at the current pace: the search with an inflated radius costs
+            // ~(1 + skin)^2 searches (measured at c3: 3.9 x at skin 1) and every listed pair is evaluated every step
             float s = 0.f;
-            if (cap > 0.f && isfinite(r) && 2.1f * r <= cap) s = fminf(cap, fmaxf(2.2f * ctrl->reuseTarget * r, 0.05f));
+            if (cap > 0.f && isfinite(r) && 2.2f * ctrl->reuseTarget * r <= cap) s = fminf(cap, fmaxf(2.2f * ctrl->reuseTarget * r, 0.05f));
             const float Ls = pol.edgeLength * (1.f + s);
             ctrl->skin = s;
             ctrl->listL2 = Ls * Ls * (1.f + kPruneSlack);

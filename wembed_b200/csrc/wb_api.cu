@@ -143,11 +143,12 @@ struct wb_embedder {
     wb::TreeView tree{};
     wb::TreePlanes planes{};
 
-    // reductions (all over GLOBAL tiles, see step.cuh)
-    int tileVerts = 0, numTiles = 0, numGroups = 0, cols = 0;       // fused-kernel tiles, groups of kTileGroup tiles, sums per tile
-    int fusedBlocks = 0, tilesPerBlock = 0, repBlocks = 0, numObsTiles = 0;
-    double *tilePartials = nullptr, *groupSums = nullptr, *forceSums = nullptr, *obsPartials = nullptr, *walkPartials = nullptr, *stats = nullptr;
+    // reductions (all over GLOBAL block rows / tiles, see step.cuh)
+    int passVerts = 0, vertsPerBlock = 0, numBlockRows = 0, cols = 0;   // fused kernel: vertices per pass, per block (fixed by n alone), rows, sums per row
+    int fusedBlocks = 0, repBlocks = 0, numObsTiles = 0;
+    double *blockPartials = nullptr, *forceSums = nullptr, *obsPartials = nullptr, *walkPartials = nullptr, *stats = nullptr;
     float* momentPartials = nullptr;
+    int momentStride = 1, numMomentTiles = 1, momentCount = 1;
     int statsTotal = 0;
 
     // vertex-sharded multi-GPU step (wb_comm_init): this rank owns vertices [ownBegin, ownEnd)
@@ -196,7 +197,7 @@ void free_all(wb_embedder* h) {
     F(h->chunkCounter); F(h->heavyVertex); F(h->heavySlot); F(h->heavyPos); F(h->hubVertex); F(h->hubSlot); F(h->hubD); F(h->hubF); F(h->mtScratch);
     F(h->keysIn); F(h->keysOut); F(h->valsIn); F(h->valsOut); F(h->cubTemp); F(h->quant); F(h->ids); F(h->blk); F(h->blkH);
     for (int l = 0; l < wb::kMaxLevels; ++l) { F(h->lvlLo[l]); if (l > 0) F(h->lvlHi[l]); F(h->lvlBound[l]); }
-    F(h->tilePartials); F(h->groupSums); F(h->forceSums); F(h->obsPartials); F(h->walkPartials); F(h->stats); F(h->momentPartials);
+    F(h->blockPartials); F(h->forceSums); F(h->obsPartials); F(h->walkPartials); F(h->stats); F(h->momentPartials);
     if (h->comm) { nccl().commDestroy(h->comm); h->comm = nullptr; }
     for (auto& p : h->pending) { cudaEventDestroy(p.done); cudaFreeHost(p.host); }
     for (auto& p : h->freeSlots) { cudaEventDestroy(p.done); cudaFreeHost(p.host); }
@@ -304,7 +305,7 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
     WB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     {   // policy of the pair list (A/B runs and tests; results never depend on it)
         const char* e = std::getenv("WB_SKIN_MAX");
-        h->skinMax = e ? (float)std::atof(e) : 1.0f;
+        h->skinMax = e ? (float)std::atof(e) : 0.3f;
         e = std::getenv("WB_REUSE_STEPS");
         h->reuseTarget = e ? std::max(1.f, (float)std::atof(e)) : 4.f;
     }
@@ -317,14 +318,22 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
     h->hostDegree.resize(n);
     for (int v = 0; v < n; ++v) h->hostDegree[v] = rowPtr[v + 1] - rowPtr[v];
 
-    // tiles of the fused kernel and of the recentre pass; rows are allocated for whole tiles so that bulk copies of a last, partial
-    // tile stay inside the arrays
-    h->tileVerts = wb::tile_vertices(V);
-    h->numTiles = div_up(std::max(n, 1), h->tileVerts);
-    h->numGroups = div_up(h->numTiles, wb::kTileGroup);
-    h->cols = wb::tile_sums(V) + 1;
+    // Block rows of the fused kernel: every block owns `vertsPerBlock` consecutive vertices, a multiple of one pass and a function of n
+    // alone, so the per-block sums are the same array on any grid and any number of GPUs.  ~16 blocks per SM of a B200.
+    h->passVerts = wb::pass_vertices(V);
+    {
+        const int passes = div_up(std::max(n, 1), h->passVerts);
+        h->vertsPerBlock = h->passVerts * std::max(1, div_up(passes, 148 * 16));
+    }
+    h->numBlockRows = div_up(std::max(n, 1), h->vertsPerBlock);
+    h->cols = wb::block_sums(V) + 1;
     h->numObsTiles = div_up(std::max(n, 1), wb::kObsTile);
-    h->rowsAlloc = (size_t)h->numTiles * h->tileVerts;
+    // tiles whose moments feed the next quantisation frame: every 8th once there are plenty
+    h->momentStride = std::max(1, std::min(8, h->numObsTiles / 16));
+    h->numMomentTiles = div_up(h->numObsTiles, h->momentStride);
+    h->momentCount = 0;
+    for (int t = 0; t < h->numObsTiles; t += h->momentStride) h->momentCount += std::min(wb::kObsTile, std::max(n, 1) - t * wb::kObsTile);
+    h->rowsAlloc = (size_t)h->numBlockRows * h->vertsPerBlock;
     const size_t rows = h->rowsAlloc * V;
     for (float4** p : {&h->x, &h->xNew, &h->mom1, &h->mom2, &h->force}) {
         *p = dalloc<float4>(rows);
@@ -409,10 +418,9 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
         WB_CUDA(cudaMemsetAsync(h->blkH, 0, h4 * sizeof(float4), h->stream));
         t.blkH = h->blkH;
         t.quant = h->quant;
-        // the walk's per-warp queries + stacks and the fused kernel's stages exceed the 48 KB static limit
+        // the walk's per-warp queries + stacks exceed the 48 KB static limit for the wider rows
         WB_DISPATCH_V(V, WB_CUDA(cudaFuncSetAttribute(wb::k_repulse_pairs<V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wb::repulse_smem_bytes(V, false)));
-                         WB_CUDA(cudaFuncSetAttribute(wb::k_repulse_pairs<V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wb::repulse_smem_bytes(V, true)));
-                         WB_CUDA(cudaFuncSetAttribute(wb::k_step_fused<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wb::step_fused_smem<V>())));
+                         WB_CUDA(cudaFuncSetAttribute(wb::k_repulse_pairs<V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wb::repulse_smem_bytes(V, true))));
     }
     h->ids = dalloc<int>(t.stride[0]);
     WB_CUDA(cudaMemsetAsync(h->ids, 0xff, sizeof(int) * t.stride[0], h->stream));
@@ -425,13 +433,8 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
     h->chunkCounter = dalloc<int>(1);
     h->repLayout = wb::RepLayout{1, 0, div_up(std::max(n, 1), 32) * 32};
     h->ownBegin = 0; h->ownEnd = n; h->rowsPerRank = (int)h->rowsAlloc;
-    // fused kernel: every block works through a contiguous run of tiles, as many blocks as can be resident
-    h->fusedBlocks = std::max(1, std::min(h->numTiles, sms * WB_FUSED_MINBLOCKS));
-    h->tilesPerBlock = div_up(h->numTiles, h->fusedBlocks);
-    h->fusedBlocks = div_up(h->numTiles, h->tilesPerBlock);
-    h->mtScratch = dalloc<uint32_t>((size_t)h->fusedBlocks * 8 * 624);
-    h->tilePartials = dalloc<double>((size_t)h->numTiles * h->cols);
-    h->groupSums = dalloc<double>((size_t)h->numGroups * h->cols);
+    h->fusedBlocks = h->numBlockRows;
+    h->blockPartials = dalloc<double>((size_t)h->numBlockRows * h->cols);
     h->forceSums = dalloc<double>(h->cols);
     h->obsPartials = dalloc<double>((size_t)h->numObsTiles * 2);
     h->statsTotal = h->cols + wb::kTailStats;
@@ -549,7 +552,8 @@ void launch_step(wb_embedder* h, const PendingStep& slot) {
         wb::k_scan_offsets<<<1, 1024, 0, s>>>(h->scanSums, scanBlocks, h->ctrl);
         wb::k_scan_apply<<<scanBlocks, 256, 0, s>>>(h->repDeg + h->ownBegin, own, h->scanSums, scanBlocks, h->repRowPtr + h->ownBegin, h->ctrl);
         wb::k_rep_fill<<<pairBlocks, 256, 0, s>>>(src, h->repDeg, h->repRowPtr, h->repCol, h->ctrl);
-        h->launches += 5;
+        wb::k_rep_sort_rows<<<div_up(own, 256), 256, 0, s>>>(h->repRowPtr, h->repCol, h->ownBegin, h->ownEnd, h->hubSlot, h->ctrl);
+        h->launches += 6;
     }
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[2], s));
     if (h->numHubs) {
@@ -557,21 +561,22 @@ void launch_step(wb_embedder* h, const PendingStep& slot) {
                                                                        fp, h->hubD, h->hubF, h->ctrl));
         h->launches += 1;
     }
-    const int tileBegin = h->ownBegin / h->tileVerts, tileEnd = div_up(h->ownEnd, h->tileVerts);
-    WB_DISPATCH_V(V, wb::k_step_fused<V><<<h->fusedBlocks, 256, wb::step_fused_smem<V>(), s>>>(
-                         h->x, h->iw, h->rowPtr, h->col, h->repRowPtr, h->repCol, h->ownBegin, h->ownEnd, h->tilesPerBlock, fp, h->dyn, h->hubSlot, h->hubD, h->hubF,
-                         h->xNew, h->mom1, h->mom2, h->force, h->tilePartials, h->mtScratch, h->ctrl));
-    const int ownGroups = div_up(tileEnd - tileBegin, wb::kTileGroup);
-    wb::k_reduce_tile_groups<<<div_up((int64_t)ownGroups * h->cols, 256), 256, 0, s>>>(h->tilePartials, tileBegin, tileEnd, h->cols, h->groupSums, h->ctrl);
-    wb::k_reduce_groups<<<h->cols, 256, 0, s>>>(h->groupSums, h->numGroups, h->cols, h->forceSums, h->ctrl);
+    const int ownBlocks = div_up(std::max(0, h->ownEnd - h->ownBegin), h->vertsPerBlock);
+    if (ownBlocks > 0) {
+        WB_DISPATCH_V(V, wb::k_step_fused<V><<<ownBlocks, 256, 0, s>>>(h->x, h->iw, h->rowPtr, h->col, h->repRowPtr, h->repCol, h->ownBegin, h->ownEnd, h->vertsPerBlock, fp,
+                                                                        h->dyn, h->hubSlot, h->hubD, h->hubF, h->xNew, h->mom1, h->mom2, h->force,
+                                                                        h->blockPartials, h->ctrl));
+    }
+    wb::k_reduce_rows<<<h->cols, 256, 0, s>>>(h->blockPartials, h->numBlockRows, h->cols, h->forceSums, h->ctrl);
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[3], s));
     const int obsBegin = h->ownBegin / wb::kObsTile, obsEnd = div_up(h->ownEnd, wb::kObsTile);
-    WB_DISPATCH_V(V, wb::k_recentre_observe<V><<<obsEnd - obsBegin, 256, 0, s>>>(h->x, h->xNew, n, obsBegin, h->dim, h->forceSums, h->obsPartials, h->momentPartials, h->ctrl));
+    if (obsEnd > obsBegin)
+        WB_DISPATCH_V(V, wb::k_recentre_observe<V><<<obsEnd - obsBegin, 256, 0, s>>>(h->x, h->xNew, n, obsBegin, h->dim, h->forceSums, h->obsPartials, h->momentStride, h->momentPartials, h->ctrl));
     wb::TailPolicy pol{(float)h->opt.edge_length, h->halfSigmaLimit, h->dim, h->mortonBits};
-    wb::k_step_tail<<<1, 1024, 0, s>>>(h->forceSums, h->cols, h->obsPartials, h->numObsTiles, h->momentPartials, n, h->walkPartials, repWarps + h->numHeavy,
-                                        h->pairCounts, h->world, pol, h->quant, h->ctrl, h->stats);
+    wb::k_step_tail<<<1, 1024, 0, s>>>(h->forceSums, h->cols, h->obsPartials, h->numObsTiles, h->momentPartials, h->numMomentTiles, h->momentCount, n, h->walkPartials, repWarps + h->numHeavy,
+                                        pol, h->quant, h->ctrl, h->stats);
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[4], s));
-    h->launches += 5;
+    h->launches += 4;
     WB_CUDA(cudaGetLastError());
     WB_CUDA(cudaMemcpyAsync(slot.host->sums, h->stats, sizeof(double) * h->statsTotal, cudaMemcpyDeviceToHost, s));
     WB_CUDA(cudaEventRecord(slot.done, s));
@@ -631,7 +636,7 @@ void collect_step(wb_embedder* h, wb_step_stats* out) {
         st.loss_attract = s[0];
         st.loss_repel = s[1];
         st.num_repulsion_pairs = s[2];
-        for (int k = 0; k < h->dim; ++k) st.centroid[k] = s[3 + k] / (double)h->n;
+        for (int k = 0; k < h->dim; ++k) st.centroid[k] = s[4 + k] / (double)h->n;
         st.max_displacement_ratio = s[cols - 1];
         st.num_listed_pairs = s[cols + 0];
         st.num_candidates = s[cols + 1];
