@@ -187,19 +187,25 @@ int wb_get_phase_times(wb_embedder* h, double* ms6);
 /* -- multi-GPU: one graph sharded by vertex range over the GPUs of one node ----------------------- */
 
 /*
- * One process (or thread) per GPU creates the SAME problem (same CSR, weights, coordinates) on its device and then
- * joins a communicator: rank 0 calls wb_comm_unique_id and ships the 128 bytes to the other ranks by any means
- * (bench.py uses torch.distributed), every rank calls wb_comm_init.  From then on wb_step walks the repulsion queries of
- * this rank's blocks of the sorted order (the integer result rows are reduce-scattered), and computes the attraction and
- * the optimizer update only for the vertices [rank * ceil(n / world), ...) it owns; positions stay replicated: the
- * owners' updated rows are all-gathered (NCCL over NVLink) at the end of every step, the scalar sums (losses,
- * centroid, displacement) are all-gathered and added in rank order, so all ranks return identical statistics and the
- * sharded step is bit-identical to the single-GPU step.
- * The reference has no distributed code; this is the multi-GPU form of its OpenMP `parallel for` over vertices
- * (WembedEmbedder.cpp:262,279), every vertex still being written by exactly one owner.
+ * One process per GPU creates the SAME problem (same CSR, weights, coordinates) on its device and then joins the group: rank 0 calls
+ * wb_comm_unique_id and ships the 128 bytes to the other ranks by any means (bench.py uses torch.distributed), every rank calls
+ * wb_comm_init (world <= 8, one node).  The ranks map each other's buffers through CUDA IPC (NCCL only carries the handles) and from
+ * then on a step on rank r
+ *   - searches the repulsion pairs of its blocks of the sorted order and stores every pair straight into the pair buffer of the
+ *     rank(s) owning its two vertices (peer stores over NVLink);
+ *   - runs the fused force + optimizer kernel for the vertices [r * rows, (r + 1) * rows) it owns (wb_get_partition) and stores each
+ *     block's row of sums into every rank's copy of the sum rows;
+ *   - recentres its rows and stores them into EVERY replica of the positions, together with its observation tiles;
+ * with three flag barriers in between (k_exchange).  Positions stay replicated; every vertex is written by exactly one owner (the
+ * multi-GPU form of the reference's OpenMP `parallel for` over vertices, WembedEmbedder.cpp:262,279).  All sums are taken over
+ * global block rows / tiles in a fixed order, so the sharded step is bit-identical to the single-GPU step and all ranks return
+ * identical statistics (except num_candidates / num_box_tests, which count the rank's own share of the search).
+ * The reference has no distributed code.
  */
 int wb_comm_unique_id(char* id128);
 int wb_comm_init(wb_embedder* h, const char* id128, int32_t rank, int32_t world);
+/* [begin, end) of the vertices this handle owns (everything before wb_comm_init). */
+int wb_get_partition(wb_embedder* h, int32_t* begin, int32_t* end);
 
 /* -- evaluation ("next") ---------------------------------------------------------- */
 

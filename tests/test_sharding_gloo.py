@@ -14,7 +14,9 @@ def test_partition_covers_every_vertex_once():
         parts = sharding.partition(n, world)
         assert len(parts) == world and parts[0][0] == 0 and parts[-1][1] == n
         assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
-        assert all(0 <= e - b <= -(-max(n, 1) // world) for b, e in parts)
+        rows = sharding.rows_per_rank(n, world, 4)
+        assert rows % 1024 == 0 and rows * world >= n           # whole observation tiles and block rows per rank
+        assert all(0 <= e - b <= rows for b, e in parts)
         if n:
             own = sharding.owner_of(np.arange(n), n, world)
             for r, (b, e) in enumerate(parts):
@@ -27,7 +29,7 @@ def _worker(rank, world, port, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         uid = sharding.exchange_unique_id(lambda: bytes(range(128)), rank, world)
-        lo, hi = sharding.partition(1001, world)[rank]
+        lo, hi = sharding.partition(3001, world)[rank]
         # fixed-order sum of per-rank partials, as the device does it (k_sum_ranks): gather, add in rank order
         import torch
         mine = torch.tensor([float(hi - lo), float(rank + 1) * 0.1], dtype=torch.float64)
@@ -54,5 +56,5 @@ def test_two_ranks_share_id_and_partition():
         assert p.exitcode == 0
     (r0, id0, lo0, hi0, t0), (r1, id1, lo1, hi1, t1) = res
     assert id0 == id1 == bytes(range(128))
-    assert (lo0, hi0, lo1, hi1) == (0, 501, 501, 1001)
-    assert t0 == t1 and t0[0] == 1001.0
+    assert (lo0, hi0, lo1, hi1) == (0, 2048, 2048, 3001)
+    assert t0 == t1 and t0[0] == 3001.0

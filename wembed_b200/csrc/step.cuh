@@ -15,33 +15,76 @@ __device__ __forceinline__ long long to_fixed(float term, double scale) { return
 
 // ---------------------------------------------------------------------------------------------
 // First kernel of every step: resets the work counters of a build.
-__global__ void k_step_begin(StepCtrl* ctrl, unsigned int* pairCounts, int world, int* chunkCounter) {
+__global__ void k_step_begin(StepCtrl* ctrl, unsigned int* pairCounts /* this rank's row of the counts matrix */, int world, int* chunkCounter) {
     if (ctrl->overflow != 0 || ctrl->rebuild == 0) return;
     if ((int)threadIdx.x < world) pairCounts[threadIdx.x] = 0u;
     if (threadIdx.x == 0) *chunkCounter = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
+// Sharded run (wb_comm_init): every rank maps the other ranks' buffers (CUDA IPC over NVLink) and the kernels that produce data other
+// ranks need store it straight into the consumers' memory - found pairs into the owners' inboxes (walk.cuh), a block's sums into every
+// rank's copy of the sum rows, recentred positions into every replica of x.  What is left of the collectives is a barrier:
+// k_exchange publishes "my kernels up to here are done" to every peer (release at system scope) and waits until every peer has said
+// the same.  Mail = one buffer per rank: [flags | counts matrix | block sum rows | observation tiles | moment tiles].
+constexpr int kMailFlags = 0;                      // int[kMaxRanks]: last barrier epoch each peer has reached
+constexpr int kMailCounts = 64;                    // unsigned[kMaxRanks][kMaxRanks]: pairs produced by rank p for rank d
+constexpr int kMailData = 64 + 4 * kMaxRanks * kMaxRanks;
+struct Peers {
+    char* mail[kMaxRanks];
+    int world, rank;
+};
+// where a kernel's output rows go: every rank's copy (one GPU: the only copy)
+template <typename T>
+struct Replicas {
+    T* at[kMaxRanks];
+    int world;
+};
+
+__global__ void k_exchange(const Peers pm, int epoch, int withCounts, StepCtrl* ctrl) {
+    const int p = threadIdx.x;
+    if (p < pm.world) {
+        if (withCounts) {                          // my row of the counts matrix -> every rank (mine included: it is the row I counted into)
+            const unsigned int* mine = reinterpret_cast<const unsigned int*>(pm.mail[pm.rank] + kMailCounts) + pm.rank * kMaxRanks;
+            unsigned int* dst = reinterpret_cast<unsigned int*>(pm.mail[p] + kMailCounts) + pm.rank * kMaxRanks;
+            if (p != pm.rank)
+                for (int d = 0; d < pm.world; ++d) dst[d] = mine[d];
+        }
+        __threadfence_system();
+        *(reinterpret_cast<volatile int*>(pm.mail[p] + kMailFlags) + pm.rank) = epoch;
+        volatile int* flag = reinterpret_cast<volatile int*>(pm.mail[pm.rank] + kMailFlags) + p;
+        const long long t0 = clock64();
+        while (*flag < epoch) {
+            if (clock64() - t0 > (20ll << 30)) { ctrl->overflow = 2; break; }       // ~10 s: a peer died; the host reports it
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+}
+
+// ---------------------------------------------------------------------------------------------
 // Pair list -> CSR of partners (both directions) for the vertices [ownBegin, ownEnd) of this rank.
 struct PairSource {
     const int2* seg[kMaxRanks];        // one segment per producing rank (one GPU: the walk's own buffer)
-    const unsigned int* count;         // [world] pairs in each segment
+    const unsigned int* counts;        // counts[p * kMaxRanks + d] = pairs rank p produced for rank d (one GPU: counts[0])
     unsigned int cap;
-    int world, ownBegin, ownEnd;
+    int world, rank, ownBegin, ownEnd;
 };
 
 // degrees; also raises StepCtrl::overflow when a segment ran out of space (the rest of this step and all later ones then return at
 // once; the host grows the buffer and replays them)
 __global__ void __launch_bounds__(256) k_rep_count(const PairSource src, int* __restrict__ deg, StepCtrl* ctrl) {
     if (build_skipped(ctrl, 0)) return;
+    // every rank looks at the whole matrix of counts, so all ranks of a sharded run take the same decision
     unsigned int worst = 0u;
-    for (int s = 0; s < src.world; ++s) worst = max(worst, src.count[s]);
+    for (int p = 0; p < src.world; ++p)
+        for (int d = 0; d < src.world; ++d) worst = max(worst, src.counts[p * kMaxRanks + d]);
     if (worst > src.cap) {
         if (blockIdx.x == 0 && threadIdx.x == 0) { ctrl->pairNeeded = worst; ctrl->listValid = 0; ctrl->overflow = 1; }
         return;
     }
     for (int s = 0; s < src.world; ++s) {
-        const unsigned int cnt = src.count[s];
+        const unsigned int cnt = src.counts[s * kMaxRanks + src.rank];
         for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
             const int2 p = src.seg[s][i];
             if (p.x >= src.ownBegin && p.x < src.ownEnd) atomicAdd(deg + p.x, 1);
@@ -122,7 +165,7 @@ __global__ void __launch_bounds__(256) k_rep_fill(const PairSource src, int* __r
                                                   int* __restrict__ repCol, StepCtrl* ctrl) {
     if (build_skipped(ctrl, 0)) return;
     for (int s = 0; s < src.world; ++s) {
-        const unsigned int cnt = src.count[s];
+        const unsigned int cnt = src.counts[s * kMaxRanks + src.rank];
         for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
             const int2 p = src.seg[s][i];
             if (p.x >= src.ownBegin && p.x < src.ownEnd) repCol[repRowPtr[p.x] + atomicSub(deg + p.x, 1) - 1] = p.y;
@@ -195,7 +238,8 @@ k_step_fused(const float4* __restrict__ x, const float* __restrict__ iw, const i
              const int* __restrict__ repRowPtr, const int* __restrict__ repCol, int rangeBegin, int rangeEnd, int vertsPerBlock,
              const ForceParams fp, const StepDyn* __restrict__ dynp, const int* __restrict__ hubSlot, const double* __restrict__ hubD,
              const long long* __restrict__ hubF, float4* __restrict__ xNew, float4* __restrict__ mom1, float4* __restrict__ mom2,
-             float4* __restrict__ forceOut, double* __restrict__ blockPartials /* [block][K + 1] */, const StepCtrl* __restrict__ ctrl) {
+             float4* __restrict__ forceOut, const Replicas<double> blockPartials /* [block][K + 1] on every rank */,
+             const StepCtrl* __restrict__ ctrl) {
     if (ctrl->overflow != 0) return;
     constexpr int G = attract_lanes(V), VPW = 32 / G, VPB = 8 * VPW, K = block_sums(V), B = 4;
     __shared__ uint32_t mtState[8][624];
@@ -397,7 +441,7 @@ k_step_fused(const float4* __restrict__ x, const float* __restrict__ iw, const i
         double sacc = redBuf[0][threadIdx.x];
         if (threadIdx.x < K) { for (int w = 1; w < 8; ++w) sacc += redBuf[w][threadIdx.x]; }
         else { for (int w = 1; w < 8; ++w) sacc = fmax(sacc, redBuf[w][threadIdx.x]); }
-        blockPartials[(int64_t)blockRow * (K + 1) + threadIdx.x] = sacc;
+        for (int q = 0; q < blockPartials.world; ++q) blockPartials.at[q][(int64_t)blockRow * (K + 1) + threadIdx.x] = sacc;
     }
 }
 
@@ -511,9 +555,10 @@ __global__ void __launch_bounds__(256) k_reduce_rows(const double* __restrict__ 
 // quantisation frame from that sample (only locality depends on the frame, and a fixed 1-in-8 sample of the tiles pins it as well as
 // all of them while costing an eighth).
 template <int V>
-__global__ void __launch_bounds__(256) k_recentre_observe(float4* __restrict__ x, const float4* __restrict__ xNew, int n, int tileBegin, int dim,
-                                                          const double* __restrict__ forceSums, double* __restrict__ obsPartials /* [tile][2] */,
-                                                          int momentStride, float* __restrict__ momentPartials /* [tile / stride][4][kMaxDim] */,
+__global__ void __launch_bounds__(256) k_recentre_observe(const float4* xOld /* == x.at[rank]: the old rows are read before the new ones are stored */, const Replicas<float4> x, const float4* __restrict__ xNew, int n,
+                                                          int tileBegin, int dim, const double* __restrict__ forceSums,
+                                                          const Replicas<double> obsPartials /* [tile][2] */, int momentStride,
+                                                          const Replicas<float> momentPartials /* [tile / stride][4][kMaxDim] */,
                                                           const StepCtrl* __restrict__ ctrl) {
     if (ctrl->overflow != 0) return;
     __shared__ double redBuf[8 * 2];
@@ -529,9 +574,9 @@ __global__ void __launch_bounds__(256) k_recentre_observe(float4* __restrict__ x
 #pragma unroll
         for (int c = 0; c < V; ++c) {
             const int64_t at = (int64_t)v * V + c;
-            const float4 a = xNew[at], o = x[at];
+            const float4 a = xNew[at], o = xOld[at];
             const float4 r = make_float4(a.x - cen[4 * c], a.y - cen[4 * c + 1], a.z - cen[4 * c + 2], a.w - cen[4 * c + 3]);
-            x[at] = r;
+            for (int q = 0; q < x.world; ++q) x.at[q][at] = r;         // every replica (peers over NVLink)
             disp2 = fmaf(r.x - o.x, r.x - o.x, disp2); disp2 = fmaf(r.y - o.y, r.y - o.y, disp2);
             disp2 = fmaf(r.z - o.z, r.z - o.z, disp2); disp2 = fmaf(r.w - o.w, r.w - o.w, disp2);
             rad2 = fmaf(r.x, r.x, rad2); rad2 = fmaf(r.y, r.y, rad2); rad2 = fmaf(r.z, r.z, rad2); rad2 = fmaf(r.w, r.w, rad2);
@@ -539,7 +584,10 @@ __global__ void __launch_bounds__(256) k_recentre_observe(float4* __restrict__ x
         sums[0] += (double)sqrtf(disp2);
         sums[1] += (double)rad2;
     }
-    block_sum<2, 256>(sums, redBuf, obsPartials + (int64_t)tile * 2);
+    __shared__ double tileSums[2];
+    block_sum<2, 256>(sums, redBuf, tileSums);
+    if (threadIdx.x < 2)
+        for (int q = 0; q < obsPartials.world; ++q) obsPartials.at[q][(int64_t)tile * 2 + threadIdx.x] = tileSums[threadIdx.x];
     if (tile % momentStride != 0) return;
     // second pass over the tile's (L1 / L2-resident) rows for the moments
     float mn[4 * V], mx[4 * V], s1[4 * V], s2[4 * V];
@@ -548,8 +596,8 @@ __global__ void __launch_bounds__(256) k_recentre_observe(float4* __restrict__ x
     for (int v = tile * kObsTile + threadIdx.x; v < vEnd; v += 256) {
 #pragma unroll
         for (int c = 0; c < V; ++c) {
-            const float4 p = x[(int64_t)v * V + c];
-            const float e[4] = {p.x, p.y, p.z, p.w};
+            const float4 p = xNew[(int64_t)v * V + c];
+            const float e[4] = {p.x - cen[4 * c], p.y - cen[4 * c + 1], p.z - cen[4 * c + 2], p.w - cen[4 * c + 3]};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int k = 4 * c + i;
@@ -558,7 +606,13 @@ __global__ void __launch_bounds__(256) k_recentre_observe(float4* __restrict__ x
             }
         }
     }
-    moments_block_reduce<V>(mn, mx, s1, s2, smMom, momentPartials + (int64_t)(tile / momentStride) * 4 * kMaxDim);
+    __shared__ float tileMom[4 * kMaxDim];
+    moments_block_reduce<V>(mn, mx, s1, s2, smMom, tileMom);
+    __syncthreads();
+    for (int k = threadIdx.x; k < 4 * kMaxDim; k += 256) {
+        if ((k % kMaxDim) >= 4 * V) continue;
+        for (int q = 0; q < momentPartials.world; ++q) momentPartials.at[q][(int64_t)(tile / momentStride) * 4 * kMaxDim + k] = tileMom[k];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -579,7 +633,7 @@ __global__ void __launch_bounds__(1024) k_step_tail(const double* __restrict__ f
     __shared__ double sm[1024];
     __shared__ double res[5];
     if (ctrl->overflow != 0) {
-        if (threadIdx.x == 0) { stats[cols + 8] = 1.0; stats[cols + 9] = (double)ctrl->pairNeeded; }
+        if (threadIdx.x == 0) { stats[cols + 8] = (double)ctrl->overflow; stats[cols + 9] = (double)ctrl->pairNeeded; }
         return;
     }
     const bool rebuilt = ctrl->rebuild != 0;

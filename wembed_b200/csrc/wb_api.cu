@@ -16,6 +16,7 @@
 #include <cstring>
 #include <deque>
 #include <limits>
+#include <numeric>
 #include <stdexcept>
 #include <thread>
 #include <vector>
@@ -106,9 +107,11 @@ struct wb_embedder {
     // device-side control block, per-step scalars, pair list
     wb::StepCtrl* ctrl = nullptr;
     wb::StepDyn* dyn = nullptr;
-    int2* pairBuf = nullptr;
+    int2* pairBuf = nullptr;              // world segments of pairCap pairs: segment p = what rank p found for this rank's vertices
     unsigned int pairCap = 0;
-    unsigned int* pairCounts = nullptr;   // [kMaxRanks]
+    unsigned int* pairCounts = nullptr;   // counts matrix [kMaxRanks][kMaxRanks] inside `mail`
+    char* mail = nullptr;                 // [flags | counts | block sum rows | observation tiles | moment tiles] (step.cuh: k_exchange)
+    size_t mailBytes = 0;
     int *repDeg = nullptr, *repRowPtr = nullptr, *repCol = nullptr, *scanSums = nullptr;
     int scanBlocks = 0;
     float skinMax = 0.f, reuseTarget = 4.f;
@@ -147,13 +150,19 @@ struct wb_embedder {
     int passVerts = 0, vertsPerBlock = 0, numBlockRows = 0, cols = 0;   // fused kernel: vertices per pass, per block (fixed by n alone), rows, sums per row
     int fusedBlocks = 0, repBlocks = 0, numObsTiles = 0;
     double *blockPartials = nullptr, *forceSums = nullptr, *obsPartials = nullptr, *walkPartials = nullptr, *stats = nullptr;
-    float* momentPartials = nullptr;
+    float *momentPartials = nullptr, *frameScratch = nullptr;
     int momentStride = 1, numMomentTiles = 1, momentCount = 1;
     int statsTotal = 0;
 
-    // vertex-sharded multi-GPU step (wb_comm_init): this rank owns vertices [ownBegin, ownEnd)
+    // vertex-sharded multi-GPU step (wb_comm_init): this rank owns vertices [ownBegin, ownEnd); the other ranks' buffers are mapped
+    // through CUDA IPC and written to directly by the kernels (peer stores over NVLink)
     ncclComm_t comm = nullptr;
     int world = 1, rank = 0, ownBegin = 0, ownEnd = 0, rowsPerRank = 0;
+    char* peerMail[wb::kMaxRanks] = {};
+    float4* peerX[wb::kMaxRanks] = {};
+    int2* peerPairs[wb::kMaxRanks] = {};
+    bool peersOpen = false, peerPairsOpen = false;
+    int epoch = 0;                        // barrier counter (k_exchange)
 
     std::deque<PendingStep> pending;
     std::vector<PendingStep> freeSlots;
@@ -193,11 +202,19 @@ inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 void free_all(wb_embedder* h) {
     auto F = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
     F(h->rowPtr); F(h->col); F(h->x); F(h->xNew); F(h->mom1); F(h->mom2); F(h->force); F(h->iw);
-    F(h->ctrl); F(h->dyn); F(h->pairBuf); F(h->pairCounts); F(h->repDeg); F(h->repRowPtr); F(h->repCol); F(h->scanSums);
+    if (h->world > 1) {
+        for (int p = 0; p < h->world; ++p) {
+            if (p == h->rank) continue;
+            if (h->peersOpen) { cudaIpcCloseMemHandle(h->peerMail[p]); cudaIpcCloseMemHandle(h->peerX[p]); }
+            if (h->peerPairsOpen) cudaIpcCloseMemHandle(h->peerPairs[p]);
+        }
+        h->peersOpen = h->peerPairsOpen = false;
+    }
+    F(h->ctrl); F(h->dyn); F(h->pairBuf); F(h->mail); F(h->repDeg); F(h->repRowPtr); F(h->repCol); F(h->scanSums);
     F(h->chunkCounter); F(h->heavyVertex); F(h->heavySlot); F(h->heavyPos); F(h->hubVertex); F(h->hubSlot); F(h->hubD); F(h->hubF); F(h->mtScratch);
     F(h->keysIn); F(h->keysOut); F(h->valsIn); F(h->valsOut); F(h->cubTemp); F(h->quant); F(h->ids); F(h->blk); F(h->blkH);
     for (int l = 0; l < wb::kMaxLevels; ++l) { F(h->lvlLo[l]); if (l > 0) F(h->lvlHi[l]); F(h->lvlBound[l]); }
-    F(h->blockPartials); F(h->forceSums); F(h->obsPartials); F(h->walkPartials); F(h->stats); F(h->momentPartials);
+    F(h->forceSums); F(h->walkPartials); F(h->stats); F(h->frameScratch);
     if (h->comm) { nccl().commDestroy(h->comm); h->comm = nullptr; }
     for (auto& p : h->pending) { cudaEventDestroy(p.done); cudaFreeHost(p.host); }
     for (auto& p : h->freeSlots) { cudaEventDestroy(p.done); cudaFreeHost(p.host); }
@@ -295,9 +312,9 @@ void rebuild_hub_lists(wb_embedder* h) {
 void allocate_pair_list(wb_embedder* h, unsigned int cap) {
     auto F = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
     F(h->pairBuf); F(h->repCol);
-    h->pairCap = cap;
-    h->pairBuf = dalloc<int2>((size_t)cap);
-    h->repCol = dalloc<int>((size_t)2 * cap + 8);
+    h->pairCap = cap;                                            // per segment
+    h->pairBuf = dalloc<int2>((size_t)cap * h->world);
+    h->repCol = dalloc<int>((size_t)2 * cap * h->world + 8);
 }
 
 void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
@@ -346,8 +363,20 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
 
     h->ctrl = dalloc<wb::StepCtrl>(1);
     h->dyn = dalloc<wb::StepDyn>(1);
-    h->pairCounts = dalloc<unsigned int>(wb::kMaxRanks);
-    WB_CUDA(cudaMemsetAsync(h->pairCounts, 0, sizeof(unsigned int) * wb::kMaxRanks, h->stream));
+    {   // mail: one allocation, so a sharded run exports it with one IPC handle
+        size_t off = wb::kMailData;
+        auto carve = [&](size_t bytes) { const size_t at = off; off += (bytes + 255) & ~(size_t)255; return at; };
+        const size_t rowsAt = carve(sizeof(double) * h->numBlockRows * h->cols);
+        const size_t obsAt = carve(sizeof(double) * h->numObsTiles * 2);
+        const size_t momAt = carve(sizeof(float) * h->numMomentTiles * 4 * wb::kMaxDim);
+        h->mailBytes = off;
+        h->mail = dalloc<char>(off);
+        WB_CUDA(cudaMemsetAsync(h->mail, 0, off, h->stream));
+        h->pairCounts = reinterpret_cast<unsigned int*>(h->mail + wb::kMailCounts);
+        h->blockPartials = reinterpret_cast<double*>(h->mail + rowsAt);
+        h->obsPartials = reinterpret_cast<double*>(h->mail + obsAt);
+        h->momentPartials = reinterpret_cast<float*>(h->mail + momAt);
+    }
     {   // pair list: room for 8 unordered pairs per vertex (never more than all pairs); grown on demand (collect_step)
         const int64_t all = (int64_t)n * (n - 1) / 2;
         int64_t cap = std::max<int64_t>(1024, std::min<int64_t>({all + 8, (int64_t)8 * n, (int64_t)0x3fffffff}));
@@ -373,7 +402,7 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
     h->cubBytes = 0;
     WB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, h->cubBytes, h->keysIn, h->keysOut, h->valsIn, h->valsOut, std::max(n, 1), 0, 32, h->stream));
     h->cubTemp = dalloc<char>(h->cubBytes);
-    h->momentPartials = dalloc<float>((size_t)h->numObsTiles * 4 * wb::kMaxDim);
+    h->frameScratch = dalloc<float>((size_t)h->numObsTiles * 4 * wb::kMaxDim);
     h->quant = dalloc<wb::QuantParams>(1);
     WB_CUDA(cudaMemsetAsync(h->quant, 0, sizeof(wb::QuantParams), h->stream));
 
@@ -434,9 +463,7 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
     h->repLayout = wb::RepLayout{1, 0, div_up(std::max(n, 1), 32) * 32};
     h->ownBegin = 0; h->ownEnd = n; h->rowsPerRank = (int)h->rowsAlloc;
     h->fusedBlocks = h->numBlockRows;
-    h->blockPartials = dalloc<double>((size_t)h->numBlockRows * h->cols);
     h->forceSums = dalloc<double>(h->cols);
-    h->obsPartials = dalloc<double>((size_t)h->numObsTiles * 2);
     h->statsTotal = h->cols + wb::kTailStats;
     h->stats = dalloc<double>(h->statsTotal);
     WB_CUDA(cudaMemsetAsync(h->stats, 0, sizeof(double) * h->statsTotal, h->stream));
@@ -469,8 +496,8 @@ wb::ForceParams force_params(const wb_embedder* h) {
 // previous step's recentre pass
 void enqueue_frame(wb_embedder* h) {
     cudaStream_t s = h->stream;
-    WB_DISPATCH_V(h->V, wb::k_moments<V><<<h->numObsTiles, 256, 0, s>>>(h->x, h->n, h->momentPartials));
-    wb::k_quant_params<<<1, 1024, 0, s>>>(h->momentPartials, h->numObsTiles, h->n, h->dim, h->mortonBits, h->halfSigmaLimit, h->quant);
+    WB_DISPATCH_V(h->V, wb::k_moments<V><<<h->numObsTiles, 256, 0, s>>>(h->x, h->n, h->frameScratch));
+    wb::k_quant_params<<<1, 1024, 0, s>>>(h->frameScratch, h->numObsTiles, h->n, h->dim, h->mortonBits, h->halfSigmaLimit, h->quant);
     h->launches += 2;
     h->quantValid = true;
 }
@@ -518,14 +545,32 @@ void launch_step(wb_embedder* h, const PendingStep& slot) {
     const bool build = h->nextRebuild != 0 || !h->pending.empty();
 
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[0], s));
-    wb::k_step_begin<<<1, 32, 0, s>>>(h->ctrl, h->pairCounts, h->world, h->chunkCounter);
+    wb::k_step_begin<<<1, 32, 0, s>>>(h->ctrl, h->pairCounts + h->rank * wb::kMaxRanks, h->world, h->chunkCounter);
     h->launches += 1;
     if (build) enqueue_index(h, h->iw, 0);
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[1], s));
+    const bool sharded = h->world > 1;
+    wb::Peers peers{};
+    peers.world = h->world; peers.rank = h->rank;
     wb::PairSink sink{};
-    sink.seg[0] = h->pairBuf; sink.count = h->pairCounts; sink.cap = h->pairCap; sink.world = 1; sink.rowsPerRank = std::max(h->rowsPerRank, 1);
     wb::PairSource src{};
-    src.seg[0] = h->pairBuf; src.count = h->pairCounts; src.cap = h->pairCap; src.world = 1; src.ownBegin = h->ownBegin; src.ownEnd = h->ownEnd;
+    wb::Replicas<double> rowsOut{}, obsOut{};
+    wb::Replicas<float> momOut{};
+    wb::Replicas<float4> xOut{};
+    rowsOut.world = obsOut.world = momOut.world = xOut.world = h->world;
+    for (int p = 0; p < h->world; ++p) {
+        char* mail = p == h->rank ? h->mail : h->peerMail[p];
+        peers.mail[p] = mail;
+        rowsOut.at[p] = reinterpret_cast<double*>(mail + (reinterpret_cast<char*>(h->blockPartials) - h->mail));
+        obsOut.at[p] = reinterpret_cast<double*>(mail + (reinterpret_cast<char*>(h->obsPartials) - h->mail));
+        momOut.at[p] = reinterpret_cast<float*>(mail + (reinterpret_cast<char*>(h->momentPartials) - h->mail));
+        xOut.at[p] = p == h->rank ? h->x : h->peerX[p];
+        // what this rank finds for rank p's vertices goes into segment `rank` of p's buffer; it reads segment p of its own
+        sink.seg[p] = (p == h->rank ? h->pairBuf : h->peerPairs[p]) + (size_t)h->rank * h->pairCap;
+        src.seg[p] = h->pairBuf + (size_t)p * h->pairCap;
+    }
+    sink.count = h->pairCounts + h->rank * wb::kMaxRanks; sink.cap = h->pairCap; sink.world = h->world; sink.rowsPerRank = std::max(h->rowsPerRank, 1);
+    src.counts = h->pairCounts; src.cap = h->pairCap; src.world = h->world; src.rank = h->rank; src.ownBegin = h->ownBegin; src.ownEnd = h->ownEnd;
     const int repWarps = h->repBlocks * wb::repulse_warps(V);
     if (build) {
         // at least ~8 work units per resident warp, else the tail of the dynamic schedule dominates
@@ -543,9 +588,15 @@ void launch_step(wb_embedder* h, const PendingStep& slot) {
                                                                                  h->heavyPos, h->walkPartials + (size_t)repWarps * 3, h->ctrl));
             h->launches += 1;
         }
+    }
+    if (sharded) {   // every rank's pairs have landed in their owners' buffers, and every rank knows all counts
+        wb::k_exchange<<<1, 32, 0, s>>>(peers, ++h->epoch, 1, h->ctrl);
+        h->launches += 1;
+    }
+    if (build) {
         // pair list -> CSR of partners
         const int own = std::max(1, h->ownEnd - h->ownBegin);
-        const int pairBlocks = std::max(1, std::min(div_up(h->pairCap, 256), 148 * 8));
+        const int pairBlocks = std::max(1, std::min(div_up((int64_t)h->pairCap * h->world, 256), 148 * 8));
         const int scanBlocks = div_up(own, wb::kScanItems);
         wb::k_rep_count<<<pairBlocks, 256, 0, s>>>(src, h->repDeg, h->ctrl);
         wb::k_scan_sums<<<scanBlocks, 256, 0, s>>>(h->repDeg + h->ownBegin, own, h->scanSums, h->ctrl);
@@ -565,13 +616,21 @@ void launch_step(wb_embedder* h, const PendingStep& slot) {
     if (ownBlocks > 0) {
         WB_DISPATCH_V(V, wb::k_step_fused<V><<<ownBlocks, 256, 0, s>>>(h->x, h->iw, h->rowPtr, h->col, h->repRowPtr, h->repCol, h->ownBegin, h->ownEnd, h->vertsPerBlock, fp,
                                                                         h->dyn, h->hubSlot, h->hubD, h->hubF, h->xNew, h->mom1, h->mom2, h->force,
-                                                                        h->blockPartials, h->ctrl));
+                                                                        rowsOut, h->ctrl));
+    }
+    if (sharded) {   // every rank's sum rows have arrived everywhere
+        wb::k_exchange<<<1, 32, 0, s>>>(peers, ++h->epoch, 0, h->ctrl);
+        h->launches += 1;
     }
     wb::k_reduce_rows<<<h->cols, 256, 0, s>>>(h->blockPartials, h->numBlockRows, h->cols, h->forceSums, h->ctrl);
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[3], s));
     const int obsBegin = h->ownBegin / wb::kObsTile, obsEnd = div_up(h->ownEnd, wb::kObsTile);
     if (obsEnd > obsBegin)
-        WB_DISPATCH_V(V, wb::k_recentre_observe<V><<<obsEnd - obsBegin, 256, 0, s>>>(h->x, h->xNew, n, obsBegin, h->dim, h->forceSums, h->obsPartials, h->momentStride, h->momentPartials, h->ctrl));
+        WB_DISPATCH_V(V, wb::k_recentre_observe<V><<<obsEnd - obsBegin, 256, 0, s>>>(h->x, xOut, h->xNew, n, obsBegin, h->dim, h->forceSums, obsOut, h->momentStride, momOut, h->ctrl));
+    if (sharded) {   // every replica of x is complete, every rank holds all observation tiles
+        wb::k_exchange<<<1, 32, 0, s>>>(peers, ++h->epoch, 0, h->ctrl);
+        h->launches += 1;
+    }
     wb::TailPolicy pol{(float)h->opt.edge_length, h->halfSigmaLimit, h->dim, h->mortonBits};
     wb::k_step_tail<<<1, 1024, 0, s>>>(h->forceSums, h->cols, h->obsPartials, h->numObsTiles, h->momentPartials, h->numMomentTiles, h->momentCount, n, h->walkPartials, repWarps + h->numHeavy,
                                         pol, h->quant, h->ctrl, h->stats);
@@ -580,6 +639,41 @@ void launch_step(wb_embedder* h, const PendingStep& slot) {
     WB_CUDA(cudaGetLastError());
     WB_CUDA(cudaMemcpyAsync(slot.host->sums, h->stats, sizeof(double) * h->statsTotal, cudaMemcpyDeviceToHost, s));
     WB_CUDA(cudaEventRecord(slot.done, s));
+}
+
+// Sharded run: export this rank's buffers and map everybody else's (CUDA IPC; the handles travel through one small NCCL all-gather,
+// which is all NCCL is used for).  all = false: only the pair buffers (they are reallocated when they overflow).
+void map_peers(wb_embedder* h, bool all) {
+    struct Handles { cudaIpcMemHandle_t mail, x, pairs; };
+    Handles mine{};
+    if (all) {
+        WB_CUDA(cudaIpcGetMemHandle(&mine.mail, h->mail));
+        WB_CUDA(cudaIpcGetMemHandle(&mine.x, h->x));
+    }
+    WB_CUDA(cudaIpcGetMemHandle(&mine.pairs, h->pairBuf));
+    char* dSend = dalloc<char>(sizeof(Handles));
+    char* dRecv = dalloc<char>(sizeof(Handles) * h->world);
+    std::vector<Handles> got(h->world);
+    cudaError_t err = cudaMemcpyAsync(dSend, &mine, sizeof(Handles), cudaMemcpyHostToDevice, h->stream);
+    bool ncclOk = true;
+    if (err == cudaSuccess) ncclOk = nccl().allGather(dSend, dRecv, sizeof(Handles), ncclChar, h->comm, h->stream) == ncclSuccess;
+    if (err == cudaSuccess && ncclOk) err = cudaMemcpyAsync(got.data(), dRecv, sizeof(Handles) * h->world, cudaMemcpyDeviceToHost, h->stream);
+    if (err == cudaSuccess && ncclOk) err = cudaStreamSynchronize(h->stream);
+    cudaFree(dSend); cudaFree(dRecv);
+    if (!ncclOk) throw std::runtime_error("ncclAllGather (IPC handles) failed");
+    WB_CUDA(err);
+    for (int p = 0; p < h->world; ++p) {
+        if (p == h->rank) continue;
+        void* ptr = nullptr;
+        if (all) {
+            WB_CUDA(cudaIpcOpenMemHandle(&ptr, got[p].mail, cudaIpcMemLazyEnablePeerAccess)); h->peerMail[p] = static_cast<char*>(ptr);
+            WB_CUDA(cudaIpcOpenMemHandle(&ptr, got[p].x, cudaIpcMemLazyEnablePeerAccess)); h->peerX[p] = static_cast<float4*>(ptr);
+        }
+        if (h->peerPairsOpen) cudaIpcCloseMemHandle(h->peerPairs[p]);
+        WB_CUDA(cudaIpcOpenMemHandle(&ptr, got[p].pairs, cudaIpcMemLazyEnablePeerAccess)); h->peerPairs[p] = static_cast<int2*>(ptr);
+    }
+    if (all) h->peersOpen = true;
+    h->peerPairsOpen = true;
 }
 
 void enqueue_step(wb_embedder* h, double learningRate) {
@@ -608,7 +702,19 @@ void recover_from_overflow(wb_embedder* h, double needed) {
     WB_CUDA(cudaStreamSynchronize(h->stream));
     const double want = std::max(2.0 * needed, 2.0 * (double)h->pairCap);
     if (want > 1.0e9) throw std::runtime_error("repulsion pair list exceeds 1e9 pairs");
+    if (h->world > 1 && h->peerPairsOpen) {      // nobody may still hold a mapping of a buffer that is about to be freed
+        for (int p = 0; p < h->world; ++p)
+            if (p != h->rank) cudaIpcCloseMemHandle(h->peerPairs[p]);
+        h->peerPairsOpen = false;
+        char* token = dalloc<char>(h->world);      // host-visible barrier: everybody has closed before anybody frees
+        const bool ok = nccl().allGather(token + h->rank, token, 1, ncclChar, h->comm, h->stream) == ncclSuccess;
+        const cudaError_t err = cudaStreamSynchronize(h->stream);
+        cudaFree(token);
+        if (!ok) throw std::runtime_error("ncclAllGather (barrier) failed");
+        WB_CUDA(err);
+    }
     allocate_pair_list(h, (unsigned int)want);
+    if (h->world > 1) map_peers(h, false);       // collective: every rank sees the same overflow at the same step
     invalidate_list(h);
     std::deque<PendingStep> again;
     again.swap(h->pending);
@@ -625,6 +731,7 @@ void collect_step(wb_embedder* h, wb_step_stats* out) {
     for (;;) {
         WB_CUDA(cudaEventSynchronize(slot.done));
         if (slot.trivial || slot.host->sums[cols + 8] == 0.0) break;
+        if (slot.host->sums[cols + 8] != 1.0) throw std::runtime_error("sharded step: a peer did not reach the barrier (timeout)");
         recover_from_overflow(h, slot.host->sums[cols + 9]);
     }
     h->pending.pop_front();
@@ -1010,8 +1117,39 @@ int wb_comm_unique_id(char* id128) {
 }
 
 int wb_comm_init(wb_embedder* h, const char* id128, int32_t rank, int32_t world) {
-    if (h && (!id128 || world < 1 || rank < 0 || rank >= world)) return fail(WB_ERR_INVALID, "wb_comm_init: bad arguments");
-    if (h && world > 1) return fail(WB_ERR_UNSUPPORTED, "wb_comm_init: the sharded step is being rebuilt");
+    if (h && (!id128 || world < 1 || world > wb::kMaxRanks || rank < 0 || rank >= world)) return fail(WB_ERR_INVALID, "wb_comm_init: bad arguments (1 <= world <= 8)");
+    if (h && h->comm) return fail(WB_ERR_INVALID, "wb_comm_init: already initialised");
+    if (h && !h->pending.empty()) return fail(WB_ERR_INVALID, "wb_comm_init: steps in flight");
+    return guarded(h, [&] {
+        if (world == 1) return;
+        ncclUniqueId id;
+        std::memcpy(&id, id128, sizeof(id));
+        if (!nccl().ok) throw std::runtime_error("libnccl.so.2 could not be loaded");
+        if (nccl().commInitRank(&h->comm, world, id, rank) != ncclSuccess) throw std::runtime_error("ncclCommInitRank failed");
+        h->world = world;
+        h->rank = rank;
+        // whole block rows and whole observation tiles per rank, so that the global rows / tiles have exactly one writer
+        const int64_t align = std::lcm((int64_t)h->vertsPerBlock, (int64_t)wb::kObsTile);
+        h->rowsPerRank = (int)(((int64_t)div_up(std::max(h->n, 1), world) + align - 1) / align * align);
+        h->ownBegin = (int)std::min<int64_t>(h->n, (int64_t)rank * h->rowsPerRank);
+        h->ownEnd = (int)std::min<int64_t>(h->n, (int64_t)h->ownBegin + h->rowsPerRank);
+        // repulsion queries: blocks of kRepBlockChunks chunks of the sorted order dealt round-robin to the ranks
+        const int blocksPerRank = div_up(div_up(div_up(std::max(h->n, 1), 32), wb::kRepBlockChunks), world);
+        h->repLayout = wb::RepLayout{world, rank, blocksPerRank * wb::kRepBlockChunks * 32};
+        // one segment per producing rank; a rank receives ~1 / world of all pairs, spread over `world` segments
+        allocate_pair_list(h, std::max(1024u, (unsigned int)(((uint64_t)h->pairCap * 2 + world - 1) / world)));
+        WB_CUDA(cudaMemsetAsync(h->mail, 0, wb::kMailData, h->stream));
+        WB_CUDA(cudaStreamSynchronize(h->stream));
+        map_peers(h, true);
+        invalidate_list(h);
+        WB_CUDA(cudaStreamSynchronize(h->stream));
+    });
+}
+
+int wb_get_partition(wb_embedder* h, int32_t* begin, int32_t* end) {
+    if (!h || !begin || !end) return fail(WB_ERR_INVALID, "wb_get_partition: null argument");
+    *begin = h->ownBegin;
+    *end = h->ownEnd;
     return WB_OK;
 }
 

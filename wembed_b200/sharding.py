@@ -10,15 +10,27 @@ from __future__ import annotations
 import numpy as np
 
 
-def partition(n: int, world: int) -> list[tuple[int, int]]:
-    """[begin, end) of every rank: contiguous ranges of ceil(n / world) vertices (wb_comm_init)."""
-    rows = -(-max(n, 1) // world)
+def rows_per_rank(n: int, world: int, d: int) -> int:
+    """Mirror of wb_comm_init: ceil(n / world) rounded up to whole block rows of the fused kernel and whole observation tiles, so
+    every global row / tile of partial sums has exactly one writer."""
+    import math
+    v = (d + 3) // 4
+    lanes = 1 if v <= 1 else 2 if v <= 2 else 4 if v <= 4 else 8
+    pass_verts = 256 // lanes
+    passes = -(-max(n, 1) // pass_verts)
+    verts_per_block = pass_verts * max(1, -(-passes // (148 * 16)))
+    align = math.lcm(verts_per_block, 1024)
+    return -(-(-(-max(n, 1) // world)) // align) * align
+
+
+def partition(n: int, world: int, d: int = 4) -> list[tuple[int, int]]:
+    """[begin, end) of every rank (DeviceEmbedder.partition() returns the library's own answer)."""
+    rows = rows_per_rank(n, world, d)
     return [(min(n, r * rows), min(n, r * rows + rows)) for r in range(world)]
 
 
-def owner_of(v, n: int, world: int):
-    rows = -(-max(n, 1) // world)
-    return np.asarray(v) // rows
+def owner_of(v, n: int, world: int, d: int = 4):
+    return np.asarray(v) // rows_per_rank(n, world, d)
 
 
 def exchange_unique_id(make_id, rank: int, world: int, device=None) -> bytes:
@@ -41,4 +53,4 @@ def shard_embedder(dev, rank: int, world: int, device=None):
     from . import cabi
     uid = exchange_unique_id(cabi.comm_unique_id, rank, world, device)
     dev.comm_init(uid, rank, world)
-    return partition(dev.n, world)[rank]
+    return dev.partition()
