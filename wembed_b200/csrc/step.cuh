@@ -176,19 +176,86 @@ __global__ void __launch_bounds__(256) k_rep_fill(const PairSource src, int* __r
 }
 
 // rows of the pair list -> ascending partner order (the list is appended to by whoever finds a pair first, so the order inside a
-// row is arbitrary; sorting it makes the floating-point sum of a vertex' repulsive terms a fixed-order sum).  One thread per vertex,
-// insertion sort in place: rows have a handful of entries.  Hub rows (summed in fixed point by k_hub_rows) are left alone.
+// row is arbitrary; sorting it makes the floating-point sum of a vertex' repulsive terms a fixed-order sum).  Rows of up to
+// kShortRow entries - nearly all - are sorted by one thread each (insertion sort in registers); longer ones (dense phases early in a
+// run: hundreds of partners per vertex for a few steps) are queued and sorted by one warp each in shared memory (bitonic network),
+// or in global memory beyond kWarpSortMax entries.  Hub rows (summed in fixed point by k_hub_rows) are left alone.
+constexpr int kShortRow = 8;
+constexpr int kWarpSortMax = 1024;
 __global__ void __launch_bounds__(256) k_rep_sort_rows(const int* __restrict__ repRowPtr, int* __restrict__ repCol, int ownBegin, int ownEnd,
-                                                       const int* __restrict__ hubSlot, const StepCtrl* __restrict__ ctrl) {
+                                                       const int* __restrict__ hubSlot, int* __restrict__ longRows, int* __restrict__ numLong,
+                                                       const StepCtrl* __restrict__ ctrl) {
     if (build_skipped(ctrl, 0)) return;
     const int v = ownBegin + blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= ownEnd || (hubSlot && hubSlot[v] >= 0)) return;
-    const int b = repRowPtr[v], e = repRowPtr[v + 1];
-    for (int i = b + 1; i < e; ++i) {
-        const int key = repCol[i];
-        int j = i - 1;
-        while (j >= b && repCol[j] > key) { repCol[j + 1] = repCol[j]; --j; }
-        repCol[j + 1] = key;
+    const int b = repRowPtr[v], len = repRowPtr[v + 1] - b;
+    if (len < 2) return;
+    if (len > kShortRow) { longRows[atomicAdd(numLong, 1)] = v; return; }
+    int key[kShortRow];
+#pragma unroll
+    for (int i = 0; i < kShortRow; ++i) key[i] = i < len ? repCol[b + i] : 0x7fffffff;
+    // odd-even transposition network on kShortRow registers (fixed indices: stays in registers)
+#pragma unroll
+    for (int round = 0; round < kShortRow; ++round) {
+#pragma unroll
+        for (int i = round & 1; i + 1 < kShortRow; i += 2) {
+            const int lo = min(key[i], key[i + 1]), hi = max(key[i], key[i + 1]);
+            key[i] = lo; key[i + 1] = hi;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kShortRow; ++i)
+        if (i < len) repCol[b + i] = key[i];
+}
+// one warp per queued row; rows are taken from the queue in any order (each row is sorted independently).  Up to kWarpSortMax entries:
+// bitonic network on a padded copy in shared memory.  Beyond: rank sort through `scratch` (partner ids of a row are distinct, so
+// the rank of an entry = the number of smaller entries), O(len^2 / 32) per warp - such rows only exist for a few steps of a dense phase.
+__global__ void __launch_bounds__(256) k_rep_sort_long(const int* __restrict__ repRowPtr, int* __restrict__ repCol, int* __restrict__ scratch,
+                                                       const int* __restrict__ longRows, const int* __restrict__ numLong, int* __restrict__ cursor,
+                                                       const StepCtrl* __restrict__ ctrl) {
+    if (build_skipped(ctrl, 0)) return;
+    __shared__ int buf[8][kWarpSortMax];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int total = *numLong;
+    for (;;) {
+        int at = 0;
+        if (lane == 0) at = atomicAdd(cursor, 1);
+        at = __shfl_sync(0xffffffffu, at, 0);
+        if (at >= total) break;
+        const int v = longRows[at];
+        const int b = repRowPtr[v], len = repRowPtr[v + 1] - b;
+        if (len <= kWarpSortMax) {
+            int size = 32;
+            while (size < len) size <<= 1;
+            int* keys = buf[warp];
+            for (int i = lane; i < size; i += 32) keys[i] = i < len ? repCol[b + i] : 0x7fffffff;
+            __syncwarp();
+            for (int k = 2; k <= size; k <<= 1) {
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int i = lane; i < size; i += 32) {
+                        const int partner = i ^ j;
+                        if (partner > i) {
+                            const bool up = (i & k) == 0;
+                            const int a = keys[i], c = keys[partner];
+                            if ((a > c) == up) { keys[i] = c; keys[partner] = a; }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            for (int i = lane; i < len; i += 32) repCol[b + i] = keys[i];
+        } else {
+            for (int i = lane; i < len; i += 32) {
+                const int key = repCol[b + i];
+                int rank = 0;
+                for (int k = 0; k < len; ++k) rank += (int)(repCol[b + k] < key);
+                scratch[b + rank] = key;
+            }
+            __syncwarp();
+            __threadfence_block();
+            for (int i = lane; i < len; i += 32) repCol[b + i] = scratch[b + i];
+        }
+        __syncwarp();
     }
 }
 
@@ -202,8 +269,8 @@ __global__ void __launch_bounds__(256) k_rep_sort_rows(const int* __restrict__ r
 // A vertex walks ONE list of partners: its CSR row (attractionForce, :140-172) followed by its row of the repulsion pair list
 // (repellingForce, :174-210).  Both kinds of pair share the arithmetic - distance, pair weight ws = iw_v iw_u, the hinge at
 // dist ws = L - and differ in the side of the hinge they act on and in the sign of the force, so the loop body is branch-free.
-// Terms are fp32; the four terms of a batch are added in fp32 and the batch sum goes into an fp64 accumulator, in list order (rows of
-// the pair list are sorted), so the sums are reproducible bit for bit.
+// Terms are fp32 and are added one by one to fp64 accumulators in list order (rows of the pair list are sorted), so the sums are
+// reproducible bit for bit - and independent of the list's skin, because a listed pair beyond the hinge adds an exact zero.
 // Per-pair arithmetic uses the single-instruction special functions (rsqrt.approx, rcp.approx: relative error <= 2^-22, the size of
 // the fp32 rounding of the terms themselves); one-dimensional embeddings take an IEEE path with exact +-1 unit vectors.
 //
@@ -232,9 +299,20 @@ __device__ __forceinline__ float chunk_dist2(float4 a, float4 b) {
 #ifndef WB_FUSED_MINBLOCKS
 #define WB_FUSED_MINBLOCKS 4
 #endif
+#ifndef WB_EDGE_WS
+#define WB_EDGE_WS 1
+#endif
+// ws of every CSR entry (recomputed by wb_set_weights)
+__global__ void k_edge_weights(const int* __restrict__ rowPtr, const int* __restrict__ col, const float* __restrict__ iw, int n,
+                               float* __restrict__ edgeWs) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const float iwv = iw[v];
+    for (int e = rowPtr[v]; e < rowPtr[v + 1]; ++e) edgeWs[e] = iwv * iw[col[e]];
+}
 template <int V>
 __global__ void __launch_bounds__(256, WB_FUSED_MINBLOCKS)
-k_step_fused(const float4* __restrict__ x, const float* __restrict__ iw, const int* __restrict__ rowPtr, const int* __restrict__ col,
+k_step_fused(const float4* __restrict__ x, const float* __restrict__ iw, const float* __restrict__ edgeWs, const int* __restrict__ rowPtr, const int* __restrict__ col,
              const int* __restrict__ repRowPtr, const int* __restrict__ repCol, int rangeBegin, int rangeEnd, int vertsPerBlock,
              const ForceParams fp, const StepDyn* __restrict__ dynp, const int* __restrict__ hubSlot, const double* __restrict__ hubD,
              const long long* __restrict__ hubF, float4* __restrict__ xNew, float4* __restrict__ mom1, float4* __restrict__ mom2,
@@ -269,8 +347,8 @@ k_step_fused(const float4* __restrict__ x, const float* __restrict__ iw, const i
             if (chunkLane) xv = __ldg(x + at);
             iwv = __ldg(iw + v);
             hub = hubSlot ? __ldg(hubSlot + v) : -1;
-            e = __ldg(rowPtr + v); re = repRowPtr[v];
-            const int lenR = repRowPtr[v + 1] - re;
+            e = __ldg(rowPtr + v); re = __ldg(repRowPtr + v);
+            const int lenR = __ldg(repRowPtr + v + 1) - re;
             sumEntries += c == 0 ? lenR : 0;
             if (hub < 0) { lenA = __ldg(rowPtr + v + 1) - e; total = lenA + lenR; }
         }
@@ -289,12 +367,19 @@ k_step_fused(const float4* __restrict__ x, const float* __restrict__ iw, const i
                 const int idx = i + j;
                 has[j] = idx < total;
                 isRep[j] = idx >= lenA;
-                u[j] = has[j] ? (isRep[j] ? repCol[re + idx - lenA] : __ldg(col + e + idx)) : 0;
+                u[j] = has[j] ? (isRep[j] ? __ldg(repCol + re + idx - lenA) : __ldg(col + e + idx)) : 0;
             }
 #pragma unroll
             for (int j = 0; j < B; ++j) r[j] = (has[j] && chunkLane) ? __ldg(xc + (int64_t)u[j] * V) : xv;
+#if WB_EDGE_WS
+            // the pair weight of a graph edge never changes (weights are constant during a run, WembedEmbedder.cpp:121-131): it is read
+            // from a per-CSR-entry array next to `col` (coalesced stream) instead of gathering iw[u] (a second random access per edge)
+#pragma unroll
+            for (int j = 0; j < B; ++j) ws[j] = has[j] ? (isRep[j] ? iwv * __ldg(iw + u[j]) : __ldg(edgeWs + e + i + j)) : 0.f;
+#else
 #pragma unroll
             for (int j = 0; j < B; ++j) ws[j] = has[j] ? iwv * __ldg(iw + u[j]) : 0.f;
+#endif
 #pragma unroll
             for (int j = 0; j < B; ++j) dd[j] = chunkLane ? chunk_dist2(r[j], xv) : 0.f;
 #pragma unroll
@@ -302,7 +387,8 @@ k_step_fused(const float4* __restrict__ x, const float* __restrict__ iw, const i
 #pragma unroll
                 for (int j = 0; j < B; ++j) dd[j] += __shfl_xor_sync(0xffffffffu, dd[j], o);
             }
-            float bx = 0.f, by = 0.f, bz = 0.f, bw = 0.f, blA = 0.f, blR = 0.f;
+            // every term goes into the fp64 accumulators by itself, in list order: an entry that is listed but inactive (beyond the
+            // hinge: lists are built with a skin) adds an exact zero, so the sums do not depend on what else is listed
             if (V > 1 || fp.dim > 1) {
 #pragma unroll
                 for (int j = 0; j < B; ++j) {
@@ -316,11 +402,11 @@ k_step_fused(const float4* __restrict__ x, const float* __restrict__ iw, const i
                     nPairs += (int)(has[j] && isRep[j] && inside);
                     const bool act = has[j] && dd[j] > 0.f && (isRep[j] ? inside : !inside);
                     const float sc = act ? (isRep[j] ? -fp.repulsionScale : fp.attractionScale) * ws[j] * inv : 0.f;
-                    bx = fmaf(sc, r[j].x - xv.x, bx); by = fmaf(sc, r[j].y - xv.y, by);
-                    bz = fmaf(sc, r[j].z - xv.z, bz); bw = fmaf(sc, r[j].w - xv.w, bw);
+                    acc[0] += (double)(sc * (r[j].x - xv.x)); acc[1] += (double)(sc * (r[j].y - xv.y));
+                    acc[2] += (double)(sc * (r[j].z - xv.z)); acc[3] += (double)(sc * (r[j].w - xv.w));
                     const float over = fmaf(-L, rcp_approx(ws[j]), dist);               // dist - L / ws
-                    blA += (act && !isRep[j]) ? over : 0.f;
-                    blR += (act && isRep[j]) ? -over : 0.f;
+                    lossA += (double)((act && !isRep[j]) ? over : 0.f);
+                    lossR += (double)((act && isRep[j]) ? -over : 0.f);
                 }
             } else {                                            // one dimension: exact +-1 unit vectors (VectorOperations.hpp:19-24), IEEE arithmetic
 #pragma unroll
@@ -332,16 +418,14 @@ k_step_fused(const float4* __restrict__ x, const float* __restrict__ iw, const i
                     if (isRep[j]) {
                         if (!inside) continue;
                         ++nPairs;
-                        bx += copysignf(fp.repulsionScale * ws[j], xv.x - r[j].x);
-                        blR += L / ws[j] - dist;
+                        acc[0] += (double)copysignf(fp.repulsionScale * ws[j], xv.x - r[j].x);
+                        lossR += (double)(L / ws[j] - dist);
                     } else if (!inside) {
-                        bx += copysignf(fp.attractionScale * ws[j], r[j].x - xv.x);
-                        blA += dist - L / ws[j];
+                        acc[0] += (double)copysignf(fp.attractionScale * ws[j], r[j].x - xv.x);
+                        lossA += (double)(dist - L / ws[j]);
                     }
                 }
             }
-            acc[0] += (double)bx; acc[1] += (double)by; acc[2] += (double)bz; acc[3] += (double)bw;
-            lossA += (double)blA; lossR += (double)blR;
         }
         if (valid && hub >= 0) {                               // hub rows were summed by k_hub_rows
             const double* hd = hubD + (int64_t)hub * hub_doubles(V);

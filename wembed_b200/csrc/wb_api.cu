@@ -112,7 +112,8 @@ struct wb_embedder {
     unsigned int* pairCounts = nullptr;   // counts matrix [kMaxRanks][kMaxRanks] inside `mail`
     char* mail = nullptr;                 // [flags | counts | block sum rows | observation tiles | moment tiles] (step.cuh: k_exchange)
     size_t mailBytes = 0;
-    int *repDeg = nullptr, *repRowPtr = nullptr, *repCol = nullptr, *scanSums = nullptr;
+    int *repDeg = nullptr, *repRowPtr = nullptr, *repCol = nullptr, *scanSums = nullptr, *longRows = nullptr, *longCount = nullptr;
+    float* edgeWs = nullptr;              // ws(v,u) = iw_v * iw_u of every CSR entry
     int scanBlocks = 0;
     float skinMax = 0.f, reuseTarget = 4.f;
     int nextRebuild = 1;                  // what the host knows about the next step: 1 rebuilds (or unknown), 0 reuses the list
@@ -210,7 +211,7 @@ void free_all(wb_embedder* h) {
         }
         h->peersOpen = h->peerPairsOpen = false;
     }
-    F(h->ctrl); F(h->dyn); F(h->pairBuf); F(h->mail); F(h->repDeg); F(h->repRowPtr); F(h->repCol); F(h->scanSums);
+    F(h->ctrl); F(h->dyn); F(h->pairBuf); F(h->mail); F(h->repDeg); F(h->repRowPtr); F(h->repCol); F(h->scanSums); F(h->longRows); F(h->longCount); F(h->edgeWs);
     F(h->chunkCounter); F(h->heavyVertex); F(h->heavySlot); F(h->heavyPos); F(h->hubVertex); F(h->hubSlot); F(h->hubD); F(h->hubF); F(h->mtScratch);
     F(h->keysIn); F(h->keysOut); F(h->valsIn); F(h->valsOut); F(h->cubTemp); F(h->quant); F(h->ids); F(h->blk); F(h->blkH);
     for (int l = 0; l < wb::kMaxLevels; ++l) { F(h->lvlLo[l]); if (l > 0) F(h->lvlHi[l]); F(h->lvlBound[l]); }
@@ -387,6 +388,10 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
     h->repRowPtr = dalloc<int>(h->rowsAlloc + 1 + 8);
     WB_CUDA(cudaMemsetAsync(h->repDeg, 0, sizeof(int) * (h->rowsAlloc + 8), h->stream));
     WB_CUDA(cudaMemsetAsync(h->repRowPtr, 0, sizeof(int) * (h->rowsAlloc + 1 + 8), h->stream));
+    h->longRows = dalloc<int>(std::max(n, 1));
+    h->longCount = dalloc<int>(2);        // [rows queued, cursor of the sorting warps]
+    h->edgeWs = dalloc<float>(h->numDirected + 8);
+    if (h->numDirected) wb::k_fill<float><<<div_up(h->numDirected, 256), 256, 0, h->stream>>>(h->edgeWs, h->numDirected, 1.0f);
     h->scanBlocks = div_up(std::max(n, 1), wb::kScanItems);
     h->scanSums = dalloc<int>(h->scanBlocks + 1);
     choose_fixed_scales(h, 1.0, 1.0);
@@ -603,8 +608,10 @@ void launch_step(wb_embedder* h, const PendingStep& slot) {
         wb::k_scan_offsets<<<1, 1024, 0, s>>>(h->scanSums, scanBlocks, h->ctrl);
         wb::k_scan_apply<<<scanBlocks, 256, 0, s>>>(h->repDeg + h->ownBegin, own, h->scanSums, scanBlocks, h->repRowPtr + h->ownBegin, h->ctrl);
         wb::k_rep_fill<<<pairBlocks, 256, 0, s>>>(src, h->repDeg, h->repRowPtr, h->repCol, h->ctrl);
-        wb::k_rep_sort_rows<<<div_up(own, 256), 256, 0, s>>>(h->repRowPtr, h->repCol, h->ownBegin, h->ownEnd, h->hubSlot, h->ctrl);
-        h->launches += 6;
+        WB_CUDA(cudaMemsetAsync(h->longCount, 0, 2 * sizeof(int), s));
+        wb::k_rep_sort_rows<<<div_up(own, 256), 256, 0, s>>>(h->repRowPtr, h->repCol, h->ownBegin, h->ownEnd, h->hubSlot, h->longRows, h->longCount, h->ctrl);
+        wb::k_rep_sort_long<<<148 * 4, 256, 0, s>>>(h->repRowPtr, h->repCol, reinterpret_cast<int*>(h->pairBuf), h->longRows, h->longCount, h->longCount + 1, h->ctrl);
+        h->launches += 7;
     }
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[2], s));
     if (h->numHubs) {
@@ -614,7 +621,7 @@ void launch_step(wb_embedder* h, const PendingStep& slot) {
     }
     const int ownBlocks = div_up(std::max(0, h->ownEnd - h->ownBegin), h->vertsPerBlock);
     if (ownBlocks > 0) {
-        WB_DISPATCH_V(V, wb::k_step_fused<V><<<ownBlocks, 256, 0, s>>>(h->x, h->iw, h->rowPtr, h->col, h->repRowPtr, h->repCol, h->ownBegin, h->ownEnd, h->vertsPerBlock, fp,
+        WB_DISPATCH_V(V, wb::k_step_fused<V><<<ownBlocks, 256, 0, s>>>(h->x, h->iw, h->edgeWs, h->rowPtr, h->col, h->repRowPtr, h->repCol, h->ownBegin, h->ownEnd, h->vertsPerBlock, fp,
                                                                         h->dyn, h->hubSlot, h->hubD, h->hubF, h->xNew, h->mom1, h->mom2, h->force,
                                                                         rowsOut, h->ctrl));
     }
@@ -1009,6 +1016,7 @@ int wb_set_weights(wb_embedder* h, const double* weights) {
         std::vector<float> iw(n);
         for (int v = 0; v < n; ++v) iw[v] = (float)(1.0 / std::pow(weights[v], 1.0 / (double)h->dim));
         WB_CUDA(cudaMemcpyAsync(h->iw, iw.data(), sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+        wb::k_edge_weights<<<div_up(n, 256), 256, 0, h->stream>>>(h->rowPtr, h->col, h->iw, n, h->edgeWs);
         WB_CUDA(cudaStreamSynchronize(h->stream));
         const double minW = *std::min_element(h->weights.begin(), h->weights.end());
         const double maxW = *std::max_element(h->weights.begin(), h->weights.end());
