@@ -120,6 +120,10 @@ class Graph {
     std::vector<Edge> getEdgeList() const;            /* every undirected edge once, src < dst */
     std::string toString() const;
 
+    /* Additions of this build (not in the reference): read-only views of the CSR the embedder uploads, valid while the Graph lives. */
+    const std::int32_t* csrOffsets() const;           /* getNumVertices() + 1 entries */
+    const std::int32_t* csrTargets() const;           /* 2 * getNumEdges() entries, every row ascending */
+
    private:
     friend Embedder createEmbedder(const Graph& g, const Options& options);
     std::unique_ptr<impl::EmbeddingGraph> _graph;

@@ -174,3 +174,17 @@ class CpuEmbedder:
             if c <= cap:
                 return out[:c].copy()
             cap = int(c)
+
+
+def ref_read_edge_list(path, comment="#", delimiter=" "):
+    """The reference's GraphIO::readEdgeList + Graph construction on a file; returns (row_ptr, col) of the graph it built."""
+    lib = _lib("ref")
+    lib.ref_read_edge_list.restype = C.c_int32
+    lib.ref_read_edge_list.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int64)]
+    lib.ref_graph_csr.restype = None
+    lib.ref_graph_csr.argtypes = [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    directed = C.c_int64()
+    n = lib.ref_read_edge_list(str(path).encode(), comment.encode(), delimiter.encode(), C.byref(directed))
+    rp, col = np.empty(n + 1, np.int32), np.empty(max(1, directed.value), np.int32)
+    lib.ref_graph_csr(_ip(rp), _ip(col))
+    return rp, col[: directed.value]

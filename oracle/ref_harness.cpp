@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "Graph.hpp"
+#include "GraphIO.hpp"
 #include "GraphHierarchy.hpp"
 #include "LabelPropagation.hpp"
 #include "LayeredEmbedder.hpp"
@@ -222,6 +223,20 @@ int64_t ref_layered_run(int64_t m, const int32_t* src, const int32_t* dst, const
     stats8[ORC_REL_DISP] = emb.getLastRelDisplacement();
     stats8[ORC_ITERATION] = static_cast<double>(emb.currentIteration);
     return emb.currentIteration;
+}
+
+// The reference's own edge-list reader (GraphIO::readEdgeList, GraphIO.cpp:10-51) + Graph construction (Graph.cpp:87-150): the graph
+// it builds is kept until ref_graph_csr copies it out.  Returns the number of vertices; *directed = CSR entries.
+static Graph g_fileGraph;
+int32_t ref_read_edge_list(const char* path, const char* comment, const char* delimiter, int64_t* directed) {
+    g_fileGraph = GraphIO::readEdgeList(path, comment, delimiter);
+    *directed = 2 * static_cast<int64_t>(g_fileGraph.getNumEdges());
+    return g_fileGraph.getNumVertices();
+}
+void ref_graph_csr(int32_t* row_ptr, int32_t* col) {
+    const int n = g_fileGraph.getNumVertices();
+    for (int v = 0; v <= n; ++v) row_ptr[v] = g_fileGraph.nodes[v].firstEdge;
+    for (std::size_t e = 0; e < g_fileGraph.edges.size(); ++e) col[e] = g_fileGraph.edges[e].neighbour;
 }
 
 }  // extern "C"

@@ -15,10 +15,11 @@ __device__ __forceinline__ long long to_fixed(float term, double scale) { return
 
 // ---------------------------------------------------------------------------------------------
 // First kernel of every step: resets the work counters of a build.
-__global__ void k_step_begin(StepCtrl* ctrl, unsigned int* pairCounts /* this rank's row of the counts matrix */, int world, int* chunkCounter) {
+__global__ void k_step_begin(StepCtrl* ctrl, unsigned int* pairCounts /* this rank's row of the counts matrix */, int world, int* chunkCounter,
+                             int* longCount /* [2]: queue of long pair-list rows, cursor */) {
     if (ctrl->overflow != 0 || ctrl->rebuild == 0) return;
     if ((int)threadIdx.x < world) pairCounts[threadIdx.x] = 0u;
-    if (threadIdx.x == 0) *chunkCounter = 0;
+    if (threadIdx.x == 0) { *chunkCounter = 0; longCount[0] = 0; longCount[1] = 0; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -266,11 +267,11 @@ __global__ void __launch_bounds__(256) k_rep_sort_long(const int* __restrict__ r
 // touches - its own row, the partners' rows, the force, the Adam moments.  For one partner the G lanes read its row with ONE
 // coalesced access (16 B per lane), add their partial squared distances with log2(G) shuffles and each accumulates its own four
 // force components; nothing has to be reduced at the end and every lane is busy in the optimizer epilogue.
-// A vertex walks ONE list of partners: its CSR row (attractionForce, :140-172) followed by its row of the repulsion pair list
-// (repellingForce, :174-210).  Both kinds of pair share the arithmetic - distance, pair weight ws = iw_v iw_u, the hinge at
-// dist ws = L - and differ in the side of the hinge they act on and in the sign of the force, so the loop body is branch-free.
-// Terms are fp32 and are added one by one to fp64 accumulators in list order (rows of the pair list are sorted), so the sums are
-// reproducible bit for bit - and independent of the list's skin, because a listed pair beyond the hinge adds an exact zero.
+// A vertex walks its CSR row (attractionForce, :140-172) and then its row of the repulsion pair list (repellingForce, :174-210); both
+// loops gather the partner's row and weight (iw is 4n bytes and stays in L2) and share the arithmetic - distance, pair weight
+// ws = iw_v iw_u, the hinge at dist ws = L.  Terms are fp32, the sums fp64, every sum is taken in a fixed order (rows of the pair list
+// are sorted), so a step is reproducible bit for bit - and independent of the list's skin, because a listed pair beyond the hinge
+// adds an exact zero.
 // Per-pair arithmetic uses the single-instruction special functions (rsqrt.approx, rcp.approx: relative error <= 2^-22, the size of
 // the fp32 rounding of the terms themselves); one-dimensional embeddings take an IEEE path with exact +-1 unit vectors.
 //
@@ -280,7 +281,6 @@ __host__ __device__ constexpr int attract_lanes(int V) { return V <= 1 ? 1 : (V 
 __host__ __device__ constexpr int pass_vertices(int V) { return 256 / attract_lanes(V); }
 __host__ __device__ constexpr int block_sums(int V) { return 4 + 4 * V; }         // doubles per block row; + one max column behind them
 constexpr int kHubThreshold = 96;         // CSR rows longer than this are summed by one block each (k_hub_rows)
-constexpr uint32_t kRepFlag = 0x80000000u;
 
 // per-hub record written by k_hub_rows: [attraction force (4V) | lossA | coincident partners | active pairs] as doubles and
 // [repulsion force (4V) | lossR] as fixed-point integers
@@ -299,20 +299,9 @@ __device__ __forceinline__ float chunk_dist2(float4 a, float4 b) {
 #ifndef WB_FUSED_MINBLOCKS
 #define WB_FUSED_MINBLOCKS 4
 #endif
-#ifndef WB_EDGE_WS
-#define WB_EDGE_WS 1
-#endif
-// ws of every CSR entry (recomputed by wb_set_weights)
-__global__ void k_edge_weights(const int* __restrict__ rowPtr, const int* __restrict__ col, const float* __restrict__ iw, int n,
-                               float* __restrict__ edgeWs) {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= n) return;
-    const float iwv = iw[v];
-    for (int e = rowPtr[v]; e < rowPtr[v + 1]; ++e) edgeWs[e] = iwv * iw[col[e]];
-}
 template <int V>
 __global__ void __launch_bounds__(256, WB_FUSED_MINBLOCKS)
-k_step_fused(const float4* __restrict__ x, const float* __restrict__ iw, const float* __restrict__ edgeWs, const int* __restrict__ rowPtr, const int* __restrict__ col,
+k_step_fused(const float4* __restrict__ x, const float* __restrict__ iw, const int* __restrict__ rowPtr, const int* __restrict__ col,
              const int* __restrict__ repRowPtr, const int* __restrict__ repCol, int rangeBegin, int rangeEnd, int vertsPerBlock,
              const ForceParams fp, const StepDyn* __restrict__ dynp, const int* __restrict__ hubSlot, const double* __restrict__ hubD,
              const long long* __restrict__ hubF, float4* __restrict__ xNew, float4* __restrict__ mom1, float4* __restrict__ mom2,
@@ -342,44 +331,36 @@ k_step_fused(const float4* __restrict__ x, const float* __restrict__ iw, const f
         float4 xv = zero4;
         float iwv = 1.f;
         double acc[4] = {0.0, 0.0, 0.0, 0.0}, lossA = 0.0, lossR = 0.0;
-        int nCoincident = 0, nPairs = 0, e = 0, lenA = 0, re = 0, total = 0, hub = -1;
+        int nCoincident = 0, nPairs = 0, e = 0, lenA = 0, re = 0, lenR = 0, hub = -1;
         if (valid) {
             if (chunkLane) xv = __ldg(x + at);
             iwv = __ldg(iw + v);
             hub = hubSlot ? __ldg(hubSlot + v) : -1;
             e = __ldg(rowPtr + v); re = __ldg(repRowPtr + v);
-            const int lenR = __ldg(repRowPtr + v + 1) - re;
+            lenR = __ldg(repRowPtr + v + 1) - re;
             sumEntries += c == 0 ? lenR : 0;
-            if (hub < 0) { lenA = __ldg(rowPtr + v + 1) - e; total = lenA + lenR; }
+            if (hub < 0) lenA = __ldg(rowPtr + v + 1) - e; else lenR = 0;
         }
-        // all G lanes of a vertex walk the same entries; the groups of a warp have different list lengths and the shuffles need every
-        // lane, so the warp iterates to the longest list of its groups (hub rows are pre-summed)
-        int len = total;
+        // ---- attraction over the CSR row (attractionForce, :140-172; neighbours ascending, B rows in flight).  All G lanes of a vertex
+        // walk the same entries; the groups of a warp have different row lengths and the shuffles need every lane, so the warp iterates
+        // to the longest row of its groups (hub rows are pre-summed).
+        int len = lenA;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
-        for (int i = 0; i < len; i += B) {                         // B partners in flight
-            bool has[B], isRep[B];
+        for (int i = 0; i < len; i += B) {
+            bool has[B];
             int u[B];
             float ws[B], dd[B];
             float4 r[B];
 #pragma unroll
             for (int j = 0; j < B; ++j) {
-                const int idx = i + j;
-                has[j] = idx < total;
-                isRep[j] = idx >= lenA;
-                u[j] = has[j] ? (isRep[j] ? __ldg(repCol + re + idx - lenA) : __ldg(col + e + idx)) : 0;
+                has[j] = i + j < lenA;
+                u[j] = has[j] ? __ldg(col + e + i + j) : 0;
             }
 #pragma unroll
             for (int j = 0; j < B; ++j) r[j] = (has[j] && chunkLane) ? __ldg(xc + (int64_t)u[j] * V) : xv;
-#if WB_EDGE_WS
-            // the pair weight of a graph edge never changes (weights are constant during a run, WembedEmbedder.cpp:121-131): it is read
-            // from a per-CSR-entry array next to `col` (coalesced stream) instead of gathering iw[u] (a second random access per edge)
-#pragma unroll
-            for (int j = 0; j < B; ++j) ws[j] = has[j] ? (isRep[j] ? iwv * __ldg(iw + u[j]) : __ldg(edgeWs + e + i + j)) : 0.f;
-#else
 #pragma unroll
             for (int j = 0; j < B; ++j) ws[j] = has[j] ? iwv * __ldg(iw + u[j]) : 0.f;
-#endif
 #pragma unroll
             for (int j = 0; j < B; ++j) dd[j] = chunkLane ? chunk_dist2(r[j], xv) : 0.f;
 #pragma unroll
@@ -387,46 +368,98 @@ k_step_fused(const float4* __restrict__ x, const float* __restrict__ iw, const f
 #pragma unroll
                 for (int j = 0; j < B; ++j) dd[j] += __shfl_xor_sync(0xffffffffu, dd[j], o);
             }
-            // every term goes into the fp64 accumulators by itself, in list order: an entry that is listed but inactive (beyond the
-            // hinge: lists are built with a skin) adds an exact zero, so the sums do not depend on what else is listed
+            // the terms of a batch are added in fp32 (their sum carries the same relative error as each term), the batch sum goes into
+            // the fp64 accumulator: one conversion + one DADD per component per batch.  (The CSR row is the same on every step, so
+            // this grouping is fixed.)
+            float bx = 0.f, by = 0.f, bz = 0.f, bw = 0.f, bl = 0.f;
             if (V > 1 || fp.dim > 1) {
 #pragma unroll
                 for (int j = 0; j < B; ++j) {
-                    // squared distances below FLT_MIN (dist < 1.1e-19) stay away from the flush-to-zero rsqrt: such a pair is inside
-                    // the hinge for certain; its direction is kept and dist is taken as d2 / 1.1e-19 (a repulsive pair that close but
-                    // not coincident - coordinates would have to be ~1e-19 themselves - gets a force scaled down accordingly)
-                    const float inv = rsqrt_approx(fmaxf(dd[j], kFltMin));
+                    // squared distances below FLT_MIN (dist < 1.1e-19) are neither coincident (that is d2 == 0 exactly, as with sqrtf)
+                    // nor can they exceed the edge length: they contribute nothing and stay away from the flush-to-zero rsqrt
+                    const float inv = rsqrt_approx(dd[j]);
                     const float dist = dd[j] * inv;
-                    const bool inside = dist * ws[j] <= L;                              // the hinge (:163, :196)
-                    nCoincident += (int)(has[j] && dd[j] == 0.f);                       // :150-155, :183-188, resolved below
-                    nPairs += (int)(has[j] && isRep[j] && inside);
-                    const bool act = has[j] && dd[j] > 0.f && (isRep[j] ? inside : !inside);
-                    const float sc = act ? (isRep[j] ? -fp.repulsionScale : fp.attractionScale) * ws[j] * inv : 0.f;
-                    acc[0] += (double)(sc * (r[j].x - xv.x)); acc[1] += (double)(sc * (r[j].y - xv.y));
-                    acc[2] += (double)(sc * (r[j].z - xv.z)); acc[3] += (double)(sc * (r[j].w - xv.w));
-                    const float over = fmaf(-L, rcp_approx(ws[j]), dist);               // dist - L / ws
-                    lossA += (double)((act && !isRep[j]) ? over : 0.f);
-                    lossR += (double)((act && isRep[j]) ? -over : 0.f);
+                    nCoincident += (int)(has[j] && dd[j] == 0.f);                        // :150-155, resolved below
+                    const bool act = has[j] && dd[j] >= kFltMin && dist * ws[j] > L;     // :163-168
+                    const float sc = act ? fp.attractionScale * ws[j] * inv : 0.f;
+                    bx = fmaf(sc, r[j].x - xv.x, bx); by = fmaf(sc, r[j].y - xv.y, by);
+                    bz = fmaf(sc, r[j].z - xv.z, bz); bw = fmaf(sc, r[j].w - xv.w, bw);
+                    bl += act ? fmaf(-L, rcp_approx(ws[j]), dist) : 0.f;
                 }
             } else {                                            // one dimension: exact +-1 unit vectors (VectorOperations.hpp:19-24), IEEE arithmetic
 #pragma unroll
                 for (int j = 0; j < B; ++j) {
                     if (!has[j]) continue;
                     const float dist = sqrtf(dd[j]);
-                    if (dist <= 0.f) { ++nCoincident; nPairs += (int)isRep[j]; continue; }
-                    const bool inside = dist * ws[j] <= L;
-                    if (isRep[j]) {
-                        if (!inside) continue;
-                        ++nPairs;
-                        acc[0] += (double)copysignf(fp.repulsionScale * ws[j], xv.x - r[j].x);
-                        lossR += (double)(L / ws[j] - dist);
-                    } else if (!inside) {
-                        acc[0] += (double)copysignf(fp.attractionScale * ws[j], r[j].x - xv.x);
-                        lossA += (double)(dist - L / ws[j]);
+                    if (dist <= 0.f) { ++nCoincident; continue; }
+                    if (dist * ws[j] > L) {
+                        bx += copysignf(fp.attractionScale * ws[j], r[j].x - xv.x);
+                        bl += dist - L / ws[j];
                     }
                 }
             }
+            acc[0] += (double)bx; acc[1] += (double)by; acc[2] += (double)bz; acc[3] += (double)bw;
+            lossA += (double)bl;
         }
+        // ---- repulsion over the vertex' row of the pair list (repellingForce, :174-210; partners ascending, the row is sorted).  Every
+        // term goes into the fp64 accumulators by itself: an entry that is listed but beyond the hinge (lists are built with a skin)
+        // adds an exact zero, so the sums do not depend on what else is listed.
+        int rlen = lenR;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rlen = max(rlen, __shfl_xor_sync(0xffffffffu, rlen, o));
+        float lossRf = 0.f;
+        for (int i = 0; i < rlen; i += 2) {
+            bool has[2];
+            int u[2];
+            float ws[2], dd[2];
+            float4 r[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                has[j] = i + j < lenR;
+                u[j] = has[j] ? __ldg(repCol + re + i + j) : 0;
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) r[j] = (has[j] && chunkLane) ? __ldg(xc + (int64_t)u[j] * V) : xv;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) ws[j] = has[j] ? iwv * __ldg(iw + u[j]) : 1.f;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) dd[j] = chunkLane ? chunk_dist2(xv, r[j]) : 0.f;
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) dd[j] += __shfl_xor_sync(0xffffffffu, dd[j], o);
+            }
+            if (V > 1 || fp.dim > 1) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    // squared distances below FLT_MIN stay away from the flush-to-zero rsqrt: such a pair is inside the hinge for certain;
+                    // its direction is kept and dist is taken as d2 / 1.1e-19 (a pair that close but not coincident - coordinates would
+                    // have to be ~1e-19 themselves - gets a force scaled down accordingly)
+                    const float inv = rsqrt_approx(fmaxf(dd[j], kFltMin));
+                    const float dist = dd[j] * inv;
+                    const bool inside = has[j] && dist * ws[j] <= L;                    // :196
+                    nCoincident += (int)(has[j] && dd[j] == 0.f);                       // :183-188, resolved below
+                    nPairs += (int)inside;
+                    const bool act = inside && dd[j] > 0.f;
+                    const float sc = act ? fp.repulsionScale * ws[j] * inv : 0.f;
+                    acc[0] += (double)(sc * (xv.x - r[j].x)); acc[1] += (double)(sc * (xv.y - r[j].y));
+                    acc[2] += (double)(sc * (xv.z - r[j].z)); acc[3] += (double)(sc * (xv.w - r[j].w));
+                    lossRf += act ? fmaf(L, rcp_approx(ws[j]), -dist) : 0.f;           // L / ws - dist
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (!has[j]) continue;
+                    const float dist = sqrtf(dd[j]);
+                    if (dist <= 0.f) { ++nCoincident; ++nPairs; continue; }
+                    if (!(dist * ws[j] <= L)) continue;
+                    ++nPairs;
+                    acc[0] += (double)copysignf(fp.repulsionScale * ws[j], xv.x - r[j].x);
+                    lossRf += L / ws[j] - dist;
+                }
+            }
+        }
+        lossR = (double)lossRf;
         if (valid && hub >= 0) {                               // hub rows were summed by k_hub_rows
             const double* hd = hubD + (int64_t)hub * hub_doubles(V);
             const long long* hf = hubF + (int64_t)hub * hub_fixed(V);
@@ -635,67 +668,59 @@ __global__ void __launch_bounds__(256) k_reduce_rows(const double* __restrict__ 
 // applyGravityCentre + observeDisplacement (WembedEmbedder.cpp:303-352): x = xnew - centroid and the sums of ||x - xprev|| and
 // ||x||^2.  One block per tile of kObsTile vertices (global tiles: the partial sums do not depend on the grid or on the number of
 // GPUs).  forceSums = output of k_reduce_rows ({lossA, lossR, pairs, list entries, sum xnew[k], max displacement}).
-// Every momentStride-th tile also takes the per-dimension moments of the final layout: the next index build derives its
-// quantisation frame from that sample (only locality depends on the frame, and a fixed 1-in-8 sample of the tiles pins it as well as
-// all of them while costing an eighth).
+// The first 256 vertices of every tile (one per thread) also feed the per-dimension moments of the final layout: the next index build
+// derives its quantisation frame from that 1-in-4 sample (only locality depends on the frame, never results).
+constexpr int kMomentSample = 256;
 template <int V>
-__global__ void __launch_bounds__(256) k_recentre_observe(const float4* xOld /* == x.at[rank]: the old rows are read before the new ones are stored */, const Replicas<float4> x, const float4* __restrict__ xNew, int n,
-                                                          int tileBegin, int dim, const double* __restrict__ forceSums,
-                                                          const Replicas<double> obsPartials /* [tile][2] */, int momentStride,
-                                                          const Replicas<float> momentPartials /* [tile / stride][4][kMaxDim] */,
+__global__ void __launch_bounds__(256) k_recentre_observe(const float4* xOld /* == x.at[rank]: the old rows are read before the new ones are stored */, const Replicas<float4> x,
+                                                          const float4* __restrict__ xNew, int n, int tileBegin, int dim, const double* __restrict__ forceSums,
+                                                          const Replicas<double> obsPartials /* [tile][2] */,
+                                                          const Replicas<float> momentPartials /* [tile][4][kMaxDim] */,
                                                           const StepCtrl* __restrict__ ctrl) {
     if (ctrl->overflow != 0) return;
     __shared__ double redBuf[8 * 2];
     __shared__ float smMom[8][4][4 * V];
+    __shared__ double tileSums[2];
+    __shared__ float tileMom[4 * kMaxDim];
     float cen[4 * V];
 #pragma unroll
     for (int k = 0; k < 4 * V; ++k) cen[k] = (k < dim) ? (float)(forceSums[4 + k] / (double)n) : 0.f;
     const int tile = tileBegin + blockIdx.x;
     const int vEnd = min(n, (tile + 1) * kObsTile);
     double sums[2] = {0.0, 0.0};
-    for (int v = tile * kObsTile + threadIdx.x; v < vEnd; v += 256) {
+    float mn[4 * V], mx[4 * V], s1[4 * V], s2[4 * V];
+#pragma unroll
+    for (int k = 0; k < 4 * V; ++k) { mn[k] = 3.0e38f; mx[k] = -3.0e38f; s1[k] = 0.f; s2[k] = 0.f; }
+    const int vFirst = tile * kObsTile + threadIdx.x;
+    for (int v = vFirst; v < vEnd; v += 256) {
         float disp2 = 0.f, rad2 = 0.f;
 #pragma unroll
         for (int c = 0; c < V; ++c) {
             const int64_t at = (int64_t)v * V + c;
             const float4 a = xNew[at], o = xOld[at];
             const float4 r = make_float4(a.x - cen[4 * c], a.y - cen[4 * c + 1], a.z - cen[4 * c + 2], a.w - cen[4 * c + 3]);
-            for (int q = 0; q < x.world; ++q) x.at[q][at] = r;         // every replica (peers over NVLink)
+            x.at[0][at] = r;
+            for (int q = 1; q < x.world; ++q) x.at[q][at] = r;         // the other replicas (peers over NVLink)
             disp2 = fmaf(r.x - o.x, r.x - o.x, disp2); disp2 = fmaf(r.y - o.y, r.y - o.y, disp2);
             disp2 = fmaf(r.z - o.z, r.z - o.z, disp2); disp2 = fmaf(r.w - o.w, r.w - o.w, disp2);
             rad2 = fmaf(r.x, r.x, rad2); rad2 = fmaf(r.y, r.y, rad2); rad2 = fmaf(r.z, r.z, rad2); rad2 = fmaf(r.w, r.w, rad2);
+            if (v == vFirst) {
+                const float e[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { mn[4 * c + i] = e[i]; mx[4 * c + i] = e[i]; s1[4 * c + i] = e[i]; s2[4 * c + i] = e[i] * e[i]; }
+            }
         }
         sums[0] += (double)sqrtf(disp2);
         sums[1] += (double)rad2;
     }
-    __shared__ double tileSums[2];
     block_sum<2, 256>(sums, redBuf, tileSums);
-    if (threadIdx.x < 2)
-        for (int q = 0; q < obsPartials.world; ++q) obsPartials.at[q][(int64_t)tile * 2 + threadIdx.x] = tileSums[threadIdx.x];
-    if (tile % momentStride != 0) return;
-    // second pass over the tile's (L1 / L2-resident) rows for the moments
-    float mn[4 * V], mx[4 * V], s1[4 * V], s2[4 * V];
-#pragma unroll
-    for (int k = 0; k < 4 * V; ++k) { mn[k] = 3.0e38f; mx[k] = -3.0e38f; s1[k] = 0.f; s2[k] = 0.f; }
-    for (int v = tile * kObsTile + threadIdx.x; v < vEnd; v += 256) {
-#pragma unroll
-        for (int c = 0; c < V; ++c) {
-            const float4 p = xNew[(int64_t)v * V + c];
-            const float e[4] = {p.x - cen[4 * c], p.y - cen[4 * c + 1], p.z - cen[4 * c + 2], p.w - cen[4 * c + 3]};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int k = 4 * c + i;
-                mn[k] = fminf(mn[k], e[i]); mx[k] = fmaxf(mx[k], e[i]);
-                s1[k] += e[i]; s2[k] = fmaf(e[i], e[i], s2[k]);
-            }
-        }
-    }
-    __shared__ float tileMom[4 * kMaxDim];
     moments_block_reduce<V>(mn, mx, s1, s2, smMom, tileMom);
     __syncthreads();
+    if (threadIdx.x < 2)
+        for (int q = 0; q < obsPartials.world; ++q) obsPartials.at[q][(int64_t)tile * 2 + threadIdx.x] = tileSums[threadIdx.x];
     for (int k = threadIdx.x; k < 4 * kMaxDim; k += 256) {
         if ((k % kMaxDim) >= 4 * V) continue;
-        for (int q = 0; q < momentPartials.world; ++q) momentPartials.at[q][(int64_t)(tile / momentStride) * 4 * kMaxDim + k] = tileMom[k];
+        for (int q = 0; q < momentPartials.world; ++q) momentPartials.at[q][(int64_t)tile * 4 * kMaxDim + k] = tileMom[k];
     }
 }
 

@@ -113,7 +113,6 @@ struct wb_embedder {
     char* mail = nullptr;                 // [flags | counts | block sum rows | observation tiles | moment tiles] (step.cuh: k_exchange)
     size_t mailBytes = 0;
     int *repDeg = nullptr, *repRowPtr = nullptr, *repCol = nullptr, *scanSums = nullptr, *longRows = nullptr, *longCount = nullptr;
-    float* edgeWs = nullptr;              // ws(v,u) = iw_v * iw_u of every CSR entry
     int scanBlocks = 0;
     float skinMax = 0.f, reuseTarget = 4.f;
     int nextRebuild = 1;                  // what the host knows about the next step: 1 rebuilds (or unknown), 0 reuses the list
@@ -152,7 +151,7 @@ struct wb_embedder {
     int fusedBlocks = 0, repBlocks = 0, numObsTiles = 0;
     double *blockPartials = nullptr, *forceSums = nullptr, *obsPartials = nullptr, *walkPartials = nullptr, *stats = nullptr;
     float *momentPartials = nullptr, *frameScratch = nullptr;
-    int momentStride = 1, numMomentTiles = 1, momentCount = 1;
+    int numMomentTiles = 1, momentCount = 1;
     int statsTotal = 0;
 
     // vertex-sharded multi-GPU step (wb_comm_init): this rank owns vertices [ownBegin, ownEnd); the other ranks' buffers are mapped
@@ -211,7 +210,7 @@ void free_all(wb_embedder* h) {
         }
         h->peersOpen = h->peerPairsOpen = false;
     }
-    F(h->ctrl); F(h->dyn); F(h->pairBuf); F(h->mail); F(h->repDeg); F(h->repRowPtr); F(h->repCol); F(h->scanSums); F(h->longRows); F(h->longCount); F(h->edgeWs);
+    F(h->ctrl); F(h->dyn); F(h->pairBuf); F(h->mail); F(h->repDeg); F(h->repRowPtr); F(h->repCol); F(h->scanSums); F(h->longRows); F(h->longCount);
     F(h->chunkCounter); F(h->heavyVertex); F(h->heavySlot); F(h->heavyPos); F(h->hubVertex); F(h->hubSlot); F(h->hubD); F(h->hubF); F(h->mtScratch);
     F(h->keysIn); F(h->keysOut); F(h->valsIn); F(h->valsOut); F(h->cubTemp); F(h->quant); F(h->ids); F(h->blk); F(h->blkH);
     for (int l = 0; l < wb::kMaxLevels; ++l) { F(h->lvlLo[l]); if (l > 0) F(h->lvlHi[l]); F(h->lvlBound[l]); }
@@ -346,11 +345,11 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
     h->numBlockRows = div_up(std::max(n, 1), h->vertsPerBlock);
     h->cols = wb::block_sums(V) + 1;
     h->numObsTiles = div_up(std::max(n, 1), wb::kObsTile);
-    // tiles whose moments feed the next quantisation frame: every 8th once there are plenty
-    h->momentStride = std::max(1, std::min(8, h->numObsTiles / 16));
-    h->numMomentTiles = div_up(h->numObsTiles, h->momentStride);
+    // the first kMomentSample vertices of every tile feed the next quantisation frame
+    h->numMomentTiles = h->numObsTiles;
     h->momentCount = 0;
-    for (int t = 0; t < h->numObsTiles; t += h->momentStride) h->momentCount += std::min(wb::kObsTile, std::max(n, 1) - t * wb::kObsTile);
+    for (int t = 0; t < h->numObsTiles; ++t) h->momentCount += std::max(0, std::min(wb::kMomentSample, n - t * wb::kObsTile));
+    h->momentCount = std::max(h->momentCount, 1);
     h->rowsAlloc = (size_t)h->numBlockRows * h->vertsPerBlock;
     const size_t rows = h->rowsAlloc * V;
     for (float4** p : {&h->x, &h->xNew, &h->mom1, &h->mom2, &h->force}) {
@@ -390,8 +389,6 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
     WB_CUDA(cudaMemsetAsync(h->repRowPtr, 0, sizeof(int) * (h->rowsAlloc + 1 + 8), h->stream));
     h->longRows = dalloc<int>(std::max(n, 1));
     h->longCount = dalloc<int>(2);        // [rows queued, cursor of the sorting warps]
-    h->edgeWs = dalloc<float>(h->numDirected + 8);
-    if (h->numDirected) wb::k_fill<float><<<div_up(h->numDirected, 256), 256, 0, h->stream>>>(h->edgeWs, h->numDirected, 1.0f);
     h->scanBlocks = div_up(std::max(n, 1), wb::kScanItems);
     h->scanSums = dalloc<int>(h->scanBlocks + 1);
     choose_fixed_scales(h, 1.0, 1.0);
@@ -550,7 +547,7 @@ void launch_step(wb_embedder* h, const PendingStep& slot) {
     const bool build = h->nextRebuild != 0 || !h->pending.empty();
 
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[0], s));
-    wb::k_step_begin<<<1, 32, 0, s>>>(h->ctrl, h->pairCounts + h->rank * wb::kMaxRanks, h->world, h->chunkCounter);
+    wb::k_step_begin<<<1, 32, 0, s>>>(h->ctrl, h->pairCounts + h->rank * wb::kMaxRanks, h->world, h->chunkCounter, h->longCount);
     h->launches += 1;
     if (build) enqueue_index(h, h->iw, 0);
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[1], s));
@@ -608,7 +605,6 @@ void launch_step(wb_embedder* h, const PendingStep& slot) {
         wb::k_scan_offsets<<<1, 1024, 0, s>>>(h->scanSums, scanBlocks, h->ctrl);
         wb::k_scan_apply<<<scanBlocks, 256, 0, s>>>(h->repDeg + h->ownBegin, own, h->scanSums, scanBlocks, h->repRowPtr + h->ownBegin, h->ctrl);
         wb::k_rep_fill<<<pairBlocks, 256, 0, s>>>(src, h->repDeg, h->repRowPtr, h->repCol, h->ctrl);
-        WB_CUDA(cudaMemsetAsync(h->longCount, 0, 2 * sizeof(int), s));
         wb::k_rep_sort_rows<<<div_up(own, 256), 256, 0, s>>>(h->repRowPtr, h->repCol, h->ownBegin, h->ownEnd, h->hubSlot, h->longRows, h->longCount, h->ctrl);
         wb::k_rep_sort_long<<<148 * 4, 256, 0, s>>>(h->repRowPtr, h->repCol, reinterpret_cast<int*>(h->pairBuf), h->longRows, h->longCount, h->longCount + 1, h->ctrl);
         h->launches += 7;
@@ -621,7 +617,7 @@ void launch_step(wb_embedder* h, const PendingStep& slot) {
     }
     const int ownBlocks = div_up(std::max(0, h->ownEnd - h->ownBegin), h->vertsPerBlock);
     if (ownBlocks > 0) {
-        WB_DISPATCH_V(V, wb::k_step_fused<V><<<ownBlocks, 256, 0, s>>>(h->x, h->iw, h->edgeWs, h->rowPtr, h->col, h->repRowPtr, h->repCol, h->ownBegin, h->ownEnd, h->vertsPerBlock, fp,
+        WB_DISPATCH_V(V, wb::k_step_fused<V><<<ownBlocks, 256, 0, s>>>(h->x, h->iw, h->rowPtr, h->col, h->repRowPtr, h->repCol, h->ownBegin, h->ownEnd, h->vertsPerBlock, fp,
                                                                         h->dyn, h->hubSlot, h->hubD, h->hubF, h->xNew, h->mom1, h->mom2, h->force,
                                                                         rowsOut, h->ctrl));
     }
@@ -633,7 +629,7 @@ void launch_step(wb_embedder* h, const PendingStep& slot) {
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[3], s));
     const int obsBegin = h->ownBegin / wb::kObsTile, obsEnd = div_up(h->ownEnd, wb::kObsTile);
     if (obsEnd > obsBegin)
-        WB_DISPATCH_V(V, wb::k_recentre_observe<V><<<obsEnd - obsBegin, 256, 0, s>>>(h->x, xOut, h->xNew, n, obsBegin, h->dim, h->forceSums, obsOut, h->momentStride, momOut, h->ctrl));
+        WB_DISPATCH_V(V, wb::k_recentre_observe<V><<<obsEnd - obsBegin, 256, 0, s>>>(h->x, xOut, h->xNew, n, obsBegin, h->dim, h->forceSums, obsOut, momOut, h->ctrl));
     if (sharded) {   // every replica of x is complete, every rank holds all observation tiles
         wb::k_exchange<<<1, 32, 0, s>>>(peers, ++h->epoch, 0, h->ctrl);
         h->launches += 1;
@@ -1016,7 +1012,6 @@ int wb_set_weights(wb_embedder* h, const double* weights) {
         std::vector<float> iw(n);
         for (int v = 0; v < n; ++v) iw[v] = (float)(1.0 / std::pow(weights[v], 1.0 / (double)h->dim));
         WB_CUDA(cudaMemcpyAsync(h->iw, iw.data(), sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
-        wb::k_edge_weights<<<div_up(n, 256), 256, 0, h->stream>>>(h->rowPtr, h->col, h->iw, n, h->edgeWs);
         WB_CUDA(cudaStreamSynchronize(h->stream));
         const double minW = *std::min_element(h->weights.begin(), h->weights.end());
         const double maxW = *std::max_element(h->weights.begin(), h->weights.end());

@@ -1,7 +1,10 @@
 // pybind11 module "wembed": the same Python surface as the reference's python/bindings.cpp:11-133
 // (enums exported by value; Edge, TimingResult, Loss, Options, Graph, Embedder; the six free functions; __version__).
+#include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
+
+#include <cstring>
 
 #include "wembed.h"
 
@@ -58,6 +61,14 @@ PYBIND11_MODULE(wembed, m) {
         .def("getEdgeTarget", &Graph::getEdgeTarget)
         .def("areNeighbors", &Graph::areNeighbors)
         .def("getEdgeList", &Graph::getEdgeList)
+        // addition of this build: the CSR as two numpy arrays (copies), what the embedder uploads to the device
+        .def("csr", [](const Graph& g) {
+            const py::ssize_t n = g.getNumVertices(), m2 = 2 * (py::ssize_t)g.getNumEdges();
+            py::array_t<std::int32_t> offsets(n + 1), targets(m2);
+            std::memcpy(offsets.mutable_data(), g.csrOffsets(), sizeof(std::int32_t) * (n + 1));
+            if (m2) std::memcpy(targets.mutable_data(), g.csrTargets(), sizeof(std::int32_t) * m2);
+            return py::make_tuple(offsets, targets);
+        })
         .def("__repr__", &Graph::toString);
 
     py::class_<Embedder>(m, "Embedder")
@@ -80,6 +91,15 @@ PYBIND11_MODULE(wembed, m) {
 
     m.def("createEmbedder", &createEmbedder, py::arg("graph"), py::arg("options"));
     m.def("graphFromEdges", &graphFromEdges, py::arg("edges"));
+    // addition of this build: the same constructor fed from an (m, 2) integer array instead of a list of Edge objects
+    m.def("graphFromEdgeArray", [](py::array_t<std::int32_t, py::array::c_style | py::array::forcecast> a) {
+        if (a.ndim() != 2 || a.shape(1) != 2) throw std::invalid_argument("graphFromEdgeArray: expected an array of shape (m, 2)");
+        std::vector<Edge> edges((std::size_t)a.shape(0));
+        const std::int32_t* p = a.data();
+        for (std::size_t i = 0; i < edges.size(); ++i) edges[i] = Edge{p[2 * i], p[2 * i + 1]};
+        py::gil_scoped_release release;
+        return graphFromEdges(edges);
+    }, py::arg("edges"));
     m.def("graphFromEdgeListFile", &graphFromEdgeListFile, py::arg("filePath"), py::arg("comment") = "#", py::arg("delimiter") = " ");
     m.def("readCoordinatesFromFile", &readCoordinatesFromFile, py::arg("filePath"), py::arg("comment") = "%", py::arg("delimiter") = ",");
     m.def("timingsToString", &timingsToString, py::arg("timings"));

@@ -47,6 +47,8 @@ int Graph::getNumNeighbors(NodeId v) const { return _graph->getNumNeighbors(v); 
 NodeId Graph::getEdgeTarget(EdgeId e) const { return _graph->getEdgeTarget(e); }
 bool Graph::areNeighbors(NodeId v, NodeId u) const { return _graph->areNeighbors(v, u); }
 std::string Graph::toString() const { return _graph->toString(); }
+const std::int32_t* Graph::csrOffsets() const { return _graph->rowPtr().data(); }
+const std::int32_t* Graph::csrTargets() const { return _graph->col().data(); }
 
 std::vector<Edge> Graph::getEdgeList() const {
     std::vector<Edge> out;
