@@ -271,3 +271,28 @@ def test_ring64_displacement_and_loss_signals(device_lib, port_lib):
     it_dev, last = run_to_convergence(dev, opts)
     assert 5 < it_dev < 5000
     assert 0.5 * it_cpu <= it_dev <= 2.0 * it_cpu, (it_cpu, it_dev)
+
+
+def test_candidate_sets_follow_the_float32_copy_of_the_points(device_lib, port_lib):
+    """The reference's default index (IndexType::Sprk) answers radius queries on a float32 copy of the points
+    (SprkQueries.cpp:13-22, 52-55); the crate itself is not in the reference tree, so only that documented rounding can be pinned.
+    The device keeps fp32 positions, so for coordinates that are NOT float32-representable its candidate sets are those of the rounded
+    points - which is the Sprk view - and every candidate is still re-tested with the exact pair weight when forces are computed."""
+    n, d = 6000, 3
+    edges, w, x0 = make_problem(n, d)
+    rng = np.random.default_rng(11)
+    x64 = x0 + rng.standard_normal(x0.shape) * 1e-9            # not representable in float32
+    x32 = x64.astype(np.float32).astype(np.float64)
+    assert (x64 != x32).any()
+    rp, col = device_lib.csr_from_edges(n, edges)
+    dev = device_lib.DeviceEmbedder(rp, col, embedding_dimension=d, seed=1)
+    cpu = oracle.CpuEmbedder("port", edges, n=n, embeddingDimension=d, init_state=False)
+    for e in (cpu, dev):
+        e.set_weights(w)
+    dev.set_coordinates(x64)                                    # rounded to float32 at the boundary
+    cpu.set_coordinates(x32)                                    # the float32 copy an IndexSprk would hold
+    np.testing.assert_array_equal(dev.coordinates(), x32)
+    queries = np.arange(0, n, 41, dtype=np.int32)
+    got = dev.query_candidates(queries)
+    for k, q in enumerate(queries):
+        np.testing.assert_array_equal(got[k], cpu.candidates(int(q)))

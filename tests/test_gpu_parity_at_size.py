@@ -108,7 +108,7 @@ def test_c3_one_step_against_the_port_and_a_brute_force_census(device_lib, port_
 def test_c4_one_step_against_the_port_with_heavy_vertices(device_lib, port_lib):
     """BASELINE.json configs[3]: heavy-tailed n = 1e6, average degree 20, d = 8 (hubs: k_repulse_heavy, k_attract_hubs)."""
     from wembed_b200.datasets import degree_weights, heavy_tailed_graph, initial_coordinates
-    n, d, steps = 1_000_000, 8, 12
+    n, d, steps = 1_000_000, 8, 30
     edges, _ = heavy_tailed_graph(n, 20, seed=42)
     w, x0 = degree_weights(n, edges, d), initial_coordinates(n, d, seed=1234)
     rp, col = device_lib.csr_from_edges(n, edges)
@@ -124,4 +124,5 @@ def test_c4_one_step_against_the_port_with_heavy_vertices(device_lib, port_lib):
     # hub rows sum 1e4..1e5 fp32 terms: same coordinate tolerance as the heavy-tailed test at n = 2e4
     res = _one_step_against_port(device_lib, edges, n, d, w, rp, col, x, max_flagged_frac=0.05, coord_rtol=5e-5, pair_slack=64, tile=1024)
     lo, hi = res["lo"], res["hi"]
+    assert res["pairs"] > n                                 # a state in which the heavy vertices own most of the repulsive pairs
     print(f"c4 step {steps}: pairs {res['pairs']:.0f} in [{lo}, {hi}], near-hinge vertices {res['flagged']}, max force err {res['force_err']:.2e}")

@@ -200,7 +200,7 @@ class DeviceEmbedder:
     def phase_times(self):
         out = np.empty(6, np.float64)
         self._check(self._l.wb_get_phase_times(self._h, _dp(out)))
-        return dict(zip(("index", "attract_update", "repel", "repel_reduce_scatter", "recentre_observe", "total"), out.tolist()))
+        return dict(zip(("index", "attract_update", "repel", "unused", "recentre_observe", "total"), out.tolist()))
 
     def mark(self, slot):
         self._check(self._l.wb_mark(self._h, int(slot)))

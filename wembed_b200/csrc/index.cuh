@@ -78,8 +78,8 @@ __device__ __forceinline__ void store_block_node(float4* __restrict__ blk, float
 
 // ---------------------------------------------------------------------------------------------
 // Per-dimension min / max / sum / sum of squares of a layout (fixed-order reduction); partial layout [tile][4][kMaxDim] floats.
-// Inside a step the moments come out of k_recentre_observe (a sample of the tiles); this kernel serves the first step after wb_set_coordinates and the
-// test hook.  One block per tile of kObsTile vertices, like the recentre pass.
+// One block per tile of kObsTile vertices.  Inside a step it runs after the recentre pass on a 1-in-4 sample (the first 256 vertices
+// of every tile) and k_step_tail turns the partials into the frame of the next build.
 constexpr int kObsTile = 1024;
 
 template <int V>
@@ -106,12 +106,13 @@ __device__ __forceinline__ void moments_block_reduce(float (&mn)[4 * V], float (
     }
 }
 
+// perTile: how many vertices of every tile are looked at (the first ones); the frame only has to be representative
 template <int V>
-__global__ void __launch_bounds__(256) k_moments(const float4* __restrict__ x, int n, float* __restrict__ partial) {
+__global__ void __launch_bounds__(256) k_moments(const float4* __restrict__ x, int n, int perTile, float* __restrict__ partial) {
     float mn[4 * V], mx[4 * V], s1[4 * V], s2[4 * V];
 #pragma unroll
     for (int k = 0; k < 4 * V; ++k) { mn[k] = 3.0e38f; mx[k] = -3.0e38f; s1[k] = 0.f; s2[k] = 0.f; }
-    const int vEnd = min(n, (blockIdx.x + 1) * kObsTile);
+    const int vEnd = min(n, blockIdx.x * kObsTile + perTile);
     for (int v = blockIdx.x * kObsTile + threadIdx.x; v < vEnd; v += 256) {
 #pragma unroll
         for (int c = 0; c < V; ++c) {

@@ -432,19 +432,17 @@ k_step_fused(const float4* __restrict__ x, const float* __restrict__ iw, const i
             if (V > 1 || fp.dim > 1) {
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    // squared distances below FLT_MIN stay away from the flush-to-zero rsqrt: such a pair is inside the hinge for certain;
-                    // its direction is kept and dist is taken as d2 / 1.1e-19 (a pair that close but not coincident - coordinates would
-                    // have to be ~1e-19 themselves - gets a force scaled down accordingly)
-                    const float inv = rsqrt_approx(fmaxf(dd[j], kFltMin));
-                    const float dist = dd[j] * inv;
+                    // IEEE square root and divisions here (a handful of entries per vertex; a vertex near a heavy hub sums thousands of
+                    // nearly parallel terms, where the 2^-22 of the approximate forms would show)
+                    const float dist = sqrtf(dd[j]);
                     const bool inside = has[j] && dist * ws[j] <= L;                    // :196
-                    nCoincident += (int)(has[j] && dd[j] == 0.f);                       // :183-188, resolved below
+                    nCoincident += (int)(has[j] && dist <= 0.f);                        // :183-188, resolved below
                     nPairs += (int)inside;
-                    const bool act = inside && dd[j] > 0.f;
-                    const float sc = act ? fp.repulsionScale * ws[j] * inv : 0.f;
+                    const bool act = inside && dist > 0.f;
+                    const float sc = act ? fp.repulsionScale * ws[j] / dist : 0.f;
                     acc[0] += (double)(sc * (xv.x - r[j].x)); acc[1] += (double)(sc * (xv.y - r[j].y));
                     acc[2] += (double)(sc * (xv.z - r[j].z)); acc[3] += (double)(sc * (xv.w - r[j].w));
-                    lossRf += act ? fmaf(L, rcp_approx(ws[j]), -dist) : 0.f;           // L / ws - dist
+                    lossRf += act ? L / ws[j] - dist : 0.f;
                 }
             } else {
 #pragma unroll
@@ -668,59 +666,46 @@ __global__ void __launch_bounds__(256) k_reduce_rows(const double* __restrict__ 
 // applyGravityCentre + observeDisplacement (WembedEmbedder.cpp:303-352): x = xnew - centroid and the sums of ||x - xprev|| and
 // ||x||^2.  One block per tile of kObsTile vertices (global tiles: the partial sums do not depend on the grid or on the number of
 // GPUs).  forceSums = output of k_reduce_rows ({lossA, lossR, pairs, list entries, sum xnew[k], max displacement}).
-// The first 256 vertices of every tile (one per thread) also feed the per-dimension moments of the final layout: the next index build
-// derives its quantisation frame from that 1-in-4 sample (only locality depends on the frame, never results).
-constexpr int kMomentSample = 256;
-template <int V>
-__global__ void __launch_bounds__(256) k_recentre_observe(const float4* xOld /* == x.at[rank]: the old rows are read before the new ones are stored */, const Replicas<float4> x,
-                                                          const float4* __restrict__ xNew, int n, int tileBegin, int dim, const double* __restrict__ forceSums,
-                                                          const Replicas<double> obsPartials /* [tile][2] */,
-                                                          const Replicas<float> momentPartials /* [tile][4][kMaxDim] */,
-                                                          const StepCtrl* __restrict__ ctrl) {
+// MULTI: a sharded run stores the new rows into every replica of x and the tile sums into every rank's copy (peers over NVLink).
+constexpr int kMomentSample = 256;        // vertices per tile that feed the next quantisation frame (k_moments after this pass)
+template <int V, bool MULTI>
+__global__ void __launch_bounds__(256) k_recentre_observe(float4* x, const Replicas<float4> xPeers, const float4* __restrict__ xNew, int n, int tileBegin, int dim,
+                                                          const double* __restrict__ forceSums, double* __restrict__ obsPartials /* [tile][2] */,
+                                                          const Replicas<double> obsPeers, int rank, const StepCtrl* __restrict__ ctrl) {
     if (ctrl->overflow != 0) return;
     __shared__ double redBuf[8 * 2];
-    __shared__ float smMom[8][4][4 * V];
-    __shared__ double tileSums[2];
-    __shared__ float tileMom[4 * kMaxDim];
     float cen[4 * V];
 #pragma unroll
     for (int k = 0; k < 4 * V; ++k) cen[k] = (k < dim) ? (float)(forceSums[4 + k] / (double)n) : 0.f;
     const int tile = tileBegin + blockIdx.x;
     const int vEnd = min(n, (tile + 1) * kObsTile);
     double sums[2] = {0.0, 0.0};
-    float mn[4 * V], mx[4 * V], s1[4 * V], s2[4 * V];
-#pragma unroll
-    for (int k = 0; k < 4 * V; ++k) { mn[k] = 3.0e38f; mx[k] = -3.0e38f; s1[k] = 0.f; s2[k] = 0.f; }
-    const int vFirst = tile * kObsTile + threadIdx.x;
-    for (int v = vFirst; v < vEnd; v += 256) {
+    for (int v = tile * kObsTile + threadIdx.x; v < vEnd; v += 256) {
         float disp2 = 0.f, rad2 = 0.f;
 #pragma unroll
         for (int c = 0; c < V; ++c) {
             const int64_t at = (int64_t)v * V + c;
-            const float4 a = xNew[at], o = xOld[at];
+            const float4 a = xNew[at], o = x[at];
             const float4 r = make_float4(a.x - cen[4 * c], a.y - cen[4 * c + 1], a.z - cen[4 * c + 2], a.w - cen[4 * c + 3]);
-            x.at[0][at] = r;
-            for (int q = 1; q < x.world; ++q) x.at[q][at] = r;         // the other replicas (peers over NVLink)
+            x[at] = r;
+            if constexpr (MULTI) {
+                for (int q = 0; q < xPeers.world; ++q)
+                    if (q != rank) xPeers.at[q][at] = r;
+            }
             disp2 = fmaf(r.x - o.x, r.x - o.x, disp2); disp2 = fmaf(r.y - o.y, r.y - o.y, disp2);
             disp2 = fmaf(r.z - o.z, r.z - o.z, disp2); disp2 = fmaf(r.w - o.w, r.w - o.w, disp2);
             rad2 = fmaf(r.x, r.x, rad2); rad2 = fmaf(r.y, r.y, rad2); rad2 = fmaf(r.z, r.z, rad2); rad2 = fmaf(r.w, r.w, rad2);
-            if (v == vFirst) {
-                const float e[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { mn[4 * c + i] = e[i]; mx[4 * c + i] = e[i]; s1[4 * c + i] = e[i]; s2[4 * c + i] = e[i] * e[i]; }
-            }
         }
         sums[0] += (double)sqrtf(disp2);
         sums[1] += (double)rad2;
     }
-    block_sum<2, 256>(sums, redBuf, tileSums);
-    moments_block_reduce<V>(mn, mx, s1, s2, smMom, tileMom);
-    __syncthreads();
-    if (threadIdx.x < 2)
-        for (int q = 0; q < obsPartials.world; ++q) obsPartials.at[q][(int64_t)tile * 2 + threadIdx.x] = tileSums[threadIdx.x];
-    for (int k = threadIdx.x; k < 4 * kMaxDim; k += 256) {
-        if ((k % kMaxDim) >= 4 * V) continue;
-        for (int q = 0; q < momentPartials.world; ++q) momentPartials.at[q][(int64_t)tile * 4 * kMaxDim + k] = tileMom[k];
+    block_sum<2, 256>(sums, redBuf, obsPartials + (int64_t)tile * 2);
+    if constexpr (MULTI) {
+        if (threadIdx.x < 2) {
+            const double v = obsPartials[(int64_t)tile * 2 + threadIdx.x];
+            for (int q = 0; q < obsPeers.world; ++q)
+                if (q != rank) obsPeers.at[q][(int64_t)tile * 2 + threadIdx.x] = v;
+        }
     }
 }
 

@@ -150,7 +150,7 @@ struct wb_embedder {
     int passVerts = 0, vertsPerBlock = 0, numBlockRows = 0, cols = 0;   // fused kernel: vertices per pass, per block (fixed by n alone), rows, sums per row
     int fusedBlocks = 0, repBlocks = 0, numObsTiles = 0;
     double *blockPartials = nullptr, *forceSums = nullptr, *obsPartials = nullptr, *walkPartials = nullptr, *stats = nullptr;
-    float *momentPartials = nullptr, *frameScratch = nullptr;
+    float* frameScratch = nullptr;        // per-tile moments of the layout (k_moments)
     int numMomentTiles = 1, momentCount = 1;
     int statsTotal = 0;
 
@@ -368,14 +368,12 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
         auto carve = [&](size_t bytes) { const size_t at = off; off += (bytes + 255) & ~(size_t)255; return at; };
         const size_t rowsAt = carve(sizeof(double) * h->numBlockRows * h->cols);
         const size_t obsAt = carve(sizeof(double) * h->numObsTiles * 2);
-        const size_t momAt = carve(sizeof(float) * h->numMomentTiles * 4 * wb::kMaxDim);
         h->mailBytes = off;
         h->mail = dalloc<char>(off);
         WB_CUDA(cudaMemsetAsync(h->mail, 0, off, h->stream));
         h->pairCounts = reinterpret_cast<unsigned int*>(h->mail + wb::kMailCounts);
         h->blockPartials = reinterpret_cast<double*>(h->mail + rowsAt);
         h->obsPartials = reinterpret_cast<double*>(h->mail + obsAt);
-        h->momentPartials = reinterpret_cast<float*>(h->mail + momAt);
     }
     {   // pair list: room for 8 unordered pairs per vertex (never more than all pairs); grown on demand (collect_step)
         const int64_t all = (int64_t)n * (n - 1) / 2;
@@ -498,7 +496,7 @@ wb::ForceParams force_params(const wb_embedder* h) {
 // previous step's recentre pass
 void enqueue_frame(wb_embedder* h) {
     cudaStream_t s = h->stream;
-    WB_DISPATCH_V(h->V, wb::k_moments<V><<<h->numObsTiles, 256, 0, s>>>(h->x, h->n, h->frameScratch));
+    WB_DISPATCH_V(h->V, wb::k_moments<V><<<h->numObsTiles, 256, 0, s>>>(h->x, h->n, wb::kObsTile, h->frameScratch));
     wb::k_quant_params<<<1, 1024, 0, s>>>(h->frameScratch, h->numObsTiles, h->n, h->dim, h->mortonBits, h->halfSigmaLimit, h->quant);
     h->launches += 2;
     h->quantValid = true;
@@ -557,15 +555,13 @@ void launch_step(wb_embedder* h, const PendingStep& slot) {
     wb::PairSink sink{};
     wb::PairSource src{};
     wb::Replicas<double> rowsOut{}, obsOut{};
-    wb::Replicas<float> momOut{};
     wb::Replicas<float4> xOut{};
-    rowsOut.world = obsOut.world = momOut.world = xOut.world = h->world;
+    rowsOut.world = obsOut.world = xOut.world = h->world;
     for (int p = 0; p < h->world; ++p) {
         char* mail = p == h->rank ? h->mail : h->peerMail[p];
         peers.mail[p] = mail;
         rowsOut.at[p] = reinterpret_cast<double*>(mail + (reinterpret_cast<char*>(h->blockPartials) - h->mail));
         obsOut.at[p] = reinterpret_cast<double*>(mail + (reinterpret_cast<char*>(h->obsPartials) - h->mail));
-        momOut.at[p] = reinterpret_cast<float*>(mail + (reinterpret_cast<char*>(h->momentPartials) - h->mail));
         xOut.at[p] = p == h->rank ? h->x : h->peerX[p];
         // what this rank finds for rank p's vertices goes into segment `rank` of p's buffer; it reads segment p of its own
         sink.seg[p] = (p == h->rank ? h->pairBuf : h->peerPairs[p]) + (size_t)h->rank * h->pairCap;
@@ -628,17 +624,26 @@ void launch_step(wb_embedder* h, const PendingStep& slot) {
     wb::k_reduce_rows<<<h->cols, 256, 0, s>>>(h->blockPartials, h->numBlockRows, h->cols, h->forceSums, h->ctrl);
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[3], s));
     const int obsBegin = h->ownBegin / wb::kObsTile, obsEnd = div_up(h->ownEnd, wb::kObsTile);
-    if (obsEnd > obsBegin)
-        WB_DISPATCH_V(V, wb::k_recentre_observe<V><<<obsEnd - obsBegin, 256, 0, s>>>(h->x, xOut, h->xNew, n, obsBegin, h->dim, h->forceSums, obsOut, momOut, h->ctrl));
+    if (obsEnd > obsBegin) {
+        if (sharded) {
+            WB_DISPATCH_V(V, (wb::k_recentre_observe<V, true><<<obsEnd - obsBegin, 256, 0, s>>>(h->x, xOut, h->xNew, n, obsBegin, h->dim, h->forceSums, h->obsPartials, obsOut,
+                                                                                               h->rank, h->ctrl)));
+        } else {
+            WB_DISPATCH_V(V, (wb::k_recentre_observe<V, false><<<obsEnd - obsBegin, 256, 0, s>>>(h->x, xOut, h->xNew, n, obsBegin, h->dim, h->forceSums, h->obsPartials, obsOut,
+                                                                                                0, h->ctrl)));
+        }
+    }
     if (sharded) {   // every replica of x is complete, every rank holds all observation tiles
         wb::k_exchange<<<1, 32, 0, s>>>(peers, ++h->epoch, 0, h->ctrl);
         h->launches += 1;
     }
+    // moments of a sample of the final layout -> the next build's quantisation frame (k_step_tail)
+    WB_DISPATCH_V(V, wb::k_moments<V><<<h->numObsTiles, 256, 0, s>>>(h->x, n, wb::kMomentSample, h->frameScratch));
     wb::TailPolicy pol{(float)h->opt.edge_length, h->halfSigmaLimit, h->dim, h->mortonBits};
-    wb::k_step_tail<<<1, 1024, 0, s>>>(h->forceSums, h->cols, h->obsPartials, h->numObsTiles, h->momentPartials, h->numMomentTiles, h->momentCount, n, h->walkPartials, repWarps + h->numHeavy,
+    wb::k_step_tail<<<1, 1024, 0, s>>>(h->forceSums, h->cols, h->obsPartials, h->numObsTiles, h->frameScratch, h->numMomentTiles, h->momentCount, n, h->walkPartials, repWarps + h->numHeavy,
                                         pol, h->quant, h->ctrl, h->stats);
     if (h->timing) WB_CUDA(cudaEventRecord(h->ev[4], s));
-    h->launches += 4;
+    h->launches += 5;
     WB_CUDA(cudaGetLastError());
     WB_CUDA(cudaMemcpyAsync(slot.host->sums, h->stats, sizeof(double) * h->statsTotal, cudaMemcpyDeviceToHost, s));
     WB_CUDA(cudaEventRecord(slot.done, s));
