@@ -237,6 +237,9 @@ int wb_elapsed_ms(wb_embedder* h, int from, int to, double* ms);
 /* Number of kernels of this library launched through the handle since wb_create
  * (the CUB radix-sort call of the index rebuild is counted as one). */
 int64_t wb_launch_count(wb_embedder* h);
+/* How steps are issued: 1 = one CUDA graph launch per step (k_step_begin -> IF(rebuild){index, search, pair list} -> forces .. tail; one GPU,
+ * phase timing off), 0 = direct launches (phase timing on, sharded runs, WB_GRAPH=0, or the capture failed: `note` then says why). */
+int wb_exec_mode(wb_embedder* h, char* note, int32_t note_cap);
 
 #ifdef __cplusplus
 }

@@ -251,3 +251,33 @@ def test_pair_list_grows_on_overflow(device_lib, monkeypatch):
     for key in (("16", False), ("16", True)):
         assert np.array_equal(out[key][0], base[0])
         assert out[key][1] == base[1]
+
+
+def test_graph_replay_equals_direct_launches(device_lib, monkeypatch):
+    """One GPU, no phase timing: a step is one CUDA graph launch (k_step_begin -> IF(rebuild){index, search, pair list} -> forces .. tail).
+    Same kernels, same arguments: the trajectory must be bit-identical to direct launches, through rebuild and reuse steps, blocking and
+    queued, and across a re-capture (wb_set_weights voids the captured arguments)."""
+    from helpers import make_problem
+    n, d, steps = 5000, 4, 260
+    edges, w, x0 = make_problem(n, d)
+    rp, col = device_lib.csr_from_edges(n, edges)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("WB_GRAPH", mode)
+        dev = device_lib.DeviceEmbedder(rp, col, embedding_dimension=d, seed=1234)
+        dev.set_weights(w)
+        dev.set_coordinates(x0)
+        stats = [dev.step(lr_exponential(it, cooling=0.97)) for it in range(1, steps // 2 + 1)]
+        dev.set_weights(w)                                   # forces a new capture
+        for it in range(steps // 2 + 1, steps + 1):
+            dev.step_async(lr_exponential(it, cooling=0.97))
+            if it % 16 == 0:
+                stats.extend(dev.step_collect() for _ in range(16))
+        stats.extend(dev.step_collect() for _ in range(steps - len(stats)))
+        out[mode] = (dev.coordinates(), [(s["loss_attract"], s["loss_repel"], s["num_repulsion_pairs"], s["list_rebuilt"]) for s in stats], dev.exec_mode())
+        dev.close()
+    assert out["1"][2][0] == "graph", out["1"][2]
+    assert out["0"][2][0] == "direct"
+    assert np.array_equal(out["1"][0], out["0"][0])
+    assert out["1"][1] == out["0"][1]
+    assert any(s[3] == 0 for s in out["1"][1]) and any(s[3] == 1 for s in out["1"][1])     # both kinds of step were replayed

@@ -24,7 +24,7 @@ EXPORTS = (
     "wb_set_coordinates", "wb_set_weights", "wb_get_coordinates", "wb_get_weights", "wb_get_forces", "wb_reset_optimizer",
     "wb_set_iteration", "wb_step", "wb_step_async", "wb_step_collect", "wb_synchronize", "wb_query_candidates",
     "wb_enable_timing", "wb_get_phase_times", "wb_mark", "wb_elapsed_ms", "wb_launch_count", "wb_comm_unique_id", "wb_comm_init", "wb_reconstruction",
-    "wb_edge_detection", "wb_set_list_policy", "wb_get_partition",
+    "wb_edge_detection", "wb_set_list_policy", "wb_get_partition", "wb_exec_mode",
 )
 
 
@@ -85,6 +85,7 @@ def lib():
         "wb_edge_detection": (C.c_int, [H, C.c_int64, ip, ip, C.POINTER(C.c_uint8), dp]),
         "wb_set_list_policy": (C.c_int, [H, C.c_double, C.c_double]),
         "wb_get_partition": (C.c_int, [H, ip, ip]),
+        "wb_exec_mode": (C.c_int, [H, C.c_char_p, i32]),
         "wb_comm_unique_id": (C.c_int, [C.c_char_p]), "wb_comm_init": (C.c_int, [H, C.c_char_p, i32, i32]),
     }
     for name, (res, args) in sig.items():
@@ -235,6 +236,14 @@ class DeviceEmbedder:
         """Join the vertex-sharded multi-GPU step (see include/wembed_b200.h)."""
         assert len(unique_id) == 128
         self._check(self._l.wb_comm_init(self._h, unique_id, int(rank), int(world)))
+
+    def exec_mode(self):
+        """("graph" | "direct", note): how steps are issued (include/wembed_b200.h: wb_exec_mode)."""
+        buf = C.create_string_buffer(256)
+        rc = self._l.wb_exec_mode(self._h, buf, 256)
+        if rc < 0:
+            self._check(rc)
+        return ("graph" if rc == 1 else "direct"), buf.value.decode()
 
     def partition(self):
         """[begin, end) of the vertices this handle owns."""

@@ -15,9 +15,13 @@ __device__ __forceinline__ long long to_fixed(float term, double scale) { return
 
 // ---------------------------------------------------------------------------------------------
 // First kernel of every step: resets the work counters of a build.
+// In a captured step (CUDA graph) it also arms the conditional node that holds the kernels of a build: they only exist in the
+// timeline of steps that rebuild.
 __global__ void k_step_begin(StepCtrl* ctrl, unsigned int* pairCounts /* this rank's row of the counts matrix */, int world, int* chunkCounter,
-                             int* longCount /* [2]: queue of long pair-list rows, cursor */) {
-    if (ctrl->overflow != 0 || ctrl->rebuild == 0) return;
+                             int* longCount /* [2]: queue of long pair-list rows, cursor */, cudaGraphConditionalHandle buildNode, int inGraph) {
+    const bool build = ctrl->overflow == 0 && ctrl->rebuild != 0;
+    if (inGraph && threadIdx.x == 0) cudaGraphSetConditional(buildNode, build ? 1u : 0u);
+    if (!build) return;
     if ((int)threadIdx.x < world) pairCounts[threadIdx.x] = 0u;
     if (threadIdx.x == 0) { *chunkCounter = 0; longCount[0] = 0; longCount[1] = 0; }
 }
@@ -94,7 +98,8 @@ __global__ void __launch_bounds__(256) k_rep_count(const PairSource src, int* __
     }
 }
 
-// exclusive scan of m integers in three small kernels: sums of 1024-item blocks, scan of those sums by one block, local scans
+// exclusive scan of m integers (64-bit offsets: a dense phase can list billions of entries) in three small kernels: sums of 1024-item
+// blocks, scan of those sums by one block, local scans
 constexpr int kScanItems = 1024;
 __global__ void __launch_bounds__(256) k_scan_sums(const int* __restrict__ in, int m, int* __restrict__ blockSums, const StepCtrl* __restrict__ ctrl) {
     if (build_skipped(ctrl, 0)) return;
@@ -109,38 +114,39 @@ __global__ void __launch_bounds__(256) k_scan_sums(const int* __restrict__ in, i
     __syncthreads();
     if (threadIdx.x == 0) { int tot = 0; for (int w = 0; w < 8; ++w) tot += sm[w]; blockSums[blockIdx.x] = tot; }
 }
-__global__ void __launch_bounds__(1024) k_scan_offsets(int* __restrict__ blockSums, int numBlocks, const StepCtrl* __restrict__ ctrl) {
+__global__ void __launch_bounds__(1024) k_scan_offsets(const int* __restrict__ blockSums, long long* __restrict__ blockOffsets, int numBlocks,
+                                                       const StepCtrl* __restrict__ ctrl) {
     if (build_skipped(ctrl, 0)) return;
-    __shared__ int sm[32];
-    __shared__ int carry;
+    __shared__ long long sm[32];
+    __shared__ long long carry;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int base = 0; base < numBlocks; base += 1024) {
         const int i = base + threadIdx.x;
-        const int val = i < numBlocks ? blockSums[i] : 0;
-        int inc = val;
+        const long long val = i < numBlocks ? (long long)blockSums[i] : 0ll;
+        long long inc = val;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
         if (lane == 31) sm[warp] = inc;
         __syncthreads();
         if (warp == 0) {
-            int w = sm[lane];
+            long long w = sm[lane];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+            for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
             sm[lane] = w;
         }
         __syncthreads();
-        const int before = carry + (warp > 0 ? sm[warp - 1] : 0) + inc - val;
-        if (i < numBlocks) blockSums[i] = before;
+        const long long before = carry + (warp > 0 ? sm[warp - 1] : 0ll) + inc - val;
+        if (i < numBlocks) blockOffsets[i] = before;
         __syncthreads();
         if (threadIdx.x == 0) carry += sm[31];
         __syncthreads();
     }
-    if (threadIdx.x == 0) blockSums[numBlocks] = carry;       // grand total
+    if (threadIdx.x == 0) blockOffsets[numBlocks] = carry;    // grand total
 }
-__global__ void __launch_bounds__(256) k_scan_apply(const int* __restrict__ in, int m, const int* __restrict__ blockSums, int numBlocks,
-                                                    int* __restrict__ out /* [m + 1] */, const StepCtrl* __restrict__ ctrl) {
+__global__ void __launch_bounds__(256) k_scan_apply(const int* __restrict__ in, int m, const long long* __restrict__ blockOffsets, int numBlocks,
+                                                    long long* __restrict__ out /* [m + 1] */, const StepCtrl* __restrict__ ctrl) {
     if (build_skipped(ctrl, 0)) return;
     __shared__ int sm[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -154,15 +160,15 @@ __global__ void __launch_bounds__(256) k_scan_apply(const int* __restrict__ in, 
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
     if (lane == 31) sm[warp] = inc;
     __syncthreads();
-    int before = blockSums[blockIdx.x] + inc - mine;
+    long long before = blockOffsets[blockIdx.x] + inc - mine;
     for (int w = 0; w < warp; ++w) before += sm[w];
 #pragma unroll
     for (int k = 0; k < 4; ++k) { if (first + k < m) out[first + k] = before; before += v[k]; }
-    if (blockIdx.x == 0 && threadIdx.x == 0) out[m] = blockSums[numBlocks];
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[m] = blockOffsets[numBlocks];
 }
 
 // entries; leaves deg all zero again for the next build and declares the list valid
-__global__ void __launch_bounds__(256) k_rep_fill(const PairSource src, int* __restrict__ deg, const int* __restrict__ repRowPtr /* indexed by vertex */,
+__global__ void __launch_bounds__(256) k_rep_fill(const PairSource src, int* __restrict__ deg, const long long* __restrict__ repRowPtr /* indexed by vertex */,
                                                   int* __restrict__ repCol, StepCtrl* ctrl) {
     if (build_skipped(ctrl, 0)) return;
     for (int s = 0; s < src.world; ++s) {
@@ -183,13 +189,14 @@ __global__ void __launch_bounds__(256) k_rep_fill(const PairSource src, int* __r
 // or in global memory beyond kWarpSortMax entries.  Hub rows (summed in fixed point by k_hub_rows) are left alone.
 constexpr int kShortRow = 8;
 constexpr int kWarpSortMax = 1024;
-__global__ void __launch_bounds__(256) k_rep_sort_rows(const int* __restrict__ repRowPtr, int* __restrict__ repCol, int ownBegin, int ownEnd,
+__global__ void __launch_bounds__(256) k_rep_sort_rows(const long long* __restrict__ repRowPtr, int* __restrict__ repCol, int ownBegin, int ownEnd,
                                                        const int* __restrict__ hubSlot, int* __restrict__ longRows, int* __restrict__ numLong,
                                                        const StepCtrl* __restrict__ ctrl) {
     if (build_skipped(ctrl, 0)) return;
     const int v = ownBegin + blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= ownEnd || (hubSlot && hubSlot[v] >= 0)) return;
-    const int b = repRowPtr[v], len = repRowPtr[v + 1] - b;
+    const long long b = repRowPtr[v];
+    const int len = (int)(repRowPtr[v + 1] - b);
     if (len < 2) return;
     if (len > kShortRow) { longRows[atomicAdd(numLong, 1)] = v; return; }
     int key[kShortRow];
@@ -211,7 +218,7 @@ __global__ void __launch_bounds__(256) k_rep_sort_rows(const int* __restrict__ r
 // one warp per queued row; rows are taken from the queue in any order (each row is sorted independently).  Up to kWarpSortMax entries:
 // bitonic network on a padded copy in shared memory.  Beyond: rank sort through `scratch` (partner ids of a row are distinct, so
 // the rank of an entry = the number of smaller entries), O(len^2 / 32) per warp - such rows only exist for a few steps of a dense phase.
-__global__ void __launch_bounds__(256) k_rep_sort_long(const int* __restrict__ repRowPtr, int* __restrict__ repCol, int* __restrict__ scratch,
+__global__ void __launch_bounds__(256) k_rep_sort_long(const long long* __restrict__ repRowPtr, int* __restrict__ repCol, int* __restrict__ scratch,
                                                        const int* __restrict__ longRows, const int* __restrict__ numLong, int* __restrict__ cursor,
                                                        const StepCtrl* __restrict__ ctrl) {
     if (build_skipped(ctrl, 0)) return;
@@ -224,7 +231,8 @@ __global__ void __launch_bounds__(256) k_rep_sort_long(const int* __restrict__ r
         at = __shfl_sync(0xffffffffu, at, 0);
         if (at >= total) break;
         const int v = longRows[at];
-        const int b = repRowPtr[v], len = repRowPtr[v + 1] - b;
+        const long long b = repRowPtr[v];
+        const int len = (int)(repRowPtr[v + 1] - b);
         if (len <= kWarpSortMax) {
             int size = 32;
             while (size < len) size <<= 1;
@@ -302,7 +310,7 @@ __device__ __forceinline__ float chunk_dist2(float4 a, float4 b) {
 template <int V>
 __global__ void __launch_bounds__(256, WB_FUSED_MINBLOCKS)
 k_step_fused(const float4* __restrict__ x, const float* __restrict__ iw, const int* __restrict__ rowPtr, const int* __restrict__ col,
-             const int* __restrict__ repRowPtr, const int* __restrict__ repCol, int rangeBegin, int rangeEnd, int vertsPerBlock,
+             const long long* __restrict__ repRowPtr, const int* __restrict__ repCol, int rangeBegin, int rangeEnd, int vertsPerBlock,
              const ForceParams fp, const StepDyn* __restrict__ dynp, const int* __restrict__ hubSlot, const double* __restrict__ hubD,
              const long long* __restrict__ hubF, float4* __restrict__ xNew, float4* __restrict__ mom1, float4* __restrict__ mom2,
              float4* __restrict__ forceOut, const Replicas<double> blockPartials /* [block][K + 1] on every rank */,
@@ -331,13 +339,16 @@ k_step_fused(const float4* __restrict__ x, const float* __restrict__ iw, const i
         float4 xv = zero4;
         float iwv = 1.f;
         double acc[4] = {0.0, 0.0, 0.0, 0.0}, lossA = 0.0, lossR = 0.0;
-        int nCoincident = 0, nPairs = 0, e = 0, lenA = 0, re = 0, lenR = 0, hub = -1;
+        int nCoincident = 0, nPairs = 0, e = 0, lenA = 0, lenR = 0, hub = -1;
+        const int* repRow = repCol;                                // this vertex' row of the pair list
         if (valid) {
             if (chunkLane) xv = __ldg(x + at);
             iwv = __ldg(iw + v);
             hub = hubSlot ? __ldg(hubSlot + v) : -1;
-            e = __ldg(rowPtr + v); re = __ldg(repRowPtr + v);
-            lenR = __ldg(repRowPtr + v + 1) - re;
+            e = __ldg(rowPtr + v);
+            const long long re = __ldg(repRowPtr + v);
+            repRow = repCol + re;
+            lenR = (int)(__ldg(repRowPtr + v + 1) - re);
             sumEntries += c == 0 ? lenR : 0;
             if (hub < 0) lenA = __ldg(rowPtr + v + 1) - e; else lenR = 0;
         }
@@ -416,7 +427,7 @@ k_step_fused(const float4* __restrict__ x, const float* __restrict__ iw, const i
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 has[j] = i + j < lenR;
-                u[j] = has[j] ? __ldg(repCol + re + i + j) : 0;
+                u[j] = has[j] ? __ldg(repRow + i + j) : 0;
             }
 #pragma unroll
             for (int j = 0; j < 2; ++j) r[j] = (has[j] && chunkLane) ? __ldg(xc + (int64_t)u[j] * V) : xv;
@@ -565,7 +576,7 @@ k_step_fused(const float4* __restrict__ x, const float* __restrict__ iw, const i
 // of walking the rows itself.
 template <int V>
 __global__ void __launch_bounds__(256) k_hub_rows(const float4* __restrict__ x, const float* __restrict__ iw, const int* __restrict__ rowPtr,
-                                                  const int* __restrict__ col, const int* __restrict__ repRowPtr, const int* __restrict__ repCol,
+                                                  const int* __restrict__ col, const long long* __restrict__ repRowPtr, const int* __restrict__ repCol,
                                                   const int* __restrict__ hubVertex, int ownBegin, int ownEnd, const ForceParams fp,
                                                   double* __restrict__ hubD, long long* __restrict__ hubF, const StepCtrl* __restrict__ ctrl) {
     if (ctrl->overflow != 0) return;
@@ -602,8 +613,8 @@ __global__ void __launch_bounds__(256) k_hub_rows(const float4* __restrict__ x, 
             }
         }
     }
-    const int rend = repRowPtr[v + 1];
-    for (int e = repRowPtr[v] + threadIdx.x; e < rend; e += 256) {
+    const long long rend = repRowPtr[v + 1];
+    for (long long e = repRowPtr[v] + threadIdx.x; e < rend; e += 256) {
         const int u = repCol[e];
         const float ws = iwv * __ldg(iw + u);
         float4 xu[V];
@@ -731,21 +742,25 @@ __global__ void __launch_bounds__(1024) k_step_tail(const double* __restrict__ f
         return;
     }
     const bool rebuilt = ctrl->rebuild != 0;
-    // columns: 0, 1 = observation sums over the tiles; 2, 3, 4 = walk statistics over the walk's warps (integers)
-    for (int col = 0; col < 5; ++col) {
-        const double* src = col < 2 ? obsPartials + col : walkPartials + (col - 2);
-        const int rows = col < 2 ? numObsTiles : (rebuilt ? walkRows : 0), stride = col < 2 ? 2 : 3;
-        double s = 0.0;
-        for (int r = threadIdx.x; r < rows; r += 1024) s += src[(int64_t)r * stride];
-        sm[threadIdx.x] = s;
-        __syncthreads();
-        for (int o = 512; o > 0; o >>= 1) {
-            if ((int)threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) res[col] = sm[0];
-        __syncthreads();
+    // one pass: thread t adds the observation tiles t, t + 1024, .. (columns 0, 1) and the walk's warps t, t + 1024, .. (integer
+    // statistics, columns 2..4), then the 1024 thread sums are combined by a fixed tree of shuffles and one pass over the 32 warps
+    double part[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int r = threadIdx.x; r < numObsTiles; r += 1024) { part[0] += obsPartials[(int64_t)r * 2]; part[1] += obsPartials[(int64_t)r * 2 + 1]; }
+    if (rebuilt)
+        for (int r = threadIdx.x; r < walkRows; r += 1024) { part[2] += walkPartials[(int64_t)r * 3]; part[3] += walkPartials[(int64_t)r * 3 + 1]; part[4] += walkPartials[(int64_t)r * 3 + 2]; }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part[k] += __shfl_xor_sync(0xffffffffu, part[k], o);
+        if ((threadIdx.x & 31) == 0) sm[(threadIdx.x >> 5) * 5 + k] = part[k];
     }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double t = 0.0;
+        for (int w = 0; w < 32; ++w) t += sm[w * 5 + threadIdx.x];
+        res[threadIdx.x] = t;
+    }
+    __syncthreads();
     // frame of the final layout, from the sample of tiles the recentre pass took moments of (momentCount vertices)
     quant_from_partials(momentPartials, numMomentTiles, momentCount, pol.dim, pol.mortonBits, pol.halfSigmaLimit, qp, sc);
     if (threadIdx.x == 0) {

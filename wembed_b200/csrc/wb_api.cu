@@ -112,7 +112,8 @@ struct wb_embedder {
     unsigned int* pairCounts = nullptr;   // counts matrix [kMaxRanks][kMaxRanks] inside `mail`
     char* mail = nullptr;                 // [flags | counts | block sum rows | observation tiles | moment tiles] (step.cuh: k_exchange)
     size_t mailBytes = 0;
-    int *repDeg = nullptr, *repRowPtr = nullptr, *repCol = nullptr, *scanSums = nullptr, *longRows = nullptr, *longCount = nullptr;
+    int *repDeg = nullptr, *repCol = nullptr, *scanSums = nullptr, *longRows = nullptr, *longCount = nullptr;
+    long long *repRowPtr = nullptr, *scanOffsets = nullptr;
     int scanBlocks = 0;
     float skinMax = 0.f, reuseTarget = 4.f;
     int nextRebuild = 1;                  // what the host knows about the next step: 1 rebuilds (or unknown), 0 reuses the list
@@ -172,6 +173,13 @@ struct wb_embedder {
     struct StageLane { cudaStream_t stream = nullptr; float* pinned[2] = {nullptr, nullptr}; cudaEvent_t done[2] = {nullptr, nullptr}; };
     std::vector<StageLane> stageLanes;
 
+    // the step as a CUDA graph (one GPU, no phase timing): [k_step_begin] -> IF(rebuild){index, search, list} -> [forces .. tail]
+    cudaGraph_t stepGraph = nullptr;
+    cudaGraphExec_t stepExec = nullptr;
+    bool graphWanted = true, graphFailed = false;
+    int graphKernels = 0;                 // kernels one replay launches when it rebuilds (for wb_launch_count)
+    std::string graphNote;
+
     cudaEvent_t marks[8] = {};
     int64_t launches = 0;
     bool timing = false;
@@ -210,7 +218,7 @@ void free_all(wb_embedder* h) {
         }
         h->peersOpen = h->peerPairsOpen = false;
     }
-    F(h->ctrl); F(h->dyn); F(h->pairBuf); F(h->mail); F(h->repDeg); F(h->repRowPtr); F(h->repCol); F(h->scanSums); F(h->longRows); F(h->longCount);
+    F(h->ctrl); F(h->dyn); F(h->pairBuf); F(h->mail); F(h->repDeg); F(h->repRowPtr); F(h->repCol); F(h->scanSums); F(h->scanOffsets); F(h->longRows); F(h->longCount);
     F(h->chunkCounter); F(h->heavyVertex); F(h->heavySlot); F(h->heavyPos); F(h->hubVertex); F(h->hubSlot); F(h->hubD); F(h->hubF); F(h->mtScratch);
     F(h->keysIn); F(h->keysOut); F(h->valsIn); F(h->valsOut); F(h->cubTemp); F(h->quant); F(h->ids); F(h->blk); F(h->blkH);
     for (int l = 0; l < wb::kMaxLevels; ++l) { F(h->lvlLo[l]); if (l > 0) F(h->lvlHi[l]); F(h->lvlBound[l]); }
@@ -224,6 +232,8 @@ void free_all(wb_embedder* h) {
         if (l.stream) cudaStreamDestroy(l.stream);
     }
     h->stageLanes.clear();
+    if (h->stepExec) { cudaGraphExecDestroy(h->stepExec); h->stepExec = nullptr; }
+    if (h->stepGraph) { cudaGraphDestroy(h->stepGraph); h->stepGraph = nullptr; }
     for (auto& e : h->ev) if (e) { cudaEventDestroy(e); e = nullptr; }
     for (auto& e : h->marks) if (e) { cudaEventDestroy(e); e = nullptr; }
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -270,6 +280,10 @@ void invalidate_list(wb_embedder* h) {
     c.numBuilds = 0; c.numReused = 0;
     WB_CUDA(cudaMemcpyAsync(h->ctrl, &c, sizeof(c), cudaMemcpyHostToDevice, h->stream));   // pageable source: the copy is staged before the call returns
     h->nextRebuild = 1;
+    // whatever made the list void (new weights, a grown pair buffer, a new policy, ..) may also have changed arguments a captured
+    // step holds by value: capture it again on the next step
+    if (h->stepExec) { cudaGraphExecDestroy(h->stepExec); h->stepExec = nullptr; }
+    if (h->stepGraph) { cudaGraphDestroy(h->stepGraph); h->stepGraph = nullptr; }
 }
 
 // hub rows (long CSR rows; heavy vertices, whose rows of the pair list are long) and heavy vertices (walked by one block each)
@@ -312,6 +326,11 @@ void rebuild_hub_lists(wb_embedder* h) {
 void allocate_pair_list(wb_embedder* h, unsigned int cap) {
     auto F = [](auto*& p) { if (p) cudaFree(p); p = nullptr; };
     F(h->pairBuf); F(h->repCol);
+    size_t freeBytes = 0, totalBytes = 0;
+    WB_CUDA(cudaMemGetInfo(&freeBytes, &totalBytes));
+    const size_t need = (size_t)cap * h->world * 16;             // pairs + both directions of the CSR
+    if (need > freeBytes - std::min(freeBytes, (size_t)2 << 30))
+        throw std::runtime_error("repulsion pair list: " + std::to_string(need >> 20) + " MiB needed, " + std::to_string(freeBytes >> 20) + " MiB free on the device");
     h->pairCap = cap;                                            // per segment
     h->pairBuf = dalloc<int2>((size_t)cap * h->world);
     h->repCol = dalloc<int>((size_t)2 * cap * h->world + 8);
@@ -325,6 +344,8 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
         h->skinMax = e ? (float)std::atof(e) : 0.3f;
         e = std::getenv("WB_REUSE_STEPS");
         h->reuseTarget = e ? std::max(1.f, (float)std::atof(e)) : 4.f;
+        e = std::getenv("WB_GRAPH");
+        h->graphWanted = !(e && std::atoi(e) == 0);
     }
     // (+ 8: the fused kernel copies whole 16-byte groups of these arrays)
     h->rowPtr = dalloc<int>(n + 1 + 8);
@@ -382,13 +403,14 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
         allocate_pair_list(h, (unsigned int)cap);
     }
     h->repDeg = dalloc<int>(h->rowsAlloc + 8);
-    h->repRowPtr = dalloc<int>(h->rowsAlloc + 1 + 8);
+    h->repRowPtr = dalloc<long long>(h->rowsAlloc + 1 + 8);
     WB_CUDA(cudaMemsetAsync(h->repDeg, 0, sizeof(int) * (h->rowsAlloc + 8), h->stream));
-    WB_CUDA(cudaMemsetAsync(h->repRowPtr, 0, sizeof(int) * (h->rowsAlloc + 1 + 8), h->stream));
+    WB_CUDA(cudaMemsetAsync(h->repRowPtr, 0, sizeof(long long) * (h->rowsAlloc + 1 + 8), h->stream));
     h->longRows = dalloc<int>(std::max(n, 1));
     h->longCount = dalloc<int>(2);        // [rows queued, cursor of the sorting warps]
     h->scanBlocks = div_up(std::max(n, 1), wb::kScanItems);
     h->scanSums = dalloc<int>(h->scanBlocks + 1);
+    h->scanOffsets = dalloc<long long>(h->scanBlocks + 1);
     choose_fixed_scales(h, 1.0, 1.0);
 
     // Morton keys: as many bits per dimension as fit a 32-bit key
@@ -532,23 +554,26 @@ PendingStep take_slot(wb_embedder* h) {
     return p;
 }
 
-// WembedEmbedder::calculateStep (WembedEmbedder.cpp:13-63) as a stream of launches; the step's scalars are in slot.host->dyn.
-void launch_step(wb_embedder* h, const PendingStep& slot) {
+// WembedEmbedder::calculateStep (WembedEmbedder.cpp:13-63) as a stream of launches.  `parts` selects which of them are issued, so that
+// the same code serves direct launches (everything) and the capture of the step graph (build and rest separately).
+enum : int { kPartBegin = 1, kPartBuild = 2, kPartRest = 4, kPartAll = 7 };
+void launch_parts(wb_embedder* h, int parts, bool assumeBuild) {
     const int n = h->n, V = h->V;
     cudaStream_t s = h->stream;
     const wb::ForceParams fp = force_params(h);
-    WB_CUDA(cudaMemcpyAsync(h->dyn, &slot.host->dyn, sizeof(wb::StepDyn), cudaMemcpyHostToDevice, s));
-    if (!h->quantValid) enqueue_frame(h);
+    const bool timing = h->timing && parts == kPartAll;
     // What the host knows: after a blocking step it has read the device's decision for the next one and leaves out the launches of a
     // build that will not happen; with steps in flight it does not know, queues everything, and the kernels of a build return at once
     // on a reuse step (correctness never depends on this knowledge: the device flags alone decide what runs).
-    const bool build = h->nextRebuild != 0 || !h->pending.empty();
+    const bool build = (parts & kPartBuild) && (assumeBuild || h->nextRebuild != 0 || !h->pending.empty());
 
-    if (h->timing) WB_CUDA(cudaEventRecord(h->ev[0], s));
-    wb::k_step_begin<<<1, 32, 0, s>>>(h->ctrl, h->pairCounts + h->rank * wb::kMaxRanks, h->world, h->chunkCounter, h->longCount);
-    h->launches += 1;
+    if (timing) WB_CUDA(cudaEventRecord(h->ev[0], s));
+    if (parts & kPartBegin) {
+        wb::k_step_begin<<<1, 32, 0, s>>>(h->ctrl, h->pairCounts + h->rank * wb::kMaxRanks, h->world, h->chunkCounter, h->longCount, cudaGraphConditionalHandle{}, 0);
+        h->launches += 1;
+    }
     if (build) enqueue_index(h, h->iw, 0);
-    if (h->timing) WB_CUDA(cudaEventRecord(h->ev[1], s));
+    if (timing) WB_CUDA(cudaEventRecord(h->ev[1], s));
     const bool sharded = h->world > 1;
     wb::Peers peers{};
     peers.world = h->world; peers.rank = h->rank;
@@ -587,7 +612,7 @@ void launch_step(wb_embedder* h, const PendingStep& slot) {
             h->launches += 1;
         }
     }
-    if (sharded) {   // every rank's pairs have landed in their owners' buffers, and every rank knows all counts
+    if (sharded && (parts & kPartBuild)) {   // every rank's pairs have landed in their owners' buffers, and every rank knows all counts
         wb::k_exchange<<<1, 32, 0, s>>>(peers, ++h->epoch, 1, h->ctrl);
         h->launches += 1;
     }
@@ -598,14 +623,15 @@ void launch_step(wb_embedder* h, const PendingStep& slot) {
         const int scanBlocks = div_up(own, wb::kScanItems);
         wb::k_rep_count<<<pairBlocks, 256, 0, s>>>(src, h->repDeg, h->ctrl);
         wb::k_scan_sums<<<scanBlocks, 256, 0, s>>>(h->repDeg + h->ownBegin, own, h->scanSums, h->ctrl);
-        wb::k_scan_offsets<<<1, 1024, 0, s>>>(h->scanSums, scanBlocks, h->ctrl);
-        wb::k_scan_apply<<<scanBlocks, 256, 0, s>>>(h->repDeg + h->ownBegin, own, h->scanSums, scanBlocks, h->repRowPtr + h->ownBegin, h->ctrl);
+        wb::k_scan_offsets<<<1, 1024, 0, s>>>(h->scanSums, h->scanOffsets, scanBlocks, h->ctrl);
+        wb::k_scan_apply<<<scanBlocks, 256, 0, s>>>(h->repDeg + h->ownBegin, own, h->scanOffsets, scanBlocks, h->repRowPtr + h->ownBegin, h->ctrl);
         wb::k_rep_fill<<<pairBlocks, 256, 0, s>>>(src, h->repDeg, h->repRowPtr, h->repCol, h->ctrl);
         wb::k_rep_sort_rows<<<div_up(own, 256), 256, 0, s>>>(h->repRowPtr, h->repCol, h->ownBegin, h->ownEnd, h->hubSlot, h->longRows, h->longCount, h->ctrl);
-        wb::k_rep_sort_long<<<148 * 4, 256, 0, s>>>(h->repRowPtr, h->repCol, reinterpret_cast<int*>(h->pairBuf), h->longRows, h->longCount, h->longCount + 1, h->ctrl);
+        wb::k_rep_sort_long<<<148, 256, 0, s>>>(h->repRowPtr, h->repCol, reinterpret_cast<int*>(h->pairBuf), h->longRows, h->longCount, h->longCount + 1, h->ctrl);
         h->launches += 7;
     }
-    if (h->timing) WB_CUDA(cudaEventRecord(h->ev[2], s));
+    if (timing) WB_CUDA(cudaEventRecord(h->ev[2], s));
+    if (!(parts & kPartRest)) { WB_CUDA(cudaGetLastError()); return; }
     if (h->numHubs) {
         WB_DISPATCH_V(V, wb::k_hub_rows<V><<<h->numHubs, 256, 0, s>>>(h->x, h->iw, h->rowPtr, h->col, h->repRowPtr, h->repCol, h->hubVertex, h->ownBegin, h->ownEnd,
                                                                        fp, h->hubD, h->hubF, h->ctrl));
@@ -622,7 +648,7 @@ void launch_step(wb_embedder* h, const PendingStep& slot) {
         h->launches += 1;
     }
     wb::k_reduce_rows<<<h->cols, 256, 0, s>>>(h->blockPartials, h->numBlockRows, h->cols, h->forceSums, h->ctrl);
-    if (h->timing) WB_CUDA(cudaEventRecord(h->ev[3], s));
+    if (timing) WB_CUDA(cudaEventRecord(h->ev[3], s));
     const int obsBegin = h->ownBegin / wb::kObsTile, obsEnd = div_up(h->ownEnd, wb::kObsTile);
     if (obsEnd > obsBegin) {
         if (sharded) {
@@ -642,9 +668,79 @@ void launch_step(wb_embedder* h, const PendingStep& slot) {
     wb::TailPolicy pol{(float)h->opt.edge_length, h->halfSigmaLimit, h->dim, h->mortonBits};
     wb::k_step_tail<<<1, 1024, 0, s>>>(h->forceSums, h->cols, h->obsPartials, h->numObsTiles, h->frameScratch, h->numMomentTiles, h->momentCount, n, h->walkPartials, repWarps + h->numHeavy,
                                         pol, h->quant, h->ctrl, h->stats);
-    if (h->timing) WB_CUDA(cudaEventRecord(h->ev[4], s));
+    if (timing) WB_CUDA(cudaEventRecord(h->ev[4], s));
     h->launches += 5;
     WB_CUDA(cudaGetLastError());
+}
+
+// Captures the step into a graph: root = k_step_begin (arms the conditional), IF node = the kernels of a build, child graph = the rest.
+// Any failure leaves the handle on direct launches for good (graphNote says why).
+void capture_step_graph(wb_embedder* h) {
+    cudaStream_t s = h->stream;
+    cudaGraph_t g = nullptr, rest = nullptr;
+    const int64_t launchesBefore = h->launches;
+    auto bail = [&](const char* what, cudaError_t e) {
+        h->graphFailed = true;
+        h->graphNote = std::string(what) + ": " + cudaGetErrorString(e);
+        cudaStreamCaptureStatus st;
+        if (cudaStreamIsCapturing(s, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone) { cudaGraph_t junk = nullptr; cudaStreamEndCapture(s, &junk); if (junk && junk != g) cudaGraphDestroy(junk); }
+        cudaGetLastError();
+        if (rest) cudaGraphDestroy(rest);
+        if (g) cudaGraphDestroy(g);
+        h->launches = launchesBefore;
+    };
+    cudaError_t e;
+    if ((e = cudaGraphCreate(&g, 0)) != cudaSuccess) return bail("cudaGraphCreate", e);
+    cudaGraphConditionalHandle handle{};
+    if ((e = cudaGraphConditionalHandleCreate(&handle, g, 1, cudaGraphCondAssignDefault)) != cudaSuccess) return bail("cudaGraphConditionalHandleCreate", e);
+    cudaGraphNode_t root = nullptr, cond = nullptr, tail = nullptr;
+    {
+        wb::StepCtrl* ctrl = h->ctrl;
+        unsigned int* counts = h->pairCounts + h->rank * wb::kMaxRanks;
+        int world = h->world, inGraph = 1;
+        int *chunk = h->chunkCounter, *longCount = h->longCount;
+        void* args[] = {&ctrl, &counts, &world, &chunk, &longCount, &handle, &inGraph};
+        cudaKernelNodeParams kp{};
+        kp.func = reinterpret_cast<void*>(wb::k_step_begin);
+        kp.gridDim = dim3(1); kp.blockDim = dim3(32); kp.sharedMemBytes = 0; kp.kernelParams = args; kp.extra = nullptr;
+        if ((e = cudaGraphAddKernelNode(&root, g, nullptr, 0, &kp)) != cudaSuccess) return bail("cudaGraphAddKernelNode", e);
+    }
+    cudaGraphNodeParams cp{};
+    cp.type = cudaGraphNodeTypeConditional;
+    cp.conditional.handle = handle;
+    cp.conditional.type = cudaGraphCondTypeIf;
+    cp.conditional.size = 1;
+    if ((e = cudaGraphAddNode(&cond, g, &root, 1, &cp)) != cudaSuccess) return bail("cudaGraphAddNode (conditional)", e);
+    cudaGraph_t body = cp.conditional.phGraph_out[0];
+    if ((e = cudaStreamBeginCaptureToGraph(s, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed)) != cudaSuccess) return bail("cudaStreamBeginCaptureToGraph", e);
+    try { launch_parts(h, kPartBuild, true); } catch (const wb::CudaError& err) { return bail(err.what, err.code); }
+    cudaGraph_t got = nullptr;
+    if ((e = cudaStreamEndCapture(s, &got)) != cudaSuccess) return bail("cudaStreamEndCapture (build)", e);
+    if ((e = cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed)) != cudaSuccess) return bail("cudaStreamBeginCapture", e);
+    try { launch_parts(h, kPartRest, true); } catch (const wb::CudaError& err) { return bail(err.what, err.code); }
+    if ((e = cudaStreamEndCapture(s, &rest)) != cudaSuccess) return bail("cudaStreamEndCapture (rest)", e);
+    if ((e = cudaGraphAddChildGraphNode(&tail, g, &cond, 1, rest)) != cudaSuccess) return bail("cudaGraphAddChildGraphNode", e);
+    cudaGraphExec_t exec = nullptr;
+    if ((e = cudaGraphInstantiate(&exec, g, 0)) != cudaSuccess) return bail("cudaGraphInstantiate", e);
+    cudaGraphDestroy(rest);
+    h->graphKernels = (int)(h->launches - launchesBefore) + 1;
+    h->launches = launchesBefore;
+    h->stepGraph = g;
+    h->stepExec = exec;
+}
+
+void launch_step(wb_embedder* h, const PendingStep& slot) {
+    cudaStream_t s = h->stream;
+    WB_CUDA(cudaMemcpyAsync(h->dyn, &slot.host->dyn, sizeof(wb::StepDyn), cudaMemcpyHostToDevice, s));
+    if (!h->quantValid) enqueue_frame(h);
+    const bool wantGraph = h->graphWanted && !h->graphFailed && h->world == 1 && !h->timing;
+    if (wantGraph && !h->stepExec) capture_step_graph(h);
+    if (wantGraph && h->stepExec) {
+        WB_CUDA(cudaGraphLaunch(h->stepExec, s));
+        h->launches += h->graphKernels;
+    } else {
+        launch_parts(h, kPartAll, false);
+    }
     WB_CUDA(cudaMemcpyAsync(slot.host->sums, h->stats, sizeof(double) * h->statsTotal, cudaMemcpyDeviceToHost, s));
     WB_CUDA(cudaEventRecord(slot.done, s));
 }
@@ -708,8 +804,15 @@ void enqueue_step(wb_embedder* h, double learningRate) {
 // the device state is that of the step before.  Grow the buffer and run the pending steps again, with the scalars they were queued with.
 void recover_from_overflow(wb_embedder* h, double needed) {
     WB_CUDA(cudaStreamSynchronize(h->stream));
-    const double want = std::max(2.0 * needed, 2.0 * (double)h->pairCap);
-    if (want > 1.0e9) throw std::runtime_error("repulsion pair list exceeds 1e9 pairs");
+    // twice what the overflowing build wanted (a dense phase keeps growing for a step or two), or just above it if memory is short
+    double want = std::max(2.0 * needed, 2.0 * (double)h->pairCap);
+    {
+        size_t freeBytes = 0, totalBytes = 0;
+        WB_CUDA(cudaMemGetInfo(&freeBytes, &totalBytes));
+        const double room = ((double)freeBytes + 16.0 * (double)h->pairCap * h->world) * 0.9 / (16.0 * h->world);   // pairs that fit once the old buffers are gone
+        if (want > room) want = std::max(1.1 * needed, std::min(want, room));
+    }
+    if (want > 4.0e9) throw std::runtime_error("repulsion pair list exceeds 4e9 pairs per producer");
     if (h->world > 1 && h->peerPairsOpen) {      // nobody may still hold a mapping of a buffer that is about to be freed
         for (int p = 0; p < h->world; ++p)
             if (p != h->rank) cudaIpcCloseMemHandle(h->peerPairs[p]);
@@ -1277,6 +1380,12 @@ int wb_elapsed_ms(wb_embedder* h, int from, int to, double* ms) {
 }
 
 int64_t wb_launch_count(wb_embedder* h) { return h ? h->launches : 0; }
+
+int wb_exec_mode(wb_embedder* h, char* note, int32_t note_cap) {
+    if (!h) return fail(WB_ERR_INVALID, "null handle");
+    if (note && note_cap > 0) { std::strncpy(note, h->graphNote.c_str(), (size_t)note_cap - 1); note[note_cap - 1] = 0; }
+    return h->stepExec ? 1 : 0;
+}
 
 int wb_query_candidates(wb_embedder* h, int32_t nq, const int32_t* queries, int64_t* out_offsets, int32_t* out_ids, int64_t cap) {
     if (h && (nq < 0 || (nq > 0 && (!queries || !out_offsets)))) return fail(WB_ERR_INVALID, "wb_query_candidates: bad arguments");
