@@ -269,11 +269,14 @@ def test_graph_replay_equals_direct_launches(device_lib, monkeypatch):
         dev.set_coordinates(x0)
         stats = [dev.step(lr_exponential(it, cooling=0.97)) for it in range(1, steps // 2 + 1)]
         dev.set_weights(w)                                   # forces a new capture
+        inflight = 0
         for it in range(steps // 2 + 1, steps + 1):
             dev.step_async(lr_exponential(it, cooling=0.97))
-            if it % 16 == 0:
+            inflight += 1
+            if inflight == 16:
                 stats.extend(dev.step_collect() for _ in range(16))
-        stats.extend(dev.step_collect() for _ in range(steps - len(stats)))
+                inflight = 0
+        stats.extend(dev.step_collect() for _ in range(inflight))
         out[mode] = (dev.coordinates(), [(s["loss_attract"], s["loss_repel"], s["num_repulsion_pairs"], s["list_rebuilt"]) for s in stats], dev.exec_mode())
         dev.close()
     assert out["1"][2][0] == "graph", out["1"][2]
