@@ -31,6 +31,8 @@ def run(shard):
         if it == warm + 1:
             dev.mark(0)
         stats.append(dev.step(lr_exponential(it)))
+        if os.environ.get("WB_DEBUG") and (it <= 12 or it % 10 == 0):
+            print(f"[check rank {rank}] shard={shard} step {it} pairs {stats[-1]['num_repulsion_pairs']:.0f} listed {stats[-1]['num_listed_pairs']:.0f}", file=sys.stderr, flush=True)
     dev.mark(1)
     ms = dev.elapsed_ms(0, 1) * steps / (steps - warm)
     return dev.coordinates(), stats, ms

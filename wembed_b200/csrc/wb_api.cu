@@ -826,6 +826,7 @@ void recover_from_overflow(wb_embedder* h, double needed) {
     }
     allocate_pair_list(h, (unsigned int)want);
     if (h->world > 1) map_peers(h, false);       // collective: every rank sees the same overflow at the same step
+    if (std::getenv("WB_DEBUG")) std::fprintf(stderr, "[wb rank %d] pair buffer grown to %u pairs per segment, replaying %zu step(s)\n", h->rank, h->pairCap, h->pending.size());
     invalidate_list(h);
     std::deque<PendingStep> again;
     again.swap(h->pending);
@@ -842,7 +843,12 @@ void collect_step(wb_embedder* h, wb_step_stats* out) {
     for (;;) {
         WB_CUDA(cudaEventSynchronize(slot.done));
         if (slot.trivial || slot.host->sums[cols + 8] == 0.0) break;
-        if (slot.host->sums[cols + 8] != 1.0) throw std::runtime_error("sharded step: a peer did not reach the barrier (timeout)");
+        if (slot.host->sums[cols + 8] != 1.0) {
+            const long long code = (long long)slot.host->sums[cols + 9];
+            throw std::runtime_error("sharded step: rank " + std::to_string(h->rank) + " waited 10 s for rank " + std::to_string(code / 1000000) + " at barrier " +
+                                     std::to_string(code % 1000000) + " (of " + std::to_string(h->epoch) + " queued) and gave up");
+        }
+        if (std::getenv("WB_DEBUG")) std::fprintf(stderr, "[wb rank %d] step %lld: pair buffer overflow, %.0f pairs needed, segment capacity %u\n", h->rank, (long long)slot.iteration, slot.host->sums[cols + 9], h->pairCap);
         recover_from_overflow(h, slot.host->sums[cols + 9]);
     }
     h->pending.pop_front();
@@ -1254,6 +1260,7 @@ int wb_comm_init(wb_embedder* h, const char* id128, int32_t rank, int32_t world)
         map_peers(h, true);
         invalidate_list(h);
         WB_CUDA(cudaStreamSynchronize(h->stream));
+        if (std::getenv("WB_DEBUG")) std::fprintf(stderr, "[wb rank %d/%d] owns [%d, %d), %d rows per rank, %u pairs per segment\n", rank, world, h->ownBegin, h->ownEnd, h->rowsPerRank, h->pairCap);
     });
 }
 
