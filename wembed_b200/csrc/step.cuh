@@ -60,7 +60,7 @@ __global__ void k_exchange(const Peers pm, int epoch, int withCounts, StepCtrl* 
         volatile int* flag = reinterpret_cast<volatile int*>(pm.mail[pm.rank] + kMailFlags) + p;
         const long long t0 = clock64();
         while (*flag < epoch) {
-            if (clock64() - t0 > (20ll << 30)) { ctrl->pairNeeded = (unsigned int)(p * 1000000 + (epoch % 1000000)); ctrl->overflow = 2; break; }   // ~10 s: a peer died; the host reports which and when
+            if (clock64() - t0 > (110ll << 30)) { ctrl->pairNeeded = (unsigned int)(p * 1000000 + (epoch % 1000000)); ctrl->overflow = 2; break; }   // ~60 s: a peer died; the host reports which and when
         }
     }
     __syncthreads();

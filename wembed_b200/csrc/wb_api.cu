@@ -745,6 +745,16 @@ void launch_step(wb_embedder* h, const PendingStep& slot) {
     WB_CUDA(cudaEventRecord(slot.done, s));
 }
 
+// host-visible barrier of the ranks of a sharded run (a one-byte all-gather)
+void comm_barrier(wb_embedder* h) {
+    char* token = dalloc<char>(h->world);
+    const bool ok = nccl().allGather(token + h->rank, token, 1, ncclChar, h->comm, h->stream) == ncclSuccess;
+    const cudaError_t err = cudaStreamSynchronize(h->stream);
+    cudaFree(token);
+    if (!ok) throw std::runtime_error("ncclAllGather (barrier) failed");
+    WB_CUDA(err);
+}
+
 // Sharded run: export this rank's buffers and map everybody else's (CUDA IPC; the handles travel through one small NCCL all-gather,
 // which is all NCCL is used for).  all = false: only the pair buffers (they are reallocated when they overflow).
 void map_peers(wb_embedder* h, bool all) {
@@ -778,6 +788,9 @@ void map_peers(wb_embedder* h, bool all) {
     }
     if (all) h->peersOpen = true;
     h->peerPairsOpen = true;
+    // Opening mappings takes the driver anything from milliseconds to seconds per handle when 8 processes do it at once: nobody may
+    // start stepping (and spinning in k_exchange, which gives up after a minute) before everybody has finished
+    comm_barrier(h);
 }
 
 void enqueue_step(wb_embedder* h, double learningRate) {
@@ -817,12 +830,7 @@ void recover_from_overflow(wb_embedder* h, double needed) {
         for (int p = 0; p < h->world; ++p)
             if (p != h->rank) cudaIpcCloseMemHandle(h->peerPairs[p]);
         h->peerPairsOpen = false;
-        char* token = dalloc<char>(h->world);      // host-visible barrier: everybody has closed before anybody frees
-        const bool ok = nccl().allGather(token + h->rank, token, 1, ncclChar, h->comm, h->stream) == ncclSuccess;
-        const cudaError_t err = cudaStreamSynchronize(h->stream);
-        cudaFree(token);
-        if (!ok) throw std::runtime_error("ncclAllGather (barrier) failed");
-        WB_CUDA(err);
+        comm_barrier(h);                             // everybody has closed before anybody frees
     }
     allocate_pair_list(h, (unsigned int)want);
     if (h->world > 1) map_peers(h, false);       // collective: every rank sees the same overflow at the same step
@@ -845,7 +853,7 @@ void collect_step(wb_embedder* h, wb_step_stats* out) {
         if (slot.trivial || slot.host->sums[cols + 8] == 0.0) break;
         if (slot.host->sums[cols + 8] != 1.0) {
             const long long code = (long long)slot.host->sums[cols + 9];
-            throw std::runtime_error("sharded step: rank " + std::to_string(h->rank) + " waited 10 s for rank " + std::to_string(code / 1000000) + " at barrier " +
+            throw std::runtime_error("sharded step: rank " + std::to_string(h->rank) + " waited a minute for rank " + std::to_string(code / 1000000) + " at barrier " +
                                      std::to_string(code % 1000000) + " (of " + std::to_string(h->epoch) + " queued) and gave up");
         }
         if (std::getenv("WB_DEBUG")) std::fprintf(stderr, "[wb rank %d] step %lld: pair buffer overflow, %.0f pairs needed, segment capacity %u\n", h->rank, (long long)slot.iteration, slot.host->sums[cols + 9], h->pairCap);
