@@ -304,36 +304,6 @@ __device__ __forceinline__ float chunk_dist2(float4 a, float4 b) {
     return d2;
 }
 
-// Bulk asynchronous copies (the TMA unit's non-tensor path, `cp.async.bulk`) with completion on an mbarrier: used by the fused kernel to
-// bring the Adam moments of a warp's vertices into shared memory while the warp is busy with the partner gathers.
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WB_WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WB_DONE_%=;\n"
-        "bra WB_WAIT_%=;\n"
-        "WB_DONE_%=:\n"
-        "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
-}
-// global -> shared (bytes: multiple of 16, both addresses 16-byte aligned); completion is counted on `bar`
-__device__ __forceinline__ void bulk_copy(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)), "l"(src),
-                 "r"(bytes), "r"(smem_addr(bar))
-                 : "memory");
-}
-
-#ifndef WB_FUSED_BULK_MV
-#define WB_FUSED_BULK_MV 1
-#endif
 #ifndef WB_FUSED_MINBLOCKS
 #define WB_FUSED_MINBLOCKS 4
 #endif
@@ -350,22 +320,8 @@ k_step_fused(const float4* __restrict__ x, const float* __restrict__ iw, const i
     __shared__ uint32_t mtState[8][624];
     __shared__ double unitBuf[8][VPW][4 * V];
     __shared__ double redBuf[8][K + 1];
-#if WB_FUSED_BULK_MV
-    // the Adam moments of the VPW vertices a warp handles in one pass are two contiguous runs of VPW * V float4: one lane asks the
-    // copy unit for them at the top of the pass, the warp picks them up in the epilogue (mbarrier), after the partner gathers
-    __shared__ __align__(16) float4 smMV[8][2][VPW * V];
-    __shared__ __align__(8) uint64_t mvBar[8];
-    uint32_t mvPhase = 0;
-#endif
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = lane % G, gi = lane / G;
     const bool chunkLane = c < V;                                  // lanes G > V (V = 3, 5, 6, 7) only take part in the shuffles
-#if WB_FUSED_BULK_MV
-    if (lane == 0) {
-        mbar_init(&mvBar[warp], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-#endif
     const int vBegin = rangeBegin + blockIdx.x * vertsPerBlock;     // rangeBegin and vertsPerBlock are multiples of VPB
     const int vEnd = min(rangeEnd, vBegin + vertsPerBlock);
     const float L = fp.edgeLength;
@@ -380,17 +336,6 @@ k_step_fused(const float4* __restrict__ x, const float* __restrict__ iw, const i
         const int v = vBase + warp * VPW + gi;
         const bool valid = v < vEnd;
         const int64_t at = (int64_t)v * V + c;
-#if WB_FUSED_BULK_MV
-        const int mvRows = fp.optimizer == 1 ? max(0, min(VPW, vEnd - (vBase + warp * VPW))) : 0;     // warp-uniform
-        __syncwarp();                                              // the previous pass has read its moments
-        if (lane == 0 && mvRows > 0) {
-            const uint32_t bytes = (uint32_t)mvRows * V * 16u;
-            const int64_t first = (int64_t)(vBase + warp * VPW) * V;
-            mbar_expect_tx(&mvBar[warp], 2u * bytes);
-            bulk_copy(smMV[warp][0], mom1 + first, bytes, &mvBar[warp]);
-            bulk_copy(smMV[warp][1], mom2 + first, bytes, &mvBar[warp]);
-        }
-#endif
         float4 xv = zero4;
         float iwv = 1.f;
         double acc[4] = {0.0, 0.0, 0.0, 0.0}, lossA = 0.0, lossR = 0.0;
@@ -555,9 +500,6 @@ k_step_fused(const float4* __restrict__ x, const float* __restrict__ iw, const i
             __syncwarp();
         }
         float disp2 = 0.f;
-#if WB_FUSED_BULK_MV
-        if (mvRows > 0) { mbar_wait(&mvBar[warp], mvPhase); mvPhase ^= 1u; }       // the moments of this pass have landed
-#endif
         if (valid && chunkLane) {
             float4 f = make_float4((float)acc[0], (float)acc[1], (float)acc[2], (float)acc[3]);
             if (fp.centreScale != 0.f) {                   // :296-301
@@ -567,11 +509,7 @@ k_step_fused(const float4* __restrict__ x, const float* __restrict__ iw, const i
             if (fp.keepForces) forceOut[at] = f;
             float4 xn;
             if (fp.optimizer == 1) {
-#if WB_FUSED_BULK_MV
-                const float4 m = smMV[warp][0][gi * V + c], s = smMV[warp][1][gi * V + c];
-#else
                 const float4 m = mom1[at], s = mom2[at];
-#endif
                 const float fe[4] = {f.x, f.y, f.z, f.w};
                 float me[4] = {m.x, m.y, m.z, m.w}, se[4] = {s.x, s.y, s.z, s.w};
                 float xe[4] = {xv.x, xv.y, xv.z, xv.w};
