@@ -142,8 +142,8 @@ def measured_peak_gbs():
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures summarised in profiles/r2_summary.md
 # (c3; the window of the trajectory each capture was taken in is part of the record)
 NCU_TRAFFIC = {
-    "repel": {"bytes": None, "window": None},
-    "attract_update": {"bytes": None, "window": None},
+    "repel": {"bytes": 46.96e6 + 5.59e6, "window": "step 15 of c3 (profiles/r2_ncu_step15.csv); step 100: 103.9 + 20.7 MB"},
+    "attract_update": {"bytes": 171.8e6 + 114.6e6, "window": "step 15 of c3 (profiles/r2_ncu_step15.csv); step 100: 180.2 + 117.9 MB"},
 }
 
 

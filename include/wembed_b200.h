@@ -178,9 +178,10 @@ int wb_query_candidates(wb_embedder* h, int32_t nq, const int32_t* queries, int6
                         int32_t* out_ids, int64_t cap);
 
 /* Device time (ms, CUDA events) of each phase of the most recent wb_step:
- * [0] index  [1] attract + optimizer (fused)  [2] repel (kernels + row reduce-scatter)  [3] row reduce-scatter of a sharded run
- * [4] recentre+observe  [5] total.
- * Mirrors the util::Timer keys of WembedEmbedder.cpp:28-58. Requires wb_enable_timing(h,1). */
+ * [0] index rebuild  [1] forces + optimizer (k_hub_rows, k_step_fused, k_reduce_rows)  [2] repulsion search + pair list  [3] unused (0)
+ * [4] recentre + observe + tail  [5] total.  [0] and [2] are ~0 on a step that reused its pair list.
+ * Mirrors the util::Timer keys of WembedEmbedder.cpp:28-58. Requires wb_enable_timing(h,1), which also makes the step use direct
+ * launches instead of the step graph. */
 int wb_enable_timing(wb_embedder* h, int enable);
 int wb_get_phase_times(wb_embedder* h, double* ms6);
 

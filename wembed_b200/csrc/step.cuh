@@ -30,8 +30,9 @@ __global__ void k_step_begin(StepCtrl* ctrl, unsigned int* pairCounts /* this ra
 // Sharded run (wb_comm_init): every rank maps the other ranks' buffers (CUDA IPC over NVLink) and the kernels that produce data other
 // ranks need store it straight into the consumers' memory - found pairs into the owners' inboxes (walk.cuh), a block's sums into every
 // rank's copy of the sum rows, recentred positions into every replica of x.  What is left of the collectives is a barrier:
-// k_exchange publishes "my kernels up to here are done" to every peer (release at system scope) and waits until every peer has said
-// the same.  Mail = one buffer per rank: [flags | counts matrix | block sum rows | observation tiles | moment tiles].
+// k_exchange publishes "my kernels up to here are done" to every peer and waits until every peer has said the same.  The producing
+// kernels end with a system-scope fence in every thread that stored into a peer, so their data has arrived before the flag is sent
+// (without it, 8 GPUs writing 28 MB each into the fabric let flags overtake rows: measured as diverging trajectories at 8 ranks).  Mail = one buffer per rank: [flags | counts matrix | block sum rows | observation tiles | moment tiles].
 constexpr int kMailFlags = 0;                      // int[kMaxRanks]: last barrier epoch each peer has reached
 constexpr int kMailCounts = 64;                    // unsigned[kMaxRanks][kMaxRanks]: pairs produced by rank p for rank d
 constexpr int kMailData = 64 + 4 * kMaxRanks * kMaxRanks;
@@ -568,6 +569,7 @@ k_step_fused(const float4* __restrict__ x, const float* __restrict__ iw, const i
         if (threadIdx.x < K) { for (int w = 1; w < 8; ++w) sacc += redBuf[w][threadIdx.x]; }
         else { for (int w = 1; w < 8; ++w) sacc = fmax(sacc, redBuf[w][threadIdx.x]); }
         for (int q = 0; q < blockPartials.world; ++q) blockPartials.at[q][(int64_t)blockRow * (K + 1) + threadIdx.x] = sacc;
+        if (blockPartials.world > 1) __threadfence_system();     // stores into peers' memory must have arrived before the kernel counts as done
     }
 }
 
@@ -677,10 +679,12 @@ __global__ void __launch_bounds__(256) k_reduce_rows(const double* __restrict__ 
 // applyGravityCentre + observeDisplacement (WembedEmbedder.cpp:303-352): x = xnew - centroid and the sums of ||x - xprev|| and
 // ||x||^2.  One block per tile of kObsTile vertices (global tiles: the partial sums do not depend on the grid or on the number of
 // GPUs).  forceSums = output of k_reduce_rows ({lossA, lossR, pairs, list entries, sum xnew[k], max displacement}).
-// MULTI: a sharded run stores the new rows into every replica of x and the tile sums into every rank's copy (peers over NVLink).
+// MULTI: a sharded run stores the tile sums into every rank's copy (peers over NVLink); the new rows themselves are published to the
+// other replicas of x by k_publish_rows right after this kernel (one coalesced 512-byte store per warp and peer: scattering 16-byte
+// stores to 7 peers from inside this kernel ran at a quarter of that).
 constexpr int kMomentSample = 256;        // vertices per tile that feed the next quantisation frame (k_moments after this pass)
 template <int V, bool MULTI>
-__global__ void __launch_bounds__(256) k_recentre_observe(float4* x, const Replicas<float4> xPeers, const float4* __restrict__ xNew, int n, int tileBegin, int dim,
+__global__ void __launch_bounds__(256) k_recentre_observe(float4* x, const float4* __restrict__ xNew, int n, int tileBegin, int dim,
                                                           const double* __restrict__ forceSums, double* __restrict__ obsPartials /* [tile][2] */,
                                                           const Replicas<double> obsPeers, int rank, const StepCtrl* __restrict__ ctrl) {
     if (ctrl->overflow != 0) return;
@@ -699,10 +703,6 @@ __global__ void __launch_bounds__(256) k_recentre_observe(float4* x, const Repli
             const float4 a = xNew[at], o = x[at];
             const float4 r = make_float4(a.x - cen[4 * c], a.y - cen[4 * c + 1], a.z - cen[4 * c + 2], a.w - cen[4 * c + 3]);
             x[at] = r;
-            if constexpr (MULTI) {
-                for (int q = 0; q < xPeers.world; ++q)
-                    if (q != rank) xPeers.at[q][at] = r;
-            }
             disp2 = fmaf(r.x - o.x, r.x - o.x, disp2); disp2 = fmaf(r.y - o.y, r.y - o.y, disp2);
             disp2 = fmaf(r.z - o.z, r.z - o.z, disp2); disp2 = fmaf(r.w - o.w, r.w - o.w, disp2);
             rad2 = fmaf(r.x, r.x, rad2); rad2 = fmaf(r.y, r.y, rad2); rad2 = fmaf(r.z, r.z, rad2); rad2 = fmaf(r.w, r.w, rad2);
@@ -717,7 +717,22 @@ __global__ void __launch_bounds__(256) k_recentre_observe(float4* x, const Repli
             for (int q = 0; q < obsPeers.world; ++q)
                 if (q != rank) obsPeers.at[q][(int64_t)tile * 2 + threadIdx.x] = v;
         }
+        __threadfence_system();                                    // see k_publish_rows
     }
+}
+
+// Sharded run: the rows [first, first + count) of x this rank has just recentred -> every other replica of x.  Every thread ends with a
+// system-scope fence: the stores must have ARRIVED in the peers' memory before this kernel counts as done, because the barrier's flags
+// (k_exchange) travel separately and must not overtake them in the NVLink fabric.
+__global__ void __launch_bounds__(256) k_publish_rows(const float4* __restrict__ x, const Replicas<float4> peers, int rank, int64_t first, int64_t count,
+                                                      const StepCtrl* __restrict__ ctrl) {
+    if (ctrl->overflow != 0) return;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = x[first + i];
+        for (int q = 0; q < peers.world; ++q)
+            if (q != rank) peers.at[q][first + i] = v;
+    }
+    __threadfence_system();
 }
 
 // ---------------------------------------------------------------------------------------------

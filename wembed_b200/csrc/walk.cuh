@@ -417,6 +417,9 @@ k_repulse_pairs(const TreeView t, const int* __restrict__ rowPtr, const int* __r
         partials[3 * w + 1] = totalTests;
         partials[3 * w + 2] = totalBoxTests;
     }
+    // sharded run: this thread's pairs went into other GPUs' memory; they must have ARRIVED there before this kernel counts as done,
+    // because the "done" flag travels separately (k_exchange) and must not overtake them in the NVLink fabric
+    if (sink.world > 1) __threadfence_system();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -489,6 +492,7 @@ __global__ void __launch_bounds__(256) k_repulse_heavy(const TreeView t, const i
         }
     }
     block_sum<3, 256>(vals, redBuf, partials + (int64_t)blockIdx.x * 3);
+    if (sink.world > 1) __threadfence_system();               // see k_repulse_pairs
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -652,10 +652,13 @@ void launch_parts(wb_embedder* h, int parts, bool assumeBuild) {
     const int obsBegin = h->ownBegin / wb::kObsTile, obsEnd = div_up(h->ownEnd, wb::kObsTile);
     if (obsEnd > obsBegin) {
         if (sharded) {
-            WB_DISPATCH_V(V, (wb::k_recentre_observe<V, true><<<obsEnd - obsBegin, 256, 0, s>>>(h->x, xOut, h->xNew, n, obsBegin, h->dim, h->forceSums, h->obsPartials, obsOut,
+            WB_DISPATCH_V(V, (wb::k_recentre_observe<V, true><<<obsEnd - obsBegin, 256, 0, s>>>(h->x, h->xNew, n, obsBegin, h->dim, h->forceSums, h->obsPartials, obsOut,
                                                                                                h->rank, h->ctrl)));
+            // the recentred rows -> every other replica of x
+            wb::k_publish_rows<<<148 * 4, 256, 0, s>>>(h->x, xOut, h->rank, (int64_t)h->ownBegin * V, (int64_t)(h->ownEnd - h->ownBegin) * V, h->ctrl);
+            h->launches += 1;
         } else {
-            WB_DISPATCH_V(V, (wb::k_recentre_observe<V, false><<<obsEnd - obsBegin, 256, 0, s>>>(h->x, xOut, h->xNew, n, obsBegin, h->dim, h->forceSums, h->obsPartials, obsOut,
+            WB_DISPATCH_V(V, (wb::k_recentre_observe<V, false><<<obsEnd - obsBegin, 256, 0, s>>>(h->x, h->xNew, n, obsBegin, h->dim, h->forceSums, h->obsPartials, obsOut,
                                                                                                 0, h->ctrl)));
         }
     }
