@@ -47,8 +47,12 @@ struct Replicas {
     int world;
 };
 
-__global__ void k_exchange(const Peers pm, int epoch, int withCounts, StepCtrl* ctrl) {
+__global__ void k_exchange(const Peers pm, int epoch, int withCounts, StepCtrl* ctrl, long long delayCycles) {
     const int p = threadIdx.x;
+    if (delayCycles > 0) {                         // diagnostics (WB_XCHG_DELAY_US): hold the flags back
+        const long long t0 = clock64();
+        while (clock64() - t0 < delayCycles) {}
+    }
     if (p < pm.world) {
         if (withCounts) {                          // my row of the counts matrix -> every rank (mine included: it is the row I counted into)
             const unsigned int* mine = reinterpret_cast<const unsigned int*>(pm.mail[pm.rank] + kMailCounts) + pm.rank * kMaxRanks;

@@ -164,6 +164,7 @@ struct wb_embedder {
     int2* peerPairs[wb::kMaxRanks] = {};
     bool peersOpen = false, peerPairsOpen = false;
     int epoch = 0;                        // barrier counter (k_exchange)
+    long long xchgDelay = 0;              // diagnostics: cycles k_exchange waits before it sends its flags (WB_XCHG_DELAY_US)
 
     std::deque<PendingStep> pending;
     std::vector<PendingStep> freeSlots;
@@ -344,6 +345,8 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
         h->skinMax = e ? (float)std::atof(e) : 0.3f;
         e = std::getenv("WB_REUSE_STEPS");
         h->reuseTarget = e ? std::max(1.f, (float)std::atof(e)) : 4.f;
+        e = std::getenv("WB_XCHG_DELAY_US");
+        h->xchgDelay = e ? (long long)(std::atof(e) * 1900.0) : 0;
         e = std::getenv("WB_GRAPH");
         h->graphWanted = !(e && std::atoi(e) == 0);
     }
@@ -613,7 +616,7 @@ void launch_parts(wb_embedder* h, int parts, bool assumeBuild) {
         }
     }
     if (sharded && (parts & kPartBuild)) {   // every rank's pairs have landed in their owners' buffers, and every rank knows all counts
-        wb::k_exchange<<<1, 32, 0, s>>>(peers, ++h->epoch, 1, h->ctrl);
+        wb::k_exchange<<<1, 32, 0, s>>>(peers, ++h->epoch, 1, h->ctrl, h->xchgDelay);
         h->launches += 1;
     }
     if (build) {
@@ -644,7 +647,7 @@ void launch_parts(wb_embedder* h, int parts, bool assumeBuild) {
                                                                         rowsOut, h->ctrl));
     }
     if (sharded) {   // every rank's sum rows have arrived everywhere
-        wb::k_exchange<<<1, 32, 0, s>>>(peers, ++h->epoch, 0, h->ctrl);
+        wb::k_exchange<<<1, 32, 0, s>>>(peers, ++h->epoch, 0, h->ctrl, h->xchgDelay);
         h->launches += 1;
     }
     wb::k_reduce_rows<<<h->cols, 256, 0, s>>>(h->blockPartials, h->numBlockRows, h->cols, h->forceSums, h->ctrl);
@@ -663,7 +666,7 @@ void launch_parts(wb_embedder* h, int parts, bool assumeBuild) {
         }
     }
     if (sharded) {   // every replica of x is complete, every rank holds all observation tiles
-        wb::k_exchange<<<1, 32, 0, s>>>(peers, ++h->epoch, 0, h->ctrl);
+        wb::k_exchange<<<1, 32, 0, s>>>(peers, ++h->epoch, 0, h->ctrl, h->xchgDelay);
         h->launches += 1;
     }
     // moments of a sample of the final layout -> the next build's quantisation frame (k_step_tail)
