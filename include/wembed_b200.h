@@ -205,6 +205,10 @@ int wb_get_phase_times(wb_embedder* h, double* ms6);
  */
 int wb_comm_unique_id(char* id128);
 int wb_comm_init(wb_embedder* h, const char* id128, int32_t rank, int32_t world);
+/* Test hook: the same sharded step with all `world` ranks as handles of the calling process on ONE device (plain device pointers instead of
+ * IPC mappings, no NCCL); the handles must then be stepped from `world` host threads at the same time.  The pair buffers of such a group
+ * cannot grow (set WB_PAIR_CAP before wb_create). */
+int wb_comm_init_local(wb_embedder** handles, int32_t world);
 /* [begin, end) of the vertices this handle owns (everything before wb_comm_init). */
 int wb_get_partition(wb_embedder* h, int32_t* begin, int32_t* end);
 

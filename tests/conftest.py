@@ -3,6 +3,9 @@ import sys
 
 import pytest
 
+# the single-process sharded tests step 8 handles from 8 threads: give their streams separate hardware queues
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

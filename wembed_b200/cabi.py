@@ -24,7 +24,7 @@ EXPORTS = (
     "wb_set_coordinates", "wb_set_weights", "wb_get_coordinates", "wb_get_weights", "wb_get_forces", "wb_reset_optimizer",
     "wb_set_iteration", "wb_step", "wb_step_async", "wb_step_collect", "wb_synchronize", "wb_query_candidates",
     "wb_enable_timing", "wb_get_phase_times", "wb_mark", "wb_elapsed_ms", "wb_launch_count", "wb_comm_unique_id", "wb_comm_init", "wb_reconstruction",
-    "wb_edge_detection", "wb_set_list_policy", "wb_get_partition", "wb_exec_mode",
+    "wb_edge_detection", "wb_set_list_policy", "wb_get_partition", "wb_exec_mode", "wb_comm_init_local",
 )
 
 
@@ -86,6 +86,7 @@ def lib():
         "wb_set_list_policy": (C.c_int, [H, C.c_double, C.c_double]),
         "wb_get_partition": (C.c_int, [H, ip, ip]),
         "wb_exec_mode": (C.c_int, [H, C.c_char_p, i32]),
+        "wb_comm_init_local": (C.c_int, [C.POINTER(H), i32]),
         "wb_comm_unique_id": (C.c_int, [C.c_char_p]), "wb_comm_init": (C.c_int, [H, C.c_char_p, i32, i32]),
     }
     for name, (res, args) in sig.items():
@@ -263,6 +264,34 @@ class DeviceEmbedder:
                 continue
             self._check(rc)
             return [ids[offs[i]:offs[i + 1]].copy() for i in range(len(q))]
+
+
+def comm_init_local(devs):
+    """Join DeviceEmbedder handles of this process (one device) into a sharded group; step them from one thread each."""
+    arr = (C.c_void_p * len(devs))(*[d._h for d in devs])
+    rc = lib().wb_comm_init_local(arr, len(devs))
+    if rc != WB_OK:
+        raise WbError(rc, lib().wb_last_error().decode())
+
+
+def step_group(devs, lr):
+    """One step on every handle of a local group, concurrently (the ranks' barrier kernels wait for each other)."""
+    import threading
+    out, err = [None] * len(devs), []
+
+    def run(i):
+        try:
+            out[i] = devs[i].step(lr)
+        except Exception as e:      # noqa: BLE001 - reported below
+            err.append(e)
+    ts = [threading.Thread(target=run, args=(i,)) for i in range(len(devs))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    if err:
+        raise err[0]
+    return out
 
 
 def csr_from_edges(n: int, edges) -> tuple[np.ndarray, np.ndarray]:

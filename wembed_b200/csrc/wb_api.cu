@@ -163,6 +163,7 @@ struct wb_embedder {
     float4* peerX[wb::kMaxRanks] = {};
     int2* peerPairs[wb::kMaxRanks] = {};
     bool peersOpen = false, peerPairsOpen = false;
+    bool localGroup = false;              // wb_comm_init_local: the "ranks" are handles of this process on one device (tests)
     int epoch = 0;                        // barrier counter (k_exchange)
     long long xchgDelay = 0;              // diagnostics: cycles k_exchange waits before it sends its flags (WB_XCHG_DELAY_US)
 
@@ -832,6 +833,7 @@ void recover_from_overflow(wb_embedder* h, double needed) {
         if (want > room) want = std::max(1.1 * needed, std::min(want, room));
     }
     if (want > 4.0e9) throw std::runtime_error("repulsion pair list exceeds 4e9 pairs per producer");
+    if (h->localGroup) throw std::runtime_error("the pair buffer of a local group cannot grow: create the handles with a larger WB_PAIR_CAP");
     if (h->world > 1 && h->peerPairsOpen) {      // nobody may still hold a mapping of a buffer that is about to be freed
         for (int p = 0; p < h->world; ++p)
             if (p != h->rank) cudaIpcCloseMemHandle(h->peerPairs[p]);
@@ -1275,6 +1277,44 @@ int wb_comm_init(wb_embedder* h, const char* id128, int32_t rank, int32_t world)
         invalidate_list(h);
         WB_CUDA(cudaStreamSynchronize(h->stream));
         if (std::getenv("WB_DEBUG")) std::fprintf(stderr, "[wb rank %d/%d] owns [%d, %d), %d rows per rank, %u pairs per segment\n", rank, world, h->ownBegin, h->ownEnd, h->rowsPerRank, h->pairCap);
+    });
+}
+
+// Test hook: the sharded step with all `world` ranks as handles of THIS process on ONE device (same problem on every handle): the peers'
+// buffers are plain device pointers, no IPC, no NCCL.  The handles must then be stepped from `world` host threads at the same time (the
+// barrier kernels of the ranks wait for each other).  Lets the sharded logic be tested where only one GPU is available.
+int wb_comm_init_local(wb_embedder** hs, int32_t world) {
+    if (!hs || world < 2 || world > wb::kMaxRanks) return fail(WB_ERR_INVALID, "wb_comm_init_local: 2 <= world <= 8");
+    for (int r = 0; r < world; ++r) {
+        if (!hs[r] || hs[r]->comm || hs[r]->world != 1 || !hs[r]->pending.empty()) return fail(WB_ERR_INVALID, "wb_comm_init_local: handles must be fresh");
+        if (hs[r]->n != hs[0]->n || hs[r]->V != hs[0]->V || hs[r]->opt.device != hs[0]->opt.device) return fail(WB_ERR_INVALID, "wb_comm_init_local: handles differ");
+    }
+    return guarded(hs[0], [&] {
+        for (int r = 0; r < world; ++r) {
+            wb_embedder* h = hs[r];
+            h->world = world;
+            h->rank = r;
+            h->localGroup = true;
+            const int64_t align = std::lcm((int64_t)h->vertsPerBlock, (int64_t)wb::kObsTile);
+            h->rowsPerRank = (int)(((int64_t)div_up(std::max(h->n, 1), world) + align - 1) / align * align);
+            h->ownBegin = (int)std::min<int64_t>(h->n, (int64_t)r * h->rowsPerRank);
+            h->ownEnd = (int)std::min<int64_t>(h->n, (int64_t)h->ownBegin + h->rowsPerRank);
+            const int blocksPerRank = div_up(div_up(div_up(std::max(h->n, 1), 32), wb::kRepBlockChunks), world);
+            h->repLayout = wb::RepLayout{world, r, blocksPerRank * wb::kRepBlockChunks * 32};
+            allocate_pair_list(h, std::max(1024u, (unsigned int)(((uint64_t)h->pairCap * 2 + world - 1) / world)));
+            WB_CUDA(cudaMemsetAsync(h->mail, 0, wb::kMailData, h->stream));
+            WB_CUDA(cudaStreamSynchronize(h->stream));
+        }
+        for (int r = 0; r < world; ++r) {
+            for (int p = 0; p < world; ++p) {
+                if (p == r) continue;
+                hs[r]->peerMail[p] = hs[p]->mail;
+                hs[r]->peerX[p] = hs[p]->x;
+                hs[r]->peerPairs[p] = hs[p]->pairBuf;
+            }
+            invalidate_list(hs[r]);
+            WB_CUDA(cudaStreamSynchronize(hs[r]->stream));
+        }
     });
 }
 
