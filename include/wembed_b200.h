@@ -206,9 +206,11 @@ int wb_get_phase_times(wb_embedder* h, double* ms6);
 int wb_comm_unique_id(char* id128);
 int wb_comm_init(wb_embedder* h, const char* id128, int32_t rank, int32_t world);
 /* Test hook: the same sharded step with all `world` ranks as handles of the calling process on ONE device (plain device pointers instead of
- * IPC mappings, no NCCL); the handles must then be stepped from `world` host threads at the same time.  The pair buffers of such a group
- * cannot grow (set WB_PAIR_CAP before wb_create). */
+ * IPC mappings, no NCCL).  Such handles only step together, through wb_step_group: it queues the pieces of the step for all handles in
+ * lockstep on one stream, so stream order stands in for the barrier kernels (which then only publish).  stats: `world` records or NULL.
+ * The pair buffers of a local group cannot grow (set WB_PAIR_CAP before wb_create). */
 int wb_comm_init_local(wb_embedder** handles, int32_t world);
+int wb_step_group(wb_embedder** handles, int32_t world, double learning_rate, wb_step_stats* stats);
 /* [begin, end) of the vertices this handle owns (everything before wb_comm_init). */
 int wb_get_partition(wb_embedder* h, int32_t* begin, int32_t* end);
 

@@ -1,7 +1,8 @@
 """The sharded (multi-GPU) step on ONE GPU: `world` handles of this process joined by wb_comm_init_local (plain device pointers instead
-of CUDA IPC mappings), stepped from one host thread each.  Everything a rank does - searching its share of the queries, delivering pairs to
-their owners' buffers, the flag barriers, the global sum rows, publishing its rows to the replicas - runs exactly as on `world` GPUs, and
-the results must equal the single-handle step bit for bit."""
+of CUDA IPC mappings) and stepped by wb_step_group, which queues the pieces of the step for all handles in lockstep on one stream (stream
+order stands in for the waiting of the barrier kernels).  Everything else a rank does - searching its share of the queries, delivering
+pairs to their owners' buffers, the counts matrix, the global sum rows, publishing its rows to the replicas - runs exactly as on `world`
+GPUs, and the results must equal the single-handle step bit for bit."""
 import numpy as np
 import pytest
 

@@ -8,7 +8,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(_HERE, "csrc", "wb_api.cu")
 OUT = os.path.join(_HERE, "lib", "libwembed_b200.so")
-DEPS = [os.path.join(_HERE, "csrc", f) for f in ("wb_api.cu", "kernels.cuh", "common.cuh", "mt19937.cuh")] + [
+DEPS = sorted(os.path.join(_HERE, "csrc", f) for f in os.listdir(os.path.join(_HERE, "csrc")) if f.endswith((".cu", ".cuh"))) + [
     os.path.join(_HERE, "..", "include", "wembed_b200.h")]
 
 

@@ -24,7 +24,7 @@ EXPORTS = (
     "wb_set_coordinates", "wb_set_weights", "wb_get_coordinates", "wb_get_weights", "wb_get_forces", "wb_reset_optimizer",
     "wb_set_iteration", "wb_step", "wb_step_async", "wb_step_collect", "wb_synchronize", "wb_query_candidates",
     "wb_enable_timing", "wb_get_phase_times", "wb_mark", "wb_elapsed_ms", "wb_launch_count", "wb_comm_unique_id", "wb_comm_init", "wb_reconstruction",
-    "wb_edge_detection", "wb_set_list_policy", "wb_get_partition", "wb_exec_mode", "wb_comm_init_local",
+    "wb_edge_detection", "wb_set_list_policy", "wb_get_partition", "wb_exec_mode", "wb_comm_init_local", "wb_step_group",
 )
 
 
@@ -87,6 +87,7 @@ def lib():
         "wb_get_partition": (C.c_int, [H, ip, ip]),
         "wb_exec_mode": (C.c_int, [H, C.c_char_p, i32]),
         "wb_comm_init_local": (C.c_int, [C.POINTER(H), i32]),
+        "wb_step_group": (C.c_int, [C.POINTER(H), i32, C.c_double, C.POINTER(WbStepStats)]),
         "wb_comm_unique_id": (C.c_int, [C.c_char_p]), "wb_comm_init": (C.c_int, [H, C.c_char_p, i32, i32]),
     }
     for name, (res, args) in sig.items():
@@ -275,23 +276,13 @@ def comm_init_local(devs):
 
 
 def step_group(devs, lr):
-    """One step on every handle of a local group, concurrently (the ranks' barrier kernels wait for each other)."""
-    import threading
-    out, err = [None] * len(devs), []
-
-    def run(i):
-        try:
-            out[i] = devs[i].step(lr)
-        except Exception as e:      # noqa: BLE001 - reported below
-            err.append(e)
-    ts = [threading.Thread(target=run, args=(i,)) for i in range(len(devs))]
-    for t in ts:
-        t.start()
-    for t in ts:
-        t.join()
-    if err:
-        raise err[0]
-    return out
+    """One step of a local group (comm_init_local): wb_step_group; returns the handles' step records."""
+    hs = (C.c_void_p * len(devs))(*[d._h for d in devs])
+    st = (WbStepStats * len(devs))()
+    rc = lib().wb_step_group(hs, len(devs), float(lr), st)
+    if rc != WB_OK:
+        raise WbError(rc, lib().wb_last_error().decode())
+    return [st[i].as_dict() for i in range(len(devs))]
 
 
 def csr_from_edges(n: int, edges) -> tuple[np.ndarray, np.ndarray]:

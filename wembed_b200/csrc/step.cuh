@@ -47,12 +47,9 @@ struct Replicas {
     int world;
 };
 
-__global__ void k_exchange(const Peers pm, int epoch, int withCounts, StepCtrl* ctrl, long long delayCycles) {
+// wait = 0: only publish (a local group of handles on one stream: stream order already is the barrier).
+__global__ void k_exchange(const Peers pm, int epoch, int withCounts, int wait, StepCtrl* ctrl) {
     const int p = threadIdx.x;
-    if (delayCycles > 0) {                         // diagnostics (WB_XCHG_DELAY_US): hold the flags back
-        const long long t0 = clock64();
-        while (clock64() - t0 < delayCycles) {}
-    }
     if (p < pm.world) {
         if (withCounts) {                          // my row of the counts matrix -> every rank (mine included: it is the row I counted into)
             const unsigned int* mine = reinterpret_cast<const unsigned int*>(pm.mail[pm.rank] + kMailCounts) + pm.rank * kMaxRanks;
@@ -64,7 +61,7 @@ __global__ void k_exchange(const Peers pm, int epoch, int withCounts, StepCtrl* 
         *(reinterpret_cast<volatile int*>(pm.mail[p] + kMailFlags) + pm.rank) = epoch;
         volatile int* flag = reinterpret_cast<volatile int*>(pm.mail[pm.rank] + kMailFlags) + p;
         const long long t0 = clock64();
-        while (*flag < epoch) {
+        while (wait && *flag < epoch) {
             if (clock64() - t0 > (110ll << 30)) { ctrl->pairNeeded = (unsigned int)(p * 1000000 + (epoch % 1000000)); ctrl->overflow = 2; break; }   // ~60 s: a peer died; the host reports which and when
         }
     }

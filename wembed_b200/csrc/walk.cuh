@@ -128,8 +128,16 @@ struct PairSink {
     int world, rowsPerRank;           // owner(v) = v / rowsPerRank
 };
 
+// One slot of segment `dest` per calling lane.  SHARDED = false: every caller has the same destination and the lanes that are here
+// together share one atomic.  SHARDED = true: the lanes are first grouped by destination (match.any), one atomic per group.
+// (The first version looped over the destinations with the aggregation inside, "lanes with different destinations take turns".  It
+// lost 3 pairs in 10 000 at world = 8 and only there - on 8 GPUs and in the single-process group of tests/test_gpu_sharded_local.py
+// alike: slots were reserved and never written.  nvcc unrolls that loop by four, so only world = 8 runs the unrolled body twice;
+// the same loop under `#pragma unroll 1`, per-lane atomics, and this version all give the single-GPU pair set.)
+template <bool SHARDED>
 __device__ __forceinline__ void append_pair(const PairSink& sink, int dest, int v, int u) {
-    const unsigned m = __activemask();
+    unsigned m = __activemask();
+    if constexpr (SHARDED) m = __match_any_sync(m, dest);
     const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
     unsigned base = 0;
     if (lane == leader) base = atomicAdd(sink.count + dest, (unsigned)__popc(m));
@@ -138,13 +146,10 @@ __device__ __forceinline__ void append_pair(const PairSink& sink, int dest, int 
     if (slot < sink.cap) sink.seg[dest][slot] = make_int2(v, u);   // beyond the capacity: counted only, k_rep_count raises `overflow`
 }
 __device__ __forceinline__ void emit_pair(const PairSink& sink, int v, int u) {
-    if (sink.world == 1) { append_pair(sink, 0, v, u); return; }
+    if (sink.world == 1) { append_pair<false>(sink, 0, v, u); return; }
     const int ov = v / sink.rowsPerRank, ou = u / sink.rowsPerRank;
-    // lanes with different destinations take turns (append_pair aggregates the lanes that are converged at its call)
-    for (int d = 0; d < sink.world; ++d) {
-        if (ov == d) append_pair(sink, d, v, u);
-        else if (ou == d) append_pair(sink, d, v, u);
-    }
+    append_pair<true>(sink, ov, v, u);
+    if (ou != ov) append_pair<true>(sink, ou, v, u);
 }
 
 // warps per block of k_repulse_pairs: the per-warp shared memory (queries + stack) grows with V

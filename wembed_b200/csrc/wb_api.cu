@@ -165,7 +165,6 @@ struct wb_embedder {
     bool peersOpen = false, peerPairsOpen = false;
     bool localGroup = false;              // wb_comm_init_local: the "ranks" are handles of this process on one device (tests)
     int epoch = 0;                        // barrier counter (k_exchange)
-    long long xchgDelay = 0;              // diagnostics: cycles k_exchange waits before it sends its flags (WB_XCHG_DELAY_US)
 
     std::deque<PendingStep> pending;
     std::vector<PendingStep> freeSlots;
@@ -346,8 +345,6 @@ void allocate(wb_embedder* h, const int32_t* rowPtr, const int32_t* col) {
         h->skinMax = e ? (float)std::atof(e) : 0.3f;
         e = std::getenv("WB_REUSE_STEPS");
         h->reuseTarget = e ? std::max(1.f, (float)std::atof(e)) : 4.f;
-        e = std::getenv("WB_XCHG_DELAY_US");
-        h->xchgDelay = e ? (long long)(std::atof(e) * 1900.0) : 0;
         e = std::getenv("WB_GRAPH");
         h->graphWanted = !(e && std::atoi(e) == 0);
     }
@@ -560,7 +557,12 @@ PendingStep take_slot(wb_embedder* h) {
 
 // WembedEmbedder::calculateStep (WembedEmbedder.cpp:13-63) as a stream of launches.  `parts` selects which of them are issued, so that
 // the same code serves direct launches (everything) and the capture of the step graph (build and rest separately).
-enum : int { kPartBegin = 1, kPartBuild = 2, kPartRest = 4, kPartAll = 7 };
+// The step in launchable pieces.  The step graph takes Begin | [Build = Search + List] | Rest = Force + Move + Tail (one GPU: no
+// exchanges); a local group (wb_step_group) runs piece by piece over all its handles, the exchanges in between without waiting.
+enum : int {
+    kPartBegin = 1, kPartSearch = 2, kPartXPairs = 4, kPartList = 8, kPartForce = 16, kPartXRows = 32, kPartMove = 64, kPartXCoords = 128, kPartTail = 256,
+    kPartBuild = kPartSearch | kPartXPairs | kPartList, kPartRest = kPartForce | kPartXRows | kPartMove | kPartXCoords | kPartTail, kPartAll = 511
+};
 void launch_parts(wb_embedder* h, int parts, bool assumeBuild) {
     const int n = h->n, V = h->V;
     cudaStream_t s = h->stream;
@@ -569,14 +571,15 @@ void launch_parts(wb_embedder* h, int parts, bool assumeBuild) {
     // What the host knows: after a blocking step it has read the device's decision for the next one and leaves out the launches of a
     // build that will not happen; with steps in flight it does not know, queues everything, and the kernels of a build return at once
     // on a reuse step (correctness never depends on this knowledge: the device flags alone decide what runs).
-    const bool build = (parts & kPartBuild) && (assumeBuild || h->nextRebuild != 0 || !h->pending.empty());
+    const bool build = assumeBuild || h->nextRebuild != 0 || !h->pending.empty();
+    const int waitPeers = h->localGroup ? 0 : 1;    // a local group shares one stream: stream order is the barrier
 
     if (timing) WB_CUDA(cudaEventRecord(h->ev[0], s));
     if (parts & kPartBegin) {
         wb::k_step_begin<<<1, 32, 0, s>>>(h->ctrl, h->pairCounts + h->rank * wb::kMaxRanks, h->world, h->chunkCounter, h->longCount, cudaGraphConditionalHandle{}, 0);
         h->launches += 1;
     }
-    if (build) enqueue_index(h, h->iw, 0);
+    if (build && (parts & kPartSearch)) enqueue_index(h, h->iw, 0);
     if (timing) WB_CUDA(cudaEventRecord(h->ev[1], s));
     const bool sharded = h->world > 1;
     wb::Peers peers{};
@@ -599,7 +602,7 @@ void launch_parts(wb_embedder* h, int parts, bool assumeBuild) {
     sink.count = h->pairCounts + h->rank * wb::kMaxRanks; sink.cap = h->pairCap; sink.world = h->world; sink.rowsPerRank = std::max(h->rowsPerRank, 1);
     src.counts = h->pairCounts; src.cap = h->pairCap; src.world = h->world; src.rank = h->rank; src.ownBegin = h->ownBegin; src.ownEnd = h->ownEnd;
     const int repWarps = h->repBlocks * wb::repulse_warps(V);
-    if (build) {
+    if (build && (parts & kPartSearch)) {
         // at least ~8 work units per resident warp, else the tail of the dynamic schedule dominates
         const int64_t residentWarps = (int64_t)h->repBlocks * wb::repulse_warps(V);
         const int queriesPerUnit = h->repLayout.segRows / 32 >= 8 * residentWarps ? 32 : (h->repLayout.segRows / 16 >= 8 * residentWarps ? 16 : 8);
@@ -616,11 +619,11 @@ void launch_parts(wb_embedder* h, int parts, bool assumeBuild) {
             h->launches += 1;
         }
     }
-    if (sharded && (parts & kPartBuild)) {   // every rank's pairs have landed in their owners' buffers, and every rank knows all counts
-        wb::k_exchange<<<1, 32, 0, s>>>(peers, ++h->epoch, 1, h->ctrl, h->xchgDelay);
+    if (sharded && (parts & kPartXPairs)) {   // every rank's pairs have landed in their owners' buffers, and every rank knows all counts
+        wb::k_exchange<<<1, 32, 0, s>>>(peers, ++h->epoch, 1, waitPeers, h->ctrl);
         h->launches += 1;
     }
-    if (build) {
+    if (build && (parts & kPartList)) {
         // pair list -> CSR of partners
         const int own = std::max(1, h->ownEnd - h->ownBegin);
         const int pairBlocks = std::max(1, std::min(div_up((int64_t)h->pairCap * h->world, 256), 148 * 8));
@@ -635,26 +638,30 @@ void launch_parts(wb_embedder* h, int parts, bool assumeBuild) {
         h->launches += 7;
     }
     if (timing) WB_CUDA(cudaEventRecord(h->ev[2], s));
-    if (!(parts & kPartRest)) { WB_CUDA(cudaGetLastError()); return; }
-    if (h->numHubs) {
+    if (h->numHubs && (parts & kPartForce)) {
         WB_DISPATCH_V(V, wb::k_hub_rows<V><<<h->numHubs, 256, 0, s>>>(h->x, h->iw, h->rowPtr, h->col, h->repRowPtr, h->repCol, h->hubVertex, h->ownBegin, h->ownEnd,
                                                                        fp, h->hubD, h->hubF, h->ctrl));
         h->launches += 1;
     }
     const int ownBlocks = div_up(std::max(0, h->ownEnd - h->ownBegin), h->vertsPerBlock);
-    if (ownBlocks > 0) {
+    if (ownBlocks > 0 && (parts & kPartForce)) {
         WB_DISPATCH_V(V, wb::k_step_fused<V><<<ownBlocks, 256, 0, s>>>(h->x, h->iw, h->rowPtr, h->col, h->repRowPtr, h->repCol, h->ownBegin, h->ownEnd, h->vertsPerBlock, fp,
                                                                         h->dyn, h->hubSlot, h->hubD, h->hubF, h->xNew, h->mom1, h->mom2, h->force,
                                                                         rowsOut, h->ctrl));
-    }
-    if (sharded) {   // every rank's sum rows have arrived everywhere
-        wb::k_exchange<<<1, 32, 0, s>>>(peers, ++h->epoch, 0, h->ctrl, h->xchgDelay);
         h->launches += 1;
     }
-    wb::k_reduce_rows<<<h->cols, 256, 0, s>>>(h->blockPartials, h->numBlockRows, h->cols, h->forceSums, h->ctrl);
+    if (sharded && (parts & kPartXRows)) {   // every rank's sum rows have arrived everywhere
+        wb::k_exchange<<<1, 32, 0, s>>>(peers, ++h->epoch, 0, waitPeers, h->ctrl);
+        h->launches += 1;
+    }
+    if (parts & kPartMove) {
+        wb::k_reduce_rows<<<h->cols, 256, 0, s>>>(h->blockPartials, h->numBlockRows, h->cols, h->forceSums, h->ctrl);
+        h->launches += 1;
+    }
     if (timing) WB_CUDA(cudaEventRecord(h->ev[3], s));
     const int obsBegin = h->ownBegin / wb::kObsTile, obsEnd = div_up(h->ownEnd, wb::kObsTile);
-    if (obsEnd > obsBegin) {
+    if (obsEnd > obsBegin && (parts & kPartMove)) {
+        h->launches += 1;
         if (sharded) {
             WB_DISPATCH_V(V, (wb::k_recentre_observe<V, true><<<obsEnd - obsBegin, 256, 0, s>>>(h->x, h->xNew, n, obsBegin, h->dim, h->forceSums, h->obsPartials, obsOut,
                                                                                                h->rank, h->ctrl)));
@@ -666,17 +673,19 @@ void launch_parts(wb_embedder* h, int parts, bool assumeBuild) {
                                                                                                 0, h->ctrl)));
         }
     }
-    if (sharded) {   // every replica of x is complete, every rank holds all observation tiles
-        wb::k_exchange<<<1, 32, 0, s>>>(peers, ++h->epoch, 0, h->ctrl, h->xchgDelay);
+    if (sharded && (parts & kPartXCoords)) {   // every replica of x is complete, every rank holds all observation tiles
+        wb::k_exchange<<<1, 32, 0, s>>>(peers, ++h->epoch, 0, waitPeers, h->ctrl);
         h->launches += 1;
     }
-    // moments of a sample of the final layout -> the next build's quantisation frame (k_step_tail)
-    WB_DISPATCH_V(V, wb::k_moments<V><<<h->numObsTiles, 256, 0, s>>>(h->x, n, wb::kMomentSample, h->frameScratch));
-    wb::TailPolicy pol{(float)h->opt.edge_length, h->halfSigmaLimit, h->dim, h->mortonBits};
-    wb::k_step_tail<<<1, 1024, 0, s>>>(h->forceSums, h->cols, h->obsPartials, h->numObsTiles, h->frameScratch, h->numMomentTiles, h->momentCount, n, h->walkPartials, repWarps + h->numHeavy,
-                                        pol, h->quant, h->ctrl, h->stats);
+    if (parts & kPartTail) {
+        // moments of a sample of the final layout -> the next build's quantisation frame (k_step_tail)
+        WB_DISPATCH_V(V, wb::k_moments<V><<<h->numObsTiles, 256, 0, s>>>(h->x, n, wb::kMomentSample, h->frameScratch));
+        wb::TailPolicy pol{(float)h->opt.edge_length, h->halfSigmaLimit, h->dim, h->mortonBits};
+        wb::k_step_tail<<<1, 1024, 0, s>>>(h->forceSums, h->cols, h->obsPartials, h->numObsTiles, h->frameScratch, h->numMomentTiles, h->momentCount, n, h->walkPartials,
+                                            repWarps + h->numHeavy, pol, h->quant, h->ctrl, h->stats);
+        h->launches += 2;
+    }
     if (timing) WB_CUDA(cudaEventRecord(h->ev[4], s));
-    h->launches += 5;
     WB_CUDA(cudaGetLastError());
 }
 
@@ -800,24 +809,62 @@ void map_peers(wb_embedder* h, bool all) {
     comm_barrier(h);
 }
 
-void enqueue_step(wb_embedder* h, double learningRate) {
-    h->iteration++;                                           // EmbedderState::nextStep
+void collect_step(wb_embedder* h, wb_step_stats* out);
+
+// EmbedderState::nextStep + the scalars of the step (host side)
+PendingStep begin_step(wb_embedder* h, double learningRate) {
+    h->iteration++;
     PendingStep slot = take_slot(h);
     slot.iteration = h->iteration;
     slot.trivial = h->n <= 1;
-    if (slot.trivial) {                                       // "Abort in the case of the first hierarchy layer" (:19-21)
-        WB_CUDA(cudaEventRecord(slot.done, h->stream));
-        h->pending.push_back(slot);
-        return;
-    }
+    if (slot.trivial) return slot;                            // "Abort in the case of the first hierarchy layer" (:19-21)
     if (h->opt.optimizer == WB_OPT_ADAM) h->adamT++;          // AdamOptimizer.cpp:19
     slot.host->dyn.lr = (float)learningRate;
     slot.host->dyn.invBias1 = (float)(1.0 / (1.0 - std::pow(0.9, h->adamT)));
     slot.host->dyn.invBias2 = (float)(1.0 / (1.0 - std::pow(0.999, h->adamT)));
     slot.host->dyn.iteration = (uint32_t)h->iteration;
-    launch_step(h, slot);
+    return slot;
+}
+
+void enqueue_step(wb_embedder* h, double learningRate) {
+    if (h->localGroup) throw std::runtime_error("the handles of a local group step together: wb_step_group");
+    PendingStep slot = begin_step(h, learningRate);
+    if (slot.trivial) WB_CUDA(cudaEventRecord(slot.done, h->stream));
+    else launch_step(h, slot);
     h->pending.push_back(slot);
     h->nextRebuild = 1;                                       // unknown until this step has been collected
+}
+
+// One step of a local group (wb_comm_init_local), queued from this one thread on ONE stream, piece by piece over all handles: when a
+// handle's kernels of one piece run, every handle's kernels of the piece before have finished, which is what the barrier kernels of
+// a real sharded run establish (here they only publish counts and flags).
+void step_local_group(wb_embedder** hs, int world, double learningRate, wb_step_stats* out) {
+    std::vector<cudaStream_t> own(world);
+    cudaStream_t s = hs[0]->stream;
+    for (int r = 0; r < world; ++r) { own[r] = hs[r]->stream; hs[r]->stream = s; }
+    try {
+        std::vector<PendingStep> slots;
+        for (int r = 0; r < world; ++r) {
+            wb_embedder* h = hs[r];
+            slots.push_back(begin_step(h, learningRate));
+            WB_CUDA(cudaMemcpyAsync(h->dyn, &slots[r].host->dyn, sizeof(wb::StepDyn), cudaMemcpyHostToDevice, s));
+            if (!h->quantValid) enqueue_frame(h);
+        }
+        const int pieces[] = {kPartBegin | kPartSearch, kPartXPairs, kPartList | kPartForce, kPartXRows, kPartMove, kPartXCoords, kPartTail};
+        for (int piece : pieces)
+            for (int r = 0; r < world; ++r) launch_parts(hs[r], piece, false);
+        for (int r = 0; r < world; ++r) {
+            wb_embedder* h = hs[r];
+            WB_CUDA(cudaMemcpyAsync(slots[r].host->sums, h->stats, sizeof(double) * h->statsTotal, cudaMemcpyDeviceToHost, s));
+            WB_CUDA(cudaEventRecord(slots[r].done, s));
+        }
+        for (int r = 0; r < world; ++r) { hs[r]->pending.push_back(slots[r]); hs[r]->nextRebuild = 1; }
+        for (int r = 0; r < world; ++r) collect_step(hs[r], out ? out + r : nullptr);
+    } catch (...) {
+        for (int r = 0; r < world; ++r) hs[r]->stream = own[r];
+        throw;
+    }
+    for (int r = 0; r < world; ++r) hs[r]->stream = own[r];
 }
 
 // The pair buffer was too small for a build (StepCtrl::overflow): every kernel of that step and of all later ones returned at once, so
@@ -1208,6 +1255,14 @@ int wb_step(wb_embedder* h, double learning_rate, wb_step_stats* stats) {
     return guarded(h, [&] { enqueue_step(h, learning_rate); collect_step(h, stats); });
 }
 
+int wb_step_group(wb_embedder** hs, int32_t world, double learning_rate, wb_step_stats* stats) {
+    if (!hs || world < 2 || world > wb::kMaxRanks) return fail(WB_ERR_INVALID, "wb_step_group: 2 <= world <= 8");
+    for (int r = 0; r < world; ++r)
+        if (!hs[r] || !hs[r]->localGroup || hs[r]->world != world || hs[r]->rank != r || !hs[r]->pending.empty())
+            return fail(WB_ERR_INVALID, "wb_step_group: the handles of one wb_comm_init_local call, in its order, nothing in flight");
+    return guarded(hs[0], [&] { step_local_group(hs, world, learning_rate, stats); });
+}
+
 int wb_synchronize(wb_embedder* h) {
     return guarded(h, [&] { WB_CUDA(cudaStreamSynchronize(h->stream)); });
 }
@@ -1281,13 +1336,13 @@ int wb_comm_init(wb_embedder* h, const char* id128, int32_t rank, int32_t world)
 }
 
 // Test hook: the sharded step with all `world` ranks as handles of THIS process on ONE device (same problem on every handle): the peers'
-// buffers are plain device pointers, no IPC, no NCCL.  The handles must then be stepped from `world` host threads at the same time (the
-// barrier kernels of the ranks wait for each other).  Lets the sharded logic be tested where only one GPU is available.
+// buffers are plain device pointers, no IPC, no NCCL.  The handles then step together through wb_step_group (one stream, the pieces
+// of the step in lockstep).  Lets the sharded logic be tested where only one GPU is available.
 int wb_comm_init_local(wb_embedder** hs, int32_t world) {
     if (!hs || world < 2 || world > wb::kMaxRanks) return fail(WB_ERR_INVALID, "wb_comm_init_local: 2 <= world <= 8");
     for (int r = 0; r < world; ++r) {
         if (!hs[r] || hs[r]->comm || hs[r]->world != 1 || !hs[r]->pending.empty()) return fail(WB_ERR_INVALID, "wb_comm_init_local: handles must be fresh");
-        if (hs[r]->n != hs[0]->n || hs[r]->V != hs[0]->V || hs[r]->opt.device != hs[0]->opt.device) return fail(WB_ERR_INVALID, "wb_comm_init_local: handles differ");
+        if (hs[r]->n != hs[0]->n || hs[r]->V != hs[0]->V || hs[r]->opt.device != hs[0]->opt.device || hs[r]->n < 2) return fail(WB_ERR_INVALID, "wb_comm_init_local: handles differ");
     }
     return guarded(hs[0], [&] {
         for (int r = 0; r < world; ++r) {
