@@ -15,8 +15,9 @@ Lines printed (one JSON object on stdout, rank 0):
   value     device-resident throughput: K asynchronous steps, CUDA events on the handle's stream
   e2e       through the blocking C ABI with host buffers: wb_set_coordinates(host) + K x wb_step (per-step
             D2H of the observables) + wb_get_coordinates(host), all inside the timed region
-  roofline  dominant kernel (repulsion walk) - algorithmic bytes / measured time vs measured HBM peak
-  cpu_baseline  oracle port (oracle/wembed_port.cpp, OpenMP) timed for one step of the same state
+  roofline  dominant kernel (repulsion search) and, per kernel, algorithmic bytes / measured time vs the measured HBM peak
+  cpu_baseline  oracle port (oracle/wembed_port.cpp, OpenMP): 3 timed steps from the same state, + parity_at_config
+  same_sample / convergence / secondary (c5) / ranks_identical (N > 1): see DESIGN.md section 6
 --impl reference times the reference's own C++ (oracle/_ref, SNN index) on a bounded sample.
 """
 from __future__ import annotations
@@ -465,7 +466,7 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": "edge_force_updates_per_s", "value": value, "unit": "directed-edge force updates/s",
         "steps_per_s_on_sample": args.steps / dt, "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.workload} (bounded sample)"},
         "cpu_baseline": {"value": value, "unit": "directed-edge force updates/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "directed-edge force updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

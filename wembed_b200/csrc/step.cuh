@@ -31,8 +31,9 @@ __global__ void k_step_begin(StepCtrl* ctrl, unsigned int* pairCounts /* this ra
 // ranks need store it straight into the consumers' memory - found pairs into the owners' inboxes (walk.cuh), a block's sums into every
 // rank's copy of the sum rows, recentred positions into every replica of x.  What is left of the collectives is a barrier:
 // k_exchange publishes "my kernels up to here are done" to every peer and waits until every peer has said the same.  The producing
-// kernels end with a system-scope fence in every thread that stored into a peer, so their data has arrived before the flag is sent
-// (without it, 8 GPUs writing 28 MB each into the fabric let flags overtake rows: measured as diverging trajectories at 8 ranks).  Mail = one buffer per rank: [flags | counts matrix | block sum rows | observation tiles | moment tiles].
+// kernels end with a system-scope fence in every thread that stored into a peer: the flag travels separately and must not be seen
+// before the data (the release half of the barrier; k_exchange fences again before it reads).
+// Mail = one buffer per rank: [flags | counts matrix | block sum rows | observation tiles | moment tiles].
 constexpr int kMailFlags = 0;                      // int[kMaxRanks]: last barrier epoch each peer has reached
 constexpr int kMailCounts = 64;                    // unsigned[kMaxRanks][kMaxRanks]: pairs produced by rank p for rank d
 constexpr int kMailData = 64 + 4 * kMaxRanks * kMaxRanks;
