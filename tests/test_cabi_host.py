@@ -128,3 +128,12 @@ def test_datagen_helper_matches_numpy_paths():
         assert (rp == rp2).all() and (col == col2).all()
     assert datagen.csr_canonical(3, np.asarray([[1, 0]], np.int32)) is None          # src > dst: not canonical
     assert datagen.csr_canonical(3, np.asarray([[0, 1], [0, 1]], np.int32)) is None  # duplicate
+
+
+def test_build_tracks_every_kernel_source():
+    """A stale library once hid a kernel fix for two GPU runs: every file the translation unit includes must be a build dependency."""
+    from wembed_b200 import build
+    csrc = os.path.join(ROOT, "wembed_b200", "csrc")
+    tracked = {os.path.basename(p) for p in build.DEPS}
+    included = set(re.findall(r'#include\s+"([a-z0-9_]+\.cuh)"', "".join(open(os.path.join(csrc, f)).read() for f in os.listdir(csrc))))
+    assert included <= tracked and "wb_api.cu" in tracked, included - tracked
