@@ -1,5 +1,5 @@
 """Diagnostics: which vertices of a local group's step differ from the single-handle step (forces after step 1)?
-usage: python scripts/local_group_probe.py [n] [d] [world]"""
+usage: python scripts/local_group_probe.py [n] [d] [world] [geometric|heavy]"""
 import os
 import sys
 
@@ -14,7 +14,13 @@ os.environ.setdefault("WB_PAIR_CAP", str(400 * n))
 from helpers import lr_exponential, make_problem  # noqa: E402
 from wembed_b200 import cabi  # noqa: E402
 
-edges, w, x0 = make_problem(n, d)
+family = sys.argv[4] if len(sys.argv) > 4 else "geometric"
+if family == "heavy":
+    from wembed_b200.datasets import degree_weights, heavy_tailed_graph, initial_coordinates
+    edges, _ = heavy_tailed_graph(n, 20, seed=3)
+    w, x0 = degree_weights(n, edges, d), initial_coordinates(n, d, seed=5)
+else:
+    edges, w, x0 = make_problem(n, d)
 rp, col = cabi.csr_from_edges(n, edges)
 
 
@@ -28,6 +34,7 @@ def fresh():
 single = fresh()
 st_ref = single.step(lr_exponential(1))
 f_ref = single.forces()
+x_ref = single.coordinates()
 single.close()
 devs = [fresh() for _ in range(world)]
 cabi.comm_init_local(devs)
@@ -47,5 +54,19 @@ if len(bad):
         dist = np.sqrt(((x0 - x0[v]) ** 2).sum(1)) * iw * iw[v]
         cand = [int(u) for u in np.nonzero(dist <= 1.0)[0] if u != v and int(u) not in nb]
         print(f"v={v} owner={v // rows} deg={rp[v + 1] - rp[v]} partners={len(cand)} partner owners={[u // rows for u in cand]} partners in bad={[u for u in cand if u in set(bad.tolist())]}")
+xs = [dv.coordinates() for dv in devs]
+deg = np.diff(rp)
+print("stats group", st["sum_displacement"], st["sum_radius_sq"], st["centroid"][:d])
+print("stats ref  ", st_ref["sum_displacement"], st_ref["sum_radius_sq"], st_ref["centroid"][:d])
+for r, xr in enumerate(xs):
+    badx = np.nonzero((xr != x_ref).any(1))[0]
+    print(f"replica {r}: {len(badx)} rows differ from the single handle; owners {sorted(set((badx // parts[0][1]).tolist()))}; first {badx[:12].tolist()}")
+xo = np.zeros_like(x_ref)
+for xr, (b, e) in zip(xs, parts):
+    xo[b:e] = xr[b:e]
+badx = np.nonzero((xo != x_ref).any(1))[0]
+print("owners' own rows that differ:", len(badx))
+for v in badx[:25]:
+    print(f"  v={v} owner={v // parts[0][1]} deg={deg[v]} w/mean={w[v] / w.mean():.1f} |x_ref|={np.linalg.norm(x_ref[v]):.4f} |x_group|={np.linalg.norm(xo[v]):.4f} |dx|={np.linalg.norm(xo[v] - x_ref[v]):.3e} force row equal={bool((f[v] == f_ref[v]).all())}")
 for dv in devs:
     dv.close()

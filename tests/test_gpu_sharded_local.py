@@ -11,11 +11,20 @@ from helpers import lr_exponential, make_problem
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("world,n,d,steps", [(2, 30_000, 4, 6), (8, 60_000, 8, 6), (5, 20_000, 3, 5), (8, 1_000_000, 8, 2)])
-def test_local_group_equals_single_handle(device_lib, monkeypatch, world, n, d, steps):
+def heavy_problem(n, d):
+    """Heavy-tailed graph: hub rows (k_hub_rows) and heavy vertices (k_repulse_heavy) take part in the sharded step."""
+    from wembed_b200.datasets import degree_weights, heavy_tailed_graph, initial_coordinates
+    edges, _ = heavy_tailed_graph(n, 20, seed=3)
+    return edges, degree_weights(n, edges, d), initial_coordinates(n, d, seed=5)
+
+
+@pytest.mark.parametrize("world,n,d,steps,family", [
+    (2, 30_000, 4, 6, "geometric"), (8, 60_000, 8, 6, "geometric"), (5, 20_000, 3, 5, "geometric"), (8, 1_000_000, 8, 2, "geometric"),
+    (8, 20_000, 8, 4, "heavy"), (8, 30_000, 16, 4, "geometric"), (7, 20_000, 2, 4, "heavy")])
+def test_local_group_equals_single_handle(device_lib, monkeypatch, world, n, d, steps, family):
     # room for the dense early steps (~200 partners per vertex for a step or two): a local group cannot grow its buffers
     monkeypatch.setenv("WB_PAIR_CAP", str((40 if n >= 500_000 else 400) * n))
-    edges, w, x0 = make_problem(n, d)
+    edges, w, x0 = make_problem(n, d) if family == "geometric" else heavy_problem(n, d)
     rp, col = device_lib.csr_from_edges(n, edges)
 
     def fresh():

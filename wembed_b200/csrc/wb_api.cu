@@ -659,7 +659,9 @@ void launch_parts(wb_embedder* h, int parts, bool assumeBuild) {
         h->launches += 1;
     }
     if (timing) WB_CUDA(cudaEventRecord(h->ev[3], s));
-    const int obsBegin = h->ownBegin / wb::kObsTile, obsEnd = div_up(h->ownEnd, wb::kObsTile);
+    // (a rank that owns no vertices - a small graph on many GPUs - has ownBegin = ownEnd = n, which need not be a tile boundary: it must
+    // not touch the last tile, which belongs to the rank before it)
+    const int obsBegin = h->ownBegin / wb::kObsTile, obsEnd = h->ownEnd > h->ownBegin ? div_up(h->ownEnd, wb::kObsTile) : obsBegin;
     if (obsEnd > obsBegin && (parts & kPartMove)) {
         h->launches += 1;
         if (sharded) {
