@@ -17,6 +17,7 @@ def test_partition_covers_every_vertex_once():
         rows = sharding.rows_per_rank(n, world, 4)
         assert rows % 1024 == 0 and rows * world >= n           # whole observation tiles and block rows per rank
         assert all(0 <= e - b <= rows for b, e in parts)
+        assert all(b == n for b, e in parts if e == b and n)    # a rank without vertices sits at the end (wb_api.cu: it launches no tiles)
         if n:
             own = sharding.owner_of(np.arange(n), n, world)
             for r, (b, e) in enumerate(parts):
@@ -30,7 +31,7 @@ def _worker(rank, world, port, out):
     try:
         uid = sharding.exchange_unique_id(lambda: bytes(range(128)), rank, world)
         lo, hi = sharding.partition(3001, world)[rank]
-        # fixed-order sum of per-rank partials, as the device does it (k_sum_ranks): gather, add in rank order
+        # fixed-order sum of per-rank partials (every rank adds the same rows in the same order, as k_reduce_rows does on the device)
         import torch
         mine = torch.tensor([float(hi - lo), float(rank + 1) * 0.1], dtype=torch.float64)
         gathered = [torch.zeros(2, dtype=torch.float64) for _ in range(world)]

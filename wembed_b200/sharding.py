@@ -1,9 +1,11 @@
 """Host-side plumbing of the vertex-sharded multi-GPU step (one process per GPU, torch.distributed for rendezvous).
 
-The data path itself (owned-range kernels, NCCL all-gathers) lives in libwembed_b200.so; this module only
- * mirrors the library's vertex partition so callers can reason about ownership, and
- * ships the NCCL unique id from rank 0 to the other ranks over whatever torch.distributed backend is up
-   (gloo on CPU in the tests, nccl on the GPU box).
+The data path itself (owned-range kernels that store into the peers' memory over CUDA IPC mappings, flag barriers) lives in
+libwembed_b200.so; this module only
+ * mirrors the library's vertex partition so callers can reason about ownership (small graphs on many GPUs leave the last ranks
+   without vertices: begin = end = n), and
+ * ships the NCCL unique id from rank 0 to the other ranks over whatever torch.distributed backend is up (gloo on CPU in the tests,
+   nccl on the GPU box); the library uses NCCL only to exchange the IPC handles and as a host-visible barrier.
 """
 from __future__ import annotations
 
